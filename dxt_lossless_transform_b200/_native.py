@@ -1,0 +1,145 @@
+"""ctypes binding of libdxt_lossless_transform_cuda.so (the C ABI in include/*.h).
+
+There is no CPU fallback: if the shared library is missing this module raises at import of the
+symbols, and every compute entry point needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libdxt_lossless_transform_cuda.so"
+
+_lib = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+# --- shared C types -------------------------------------------------------------------------------
+class DltResult(C.Structure):
+    _fields_ = [("error_code", C.c_int32)]
+
+
+MaxCompressedSizeFn = C.CFUNCTYPE(C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t))
+EstimateCompressedSizeFn = C.CFUNCTYPE(
+    C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)
+)
+
+
+class DltSizeEstimator(C.Structure):
+    _fields_ = [
+        ("context", C.c_void_p),
+        ("max_compressed_size", MaxCompressedSizeFn),
+        ("estimate_compressed_size", EstimateCompressedSizeFn),
+    ]
+
+
+class CoreSettings(C.Structure):  # Dltbc{1,2}TransformSettings of the core crates
+    _fields_ = [("split_colour_endpoints", C.c_bool), ("decorrelation_mode", C.c_uint8)]
+
+
+class CoreAutoSettings(C.Structure):
+    _fields_ = [("use_all_modes", C.c_bool)]
+
+
+class CoreBc3Settings(C.Structure):
+    _fields_ = [
+        ("split_alpha_endpoints", C.c_bool),
+        ("split_colour_endpoints", C.c_bool),
+        ("decorrelation_mode", C.c_uint8),
+    ]
+
+
+class DltcudaSettings(C.Structure):
+    _fields_ = [
+        ("format", C.c_uint8),
+        ("decorrelation_mode", C.c_uint8),
+        ("split_alpha_endpoints", C.c_bool),
+        ("split_colour_endpoints", C.c_bool),
+    ]
+
+
+# Every exported symbol: name -> (restype, argtypes).  tests/test_cabi_symbols.py checks this table
+# against include/*.h and against the built library.
+_P = C.c_void_p
+_SZ = C.c_size_t
+SIGNATURES: dict[str, tuple] = {}
+for _n in (1, 2):
+    _p = f"dltbc{_n}_"
+    SIGNATURES.update(
+        {
+            _p + "new_ManualTransformBuilder": (_P, []),
+            _p + "free_ManualTransformBuilder": (None, [_P]),
+            _p + "clone_ManualTransformBuilder": (_P, [_P]),
+            _p + "ManualTransformBuilder_SetDecorrelationMode": (None, [_P, C.c_uint8]),
+            _p + "ManualTransformBuilder_SetSplitColourEndpoints": (None, [_P, C.c_bool]),
+            _p + "ManualTransformBuilder_ResetToDefaults": (None, [_P]),
+            _p + "ManualTransformBuilder_Transform": (DltResult, [_P, _SZ, _P, _SZ, _P]),
+            _p + "ManualTransformBuilder_Untransform": (DltResult, [_P, _SZ, _P, _SZ, _P]),
+            _p + "new_AutoTransformBuilder": (_P, [C.POINTER(DltSizeEstimator)]),
+            _p + "free_AutoTransformBuilder": (None, [_P]),
+            _p + "AutoTransformBuilder_SetUseAllDecorrelationModes": (DltResult, [_P, C.c_bool]),
+            _p + "AutoTransformBuilder_Transform": (DltResult, [_P, _P, _SZ, _P, _SZ, C.POINTER(_P)]),
+            _p + "error_message": (C.c_char_p, [C.c_int32]),
+            f"dltbc{_n}core_transform": (DltResult, [_P, _SZ, _P, _SZ, CoreSettings]),
+            f"dltbc{_n}core_untransform": (DltResult, [_P, _SZ, _P, _SZ, CoreSettings]),
+            f"dltbc{_n}core_transform_auto": (
+                DltResult,
+                [_P, _SZ, _P, _SZ, C.POINTER(DltSizeEstimator), CoreAutoSettings, C.POINTER(CoreSettings)],
+            ),
+        }
+    )
+SIGNATURES.update(
+    {
+        "dltbc3core_transform": (DltResult, [_P, _SZ, _P, _SZ, CoreBc3Settings]),
+        "dltbc3core_untransform": (DltResult, [_P, _SZ, _P, _SZ, CoreBc3Settings]),
+        "dltbc3core_transform_auto": (
+            DltResult,
+            [_P, _SZ, _P, _SZ, C.POINTER(DltSizeEstimator), CoreAutoSettings, C.POINTER(CoreBc3Settings)],
+        ),
+        "dltltu_new_size_estimator": (C.POINTER(DltSizeEstimator), []),
+        "dltltu_free_size_estimator": (None, [C.POINTER(DltSizeEstimator)]),
+        "dltcuda_ManualTransformBuilder_GetSettings": (C.c_int, [_P, C.POINTER(C.c_uint8), C.POINTER(C.c_bool)]),
+        "dltcuda_device_count": (C.c_int, []),
+        "dltcuda_set_device": (None, [C.c_int]),
+        "dltcuda_last_error": (C.c_char_p, []),
+        "dltcuda_kernel_launch_count": (C.c_uint64, []),
+        "dltcuda_alloc_pinned": (_P, [_SZ]),
+        "dltcuda_free_pinned": (None, [_P]),
+        "dltcuda_transform_device": (C.c_int, [_P, _P, _SZ, DltcudaSettings, _P]),
+        "dltcuda_untransform_device": (C.c_int, [_P, _P, _SZ, DltcudaSettings, _P]),
+        "dltcuda_transform_device_range": (C.c_int, [_P, _P, _SZ, _SZ, _SZ, DltcudaSettings, _P]),
+        "dltcuda_untransform_device_range": (C.c_int, [_P, _P, _SZ, _SZ, _SZ, DltcudaSettings, _P]),
+        "dltcuda_transform_device_streams": (C.c_int, [_P, C.POINTER(_P), _SZ, DltcudaSettings, _P]),
+        "dltcuda_untransform_device_streams": (C.c_int, [C.POINTER(_P), _P, _SZ, DltcudaSettings, _P]),
+        "dltcuda_stream_count": (C.c_int, [DltcudaSettings]),
+        "dltcuda_stream_width": (C.c_int, [DltcudaSettings, C.c_int]),
+        "dltcuda_shard_first_block": (_SZ, [C.c_int, _SZ, C.c_int, C.c_int]),
+        "dltcuda_ltu_estimate_device": (C.c_int, [_P, _SZ, C.POINTER(_SZ)]),
+        "dltcuda_transform_auto_device": (
+            C.c_int,
+            [C.c_int, _P, _P, _SZ, C.c_bool, C.POINTER(DltcudaSettings), C.POINTER(_SZ)],
+        ),
+        "dltcuda_auto_candidates": (C.c_int, [C.c_int, C.c_bool, C.POINTER(DltcudaSettings)]),
+    }
+)
+
+
+def lib() -> C.CDLL:
+    """The loaded shared library (loaded once).  Raises NativeLibraryMissing if it was not built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} is missing: build it with `python -m dxt_lossless_transform_b200.build` "
+                "(there is no CPU fallback)"
+            )
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib

@@ -1,0 +1,41 @@
+// auto_search.h — transform_bcN_auto: brute-force search for the best transform settings.
+//
+// Reference: core/dxt-lossless-transform-bc1/src/transform/transform_auto.rs:200-270,
+//            core/dxt-lossless-transform-bc2/src/transform/transform_auto.rs:196-272,
+//            core/dxt-lossless-transform-bc3/src/transform/transform_auto.rs:196-293.
+// Candidates are tried in the reference's test order; the estimate of a candidate is taken over the
+// endpoint streams only (BC1: out[0,len/2); BC2: out[len/2, len/2+len/4); BC3: out[0,2N) plus
+// out[len/2, len/2+4N)); a candidate replaces the best only on a strictly smaller estimate, so the
+// first candidate in order wins ties; the output finally holds the winner's transform.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "bcn_layout.h"
+#include "host_pipeline.h"
+
+namespace dlt {
+
+constexpr int kMaxCandidates = 16;
+
+// Test orders (bc1/bc2 settings.rs:81-98, bc3 settings.rs:91-121).  Returns the candidate count.
+int candidate_order(int format, bool use_all_modes, Settings out[kMaxCandidates]);
+
+// Bc{1,2,3}TransformSettings::default() (bc1 settings.rs:35-43, bc3 settings.rs:39-48).
+Settings default_settings(int format);
+
+// The byte ranges of the transformed payload an estimate covers (1 for BC1/BC2, 2 for BC3).
+struct EstimateRange {
+    size_t offset, len;
+};
+int estimate_ranges(int format, size_t len, EstimateRange out[2]);
+
+// Device-resident search with the GPU LTU estimator.  d_in: len bytes of blocks; d_out: len bytes,
+// holds the winner's transform on return.  `sizes` (optional) receives the per-candidate estimates
+// in test order.  Synchronises `stream`.
+Status auto_ltu_device(Context* ctx, int format, const uint8_t* d_in, uint8_t* d_out, size_t len, bool use_all_modes,
+                       Settings* best, size_t* sizes, cudaStream_t stream);
+
+}  // namespace dlt

@@ -1,0 +1,565 @@
+// bcn_kernels.cu — BCn lossless transform / untransform kernels for B200 (sm_100a).
+//
+// What they compute (reference: /root/reference/src/core, all little-endian, integer only):
+//   transform   : N interleaved BCn blocks  ->  per-field streams (bcn_layout.h), colour endpoints
+//                 optionally YCoCg-R decorrelated (common/src/color_565/decorrelate.rs:101-300)
+//                 and optionally split into c0 / c1 (and a0 / a1 for BC3).
+//   untransform : the exact inverse (decorrelate.rs:148-344).
+// One kernel family covers BC1/BC2/BC3 x every settings combination; the format, the splits and
+// the YCoCg variant are template parameters, the stream table comes from bcn_layout.h.
+//
+// Shape of a tiled kernel (HBM-bound streaming permutation, 2 x len bytes of traffic):
+//   * a CTA owns a tile of 16 KiB of blocks (2048 BC1 / 1024 BC2,BC3 blocks);
+//   * transform: every thread issues 4 coalesced 128-bit `ld.global.nc.L1::no_allocate` loads up
+//     front, does the colour arithmetic on two RGB565 values packed in one 32-bit register, and
+//     scatters the fields into a shared-memory staging area that is laid out per stream; after one
+//     barrier the CTA streams each stream segment to HBM with 128-bit stores;
+//   * untransform mirrors it: 128-bit stream loads -> shared memory -> per-thread gather ->
+//     recorrelate -> one 128-bit block store per thread and vector.
+//   * stream bases need not be 16-byte aligned (in the reference layout they sit at N*k bytes, and
+//     real mip chains give odd N): the staging area of stream s is shifted by (address & 15) so
+//     shared and global addresses are congruent mod 16; the aligned interior moves as 128-bit
+//     vectors and only the (at most two) ragged edge chunks of a segment move bytewise.
+#include "bcn_kernels.h"
+
+#include <atomic>
+#include <cstdint>
+
+namespace dlt {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;  // 128-bit vectors per thread per tile
+static_assert(kThreads * kUnroll * 16 == kTileBytes, "tile geometry");
+
+std::atomic<uint64_t> g_launches{0};
+
+// ------------------------------------------------------------------------------------------------
+// Streaming global accesses
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream8(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream16(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_stream8(void* p, const uint2& v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// YCoCg-R on two RGB565 colours packed in one 32-bit register (lanes [15:0] and [31:16]).
+// Every intermediate is a 5-bit field per lane; +32 per lane before a subtraction keeps borrows
+// from crossing lanes.  Restates Color565::{de,re}correlate_ycocg_r_var{1,2,3}.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kM5 = 0x001F001Fu, kM4 = 0x000F000Fu, kM1 = 0x00010001u, kBias = 0x00200020u;
+
+template <int VAR>
+__device__ __forceinline__ uint32_t decorrelate2(uint32_t v) {
+    if constexpr (VAR == kNone) {
+        return v;
+    } else {
+        const uint32_t r = (v >> 11) & kM5, g = (v >> 6) & kM5, gl = (v >> 5) & kM1, b = v & kM5;
+        const uint32_t co = (r + kBias - b) & kM5;
+        const uint32_t t = (b + ((co >> 1) & kM4)) & kM5;
+        const uint32_t cg = (g + kBias - t) & kM5;
+        const uint32_t y = (t + ((cg >> 1) & kM4)) & kM5;
+        if constexpr (VAR == kVariant1) return (y << 11) | (co << 6) | (gl << 5) | cg;
+        if constexpr (VAR == kVariant2) return (gl << 15) | (y << 10) | (co << 5) | cg;
+        return (y << 11) | (co << 6) | (cg << 1) | gl;
+    }
+}
+
+template <int VAR>
+__device__ __forceinline__ uint32_t recorrelate2(uint32_t v) {
+    if constexpr (VAR == kNone) {
+        return v;
+    } else {
+        uint32_t y, co, cg, gl;
+        if constexpr (VAR == kVariant1) {
+            y = (v >> 11) & kM5, co = (v >> 6) & kM5, gl = (v >> 5) & kM1, cg = v & kM5;
+        } else if constexpr (VAR == kVariant2) {
+            gl = (v >> 15) & kM1, y = (v >> 10) & kM5, co = (v >> 5) & kM5, cg = v & kM5;
+        } else {
+            y = (v >> 11) & kM5, co = (v >> 6) & kM5, cg = (v >> 1) & kM5, gl = v & kM1;
+        }
+        const uint32_t t = (y + kBias - ((cg >> 1) & kM4)) & kM5;
+        const uint32_t g = (cg + t) & kM5;
+        const uint32_t b = (t + kBias - ((co >> 1) & kM4)) & kM5;
+        const uint32_t r = (b + co) & kM5;
+        return (r << 11) | (g << 6) | (gl << 5) | b;
+    }
+}
+
+// Runtime-variant forms for the byte-granular kernel (same arithmetic, one colour in the low lane).
+__device__ __forceinline__ uint32_t decorrelate_rt(uint32_t v, int var) {
+    switch (var) {
+        case kVariant1: return decorrelate2<kVariant1>(v);
+        case kVariant2: return decorrelate2<kVariant2>(v);
+        case kVariant3: return decorrelate2<kVariant3>(v);
+        default: return v;
+    }
+}
+__device__ __forceinline__ uint32_t recorrelate_rt(uint32_t v, int var) {
+    switch (var) {
+        case kVariant1: return recorrelate2<kVariant1>(v);
+        case kVariant2: return recorrelate2<kVariant2>(v);
+        case kVariant3: return recorrelate2<kVariant3>(v);
+        default: return v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compile-time view of one (format, split_alpha, split_colour) layout.
+// ------------------------------------------------------------------------------------------------
+template <int FMT, bool SA, bool SC>
+struct Lay {
+    static constexpr int NS = num_streams(FMT, SA, SC);
+    static constexpr int BPB = block_bytes(FMT);
+    static constexpr int T = kTileBytes / BPB;    // blocks per tile
+    static constexpr int BPV = 16 / BPB;          // blocks per 128-bit vector
+    DLT_HD static constexpr int w(int s) { return stream_width(FMT, SA, SC, s); }
+    // Staging region of stream s: w*T payload bytes + 16 bytes of slack for the alignment shift.
+    DLT_HD static constexpr int region(int s) { return T * stream_prefix(FMT, SA, SC, s) + 16 * s; }
+    static constexpr int kStageBytes = kTileBytes + 16 * NS;
+    // 128-bit chunks per stream segment of a full tile (+1 when the segment is shifted).
+    DLT_HD static constexpr int iters(int s) { return (w(s) * T / 16 + 1 + kThreads - 1) / kThreads; }
+    DLT_HD static constexpr int total_iters() {
+        int a = 0;
+        for (int s = 0; s < NS; s++) a += iters(s);
+        return a;
+    }
+    DLT_HD static constexpr int iter_base(int s) {
+        int a = 0;
+        for (int i = 0; i < s; i++) a += iters(i);
+        return a;
+    }
+    // Stream indices of the logical fields.
+    static constexpr int sAlpha = 0;                          // BC2 alpha:8 / BC3 a0a1:2 or a0:1
+    static constexpr int sA1 = 1;                             // BC3 split alpha only
+    static constexpr int sAIdx = SA ? 2 : 1;                  // BC3 only
+    static constexpr int sCol = FMT == 1 ? 0 : FMT == 2 ? 1 : sAIdx + 1;  // c0c1:4 or c0:2
+    static constexpr int sC1 = sCol + 1;                      // split colour only
+    static constexpr int sIdx = NS - 1;
+};
+
+template <typename T>
+__device__ __forceinline__ void sts(uint8_t* p, T v) {
+    *reinterpret_cast<T*>(p) = v;
+}
+template <typename T>
+__device__ __forceinline__ T lds(const uint8_t* p) {
+    return *reinterpret_cast<const T*>(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tiled transform kernel
+// ------------------------------------------------------------------------------------------------
+template <int FMT, bool SA, bool SC, int VAR>
+__global__ void __launch_bounds__(kThreads, 4)
+    transform_tiled(const uint8_t* __restrict__ in, const StreamPtrs out, const uint64_t nblocks) {
+    using L = Lay<FMT, SA, SC>;
+    __shared__ __align__(16) uint8_t stage[L::kStageBytes];
+
+    const int tid = threadIdx.x;
+    const uint64_t tile_first = (uint64_t)blockIdx.x * L::T;
+    const uint64_t left = nblocks - tile_first;
+    const int nb = left < (uint64_t)L::T ? (int)left : L::T;
+
+    // (address & 15) of each stream segment; w*T is a multiple of 16 so it is tile-independent.
+    int sh[L::NS];
+#pragma unroll
+    for (int s = 0; s < L::NS; s++) sh[s] = (int)(reinterpret_cast<uintptr_t>(out.p[s]) & 15);
+
+    // ---- phase 1: 4 coalesced 128-bit loads in flight per thread
+    const uint8_t* tin = in + tile_first * L::BPB;
+    uint4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+        const int j = u * kThreads + tid;
+        const int b0 = j * L::BPV;
+        if (b0 + L::BPV <= nb) {
+            v[u] = ldg_stream16(tin + (size_t)j * 16);
+        } else if (L::BPV == 2 && b0 < nb) {
+            const uint2 h = ldg_stream8(tin + (size_t)j * 16);
+            v[u] = make_uint4(h.x, h.y, 0u, 0u);
+        } else {
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+
+    // ---- phase 2: colour arithmetic + scatter into the per-stream staging area
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+        const int j = u * kThreads + tid;
+        const int b0 = j * L::BPV;
+        if (b0 >= nb) continue;
+        if constexpr (FMT == 1) {
+            const bool two = b0 + 1 < nb;
+            const uint32_t ca = decorrelate2<VAR>(v[u].x), cb = decorrelate2<VAR>(v[u].z);
+            uint8_t* pi = stage + L::region(L::sIdx) + sh[L::sIdx] + 4 * b0;
+            sts<uint32_t>(pi, v[u].y);
+            if (two) sts<uint32_t>(pi + 4, v[u].w);
+            if constexpr (SC) {
+                uint8_t* p0 = stage + L::region(L::sCol) + sh[L::sCol] + 2 * b0;
+                uint8_t* p1 = stage + L::region(L::sC1) + sh[L::sC1] + 2 * b0;
+                sts<uint16_t>(p0, (uint16_t)ca);
+                sts<uint16_t>(p1, (uint16_t)(ca >> 16));
+                if (two) {
+                    sts<uint16_t>(p0 + 2, (uint16_t)cb);
+                    sts<uint16_t>(p1 + 2, (uint16_t)(cb >> 16));
+                }
+            } else {
+                uint8_t* pc = stage + L::region(L::sCol) + sh[L::sCol] + 4 * b0;
+                sts<uint32_t>(pc, ca);
+                if (two) sts<uint32_t>(pc + 4, cb);
+            }
+        } else {
+            // BC2 / BC3: one block per vector: [x y] = alpha part, z = colours, w = indices
+            if constexpr (FMT == 2) {
+                sts<uint2>(stage + L::region(L::sAlpha) + sh[L::sAlpha] + 8 * b0, make_uint2(v[u].x, v[u].y));
+            } else {
+                if constexpr (SA) {
+                    stage[L::region(L::sAlpha) + sh[L::sAlpha] + b0] = (uint8_t)v[u].x;
+                    stage[L::region(L::sA1) + sh[L::sA1] + b0] = (uint8_t)(v[u].x >> 8);
+                } else {
+                    sts<uint16_t>(stage + L::region(L::sAlpha) + sh[L::sAlpha] + 2 * b0, (uint16_t)v[u].x);
+                }
+                uint8_t* pa = stage + L::region(L::sAIdx) + sh[L::sAIdx] + 6 * b0;
+                sts<uint16_t>(pa, (uint16_t)(v[u].x >> 16));
+                sts<uint16_t>(pa + 2, (uint16_t)v[u].y);
+                sts<uint16_t>(pa + 4, (uint16_t)(v[u].y >> 16));
+            }
+            const uint32_t c = decorrelate2<VAR>(v[u].z);
+            if constexpr (SC) {
+                sts<uint16_t>(stage + L::region(L::sCol) + sh[L::sCol] + 2 * b0, (uint16_t)c);
+                sts<uint16_t>(stage + L::region(L::sC1) + sh[L::sC1] + 2 * b0, (uint16_t)(c >> 16));
+            } else {
+                sts<uint32_t>(stage + L::region(L::sCol) + sh[L::sCol] + 4 * b0, c);
+            }
+            sts<uint32_t>(stage + L::region(L::sIdx) + sh[L::sIdx] + 4 * b0, v[u].w);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: stream every segment out; interior as 128-bit vectors, ragged edges bytewise
+#pragma unroll
+    for (int s = 0; s < L::NS; s++) {
+        const int w = L::w(s);
+        const int lo_valid = sh[s], hi_valid = sh[s] + w * nb;
+        uint8_t* gal = out.p[s] + (uint64_t)w * tile_first - sh[s];  // 16-byte aligned
+        const uint8_t* reg = stage + L::region(s);
+        const int nch = (hi_valid + 15) >> 4;
+#pragma unroll
+        for (int it = 0; it < L::iters(s); it++) {
+            const int k = it * kThreads + tid;
+            if (k < nch) {
+                const int lo = k << 4;
+                if (lo >= lo_valid && lo + 16 <= hi_valid) {
+                    stg_stream16(gal + lo, lds<uint4>(reg + lo));
+                } else {
+                    const int a = lo > lo_valid ? lo : lo_valid;
+                    const int b = lo + 16 < hi_valid ? lo + 16 : hi_valid;
+                    for (int i = a; i < b; i++) gal[i] = reg[i];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tiled untransform kernel
+// ------------------------------------------------------------------------------------------------
+template <int FMT, bool SA, bool SC, int VAR>
+__global__ void __launch_bounds__(kThreads, 4)
+    untransform_tiled(const StreamPtrs in, uint8_t* __restrict__ out, const uint64_t nblocks) {
+    using L = Lay<FMT, SA, SC>;
+    __shared__ __align__(16) uint8_t stage[L::kStageBytes];
+
+    const int tid = threadIdx.x;
+    const uint64_t tile_first = (uint64_t)blockIdx.x * L::T;
+    const uint64_t left = nblocks - tile_first;
+    const int nb = left < (uint64_t)L::T ? (int)left : L::T;
+
+    int sh[L::NS];
+#pragma unroll
+    for (int s = 0; s < L::NS; s++) sh[s] = (int)(reinterpret_cast<uintptr_t>(in.p[s]) & 15);
+
+    // ---- phase 1: all 128-bit stream loads of the tile are issued before the first shared store
+    uint4 tmp[L::total_iters()];
+#pragma unroll
+    for (int s = 0; s < L::NS; s++) {
+        const int w = L::w(s);
+        const int lo_valid = sh[s], hi_valid = sh[s] + w * nb;
+        const uint8_t* gal = in.p[s] + (uint64_t)w * tile_first - sh[s];
+        const int nch = (hi_valid + 15) >> 4;
+#pragma unroll
+        for (int it = 0; it < L::iters(s); it++) {
+            const int k = it * kThreads + tid;
+            const int lo = k << 4;
+            if (k < nch && lo >= lo_valid && lo + 16 <= hi_valid) tmp[L::iter_base(s) + it] = ldg_stream16(gal + lo);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < L::NS; s++) {
+        const int w = L::w(s);
+        const int lo_valid = sh[s], hi_valid = sh[s] + w * nb;
+        const uint8_t* gal = in.p[s] + (uint64_t)w * tile_first - sh[s];
+        uint8_t* reg = stage + L::region(s);
+        const int nch = (hi_valid + 15) >> 4;
+#pragma unroll
+        for (int it = 0; it < L::iters(s); it++) {
+            const int k = it * kThreads + tid;
+            if (k < nch) {
+                const int lo = k << 4;
+                if (lo >= lo_valid && lo + 16 <= hi_valid) {
+                    sts<uint4>(reg + lo, tmp[L::iter_base(s) + it]);
+                } else {
+                    const int a = lo > lo_valid ? lo : lo_valid;
+                    const int b = lo + 16 < hi_valid ? lo + 16 : hi_valid;
+                    for (int i = a; i < b; i++) reg[i] = gal[i];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: gather the fields of each block, recorrelate, one 128-bit block store per vector
+    uint8_t* tout = out + tile_first * L::BPB;
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+        const int j = u * kThreads + tid;
+        const int b0 = j * L::BPV;
+        if (b0 >= nb) continue;
+        uint4 r;
+        if constexpr (FMT == 1) {
+            const bool two = b0 + 1 < nb;
+            const uint8_t* pi = stage + L::region(L::sIdx) + sh[L::sIdx] + 4 * b0;
+            uint32_t ca, cb = 0;
+            r.y = lds<uint32_t>(pi);
+            r.w = two ? lds<uint32_t>(pi + 4) : 0u;
+            if constexpr (SC) {
+                const uint8_t* p0 = stage + L::region(L::sCol) + sh[L::sCol] + 2 * b0;
+                const uint8_t* p1 = stage + L::region(L::sC1) + sh[L::sC1] + 2 * b0;
+                ca = (uint32_t)lds<uint16_t>(p0) | ((uint32_t)lds<uint16_t>(p1) << 16);
+                if (two) cb = (uint32_t)lds<uint16_t>(p0 + 2) | ((uint32_t)lds<uint16_t>(p1 + 2) << 16);
+            } else {
+                const uint8_t* pc = stage + L::region(L::sCol) + sh[L::sCol] + 4 * b0;
+                ca = lds<uint32_t>(pc);
+                if (two) cb = lds<uint32_t>(pc + 4);
+            }
+            r.x = recorrelate2<VAR>(ca);
+            r.z = recorrelate2<VAR>(cb);
+            if (two) stg_stream16(tout + (size_t)j * 16, r);
+            else stg_stream8(tout + (size_t)j * 16, make_uint2(r.x, r.y));
+        } else {
+            if constexpr (FMT == 2) {
+                const uint2 a = lds<uint2>(stage + L::region(L::sAlpha) + sh[L::sAlpha] + 8 * b0);
+                r.x = a.x;
+                r.y = a.y;
+            } else {
+                uint32_t a01;
+                if constexpr (SA) {
+                    a01 = (uint32_t)stage[L::region(L::sAlpha) + sh[L::sAlpha] + b0] |
+                          ((uint32_t)stage[L::region(L::sA1) + sh[L::sA1] + b0] << 8);
+                } else {
+                    a01 = lds<uint16_t>(stage + L::region(L::sAlpha) + sh[L::sAlpha] + 2 * b0);
+                }
+                const uint8_t* pa = stage + L::region(L::sAIdx) + sh[L::sAIdx] + 6 * b0;
+                r.x = a01 | ((uint32_t)lds<uint16_t>(pa) << 16);
+                r.y = (uint32_t)lds<uint16_t>(pa + 2) | ((uint32_t)lds<uint16_t>(pa + 4) << 16);
+            }
+            uint32_t c;
+            if constexpr (SC) {
+                c = (uint32_t)lds<uint16_t>(stage + L::region(L::sCol) + sh[L::sCol] + 2 * b0) |
+                    ((uint32_t)lds<uint16_t>(stage + L::region(L::sC1) + sh[L::sC1] + 2 * b0) << 16);
+            } else {
+                c = lds<uint32_t>(stage + L::region(L::sCol) + sh[L::sCol] + 4 * b0);
+            }
+            r.z = recorrelate2<VAR>(c);
+            r.w = lds<uint32_t>(stage + L::region(L::sIdx) + sh[L::sIdx] + 4 * b0);
+            stg_stream16(tout + (size_t)j * 16, r);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Byte-granular kernel: one thread per block, no alignment assumptions at all.  Only taken when a
+// caller hands in pointers the tiled kernels cannot address (the reference accepts any alignment).
+// ------------------------------------------------------------------------------------------------
+struct RtLayout {
+    int fmt, var, ns;
+    int w[kMaxStreams];
+    int s_alpha, s_a1, s_aidx, s_col, s_c1, s_idx;
+    bool sa, sc;
+};
+
+__global__ void __launch_bounds__(kThreads)
+    bytewise_kernel(const RtLayout L, const bool inverse, const uint8_t* blocks_in, uint8_t* blocks_out,
+                    const StreamPtrs streams, const uint64_t nblocks) {
+    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= nblocks) return;
+    const int bpb = L.fmt == 1 ? 8 : 16;
+    const int coff = L.fmt == 1 ? 0 : 8;  // colour part offset inside the block
+    uint8_t blk[16];
+    if (!inverse) {
+        for (int k = 0; k < bpb; k++) blk[k] = blocks_in[i * bpb + k];
+        if (L.fmt == 2) {
+            for (int k = 0; k < 8; k++) streams.p[L.s_alpha][i * 8 + k] = blk[k];
+        } else if (L.fmt == 3) {
+            if (L.sa) {
+                streams.p[L.s_alpha][i] = blk[0];
+                streams.p[L.s_a1][i] = blk[1];
+            } else {
+                streams.p[L.s_alpha][i * 2] = blk[0];
+                streams.p[L.s_alpha][i * 2 + 1] = blk[1];
+            }
+            for (int k = 0; k < 6; k++) streams.p[L.s_aidx][i * 6 + k] = blk[2 + k];
+        }
+        uint32_t c = (uint32_t)blk[coff] | ((uint32_t)blk[coff + 1] << 8) | ((uint32_t)blk[coff + 2] << 16) |
+                     ((uint32_t)blk[coff + 3] << 24);
+        c = decorrelate_rt(c, L.var);
+        uint8_t* p0 = L.sc ? streams.p[L.s_col] + i * 2 : streams.p[L.s_col] + i * 4;
+        uint8_t* p1 = L.sc ? streams.p[L.s_c1] + i * 2 : p0 + 2;
+        p0[0] = (uint8_t)c;
+        p0[1] = (uint8_t)(c >> 8);
+        p1[0] = (uint8_t)(c >> 16);
+        p1[1] = (uint8_t)(c >> 24);
+        for (int k = 0; k < 4; k++) streams.p[L.s_idx][i * 4 + k] = blk[coff + 4 + k];
+    } else {
+        if (L.fmt == 2) {
+            for (int k = 0; k < 8; k++) blk[k] = streams.p[L.s_alpha][i * 8 + k];
+        } else if (L.fmt == 3) {
+            if (L.sa) {
+                blk[0] = streams.p[L.s_alpha][i];
+                blk[1] = streams.p[L.s_a1][i];
+            } else {
+                blk[0] = streams.p[L.s_alpha][i * 2];
+                blk[1] = streams.p[L.s_alpha][i * 2 + 1];
+            }
+            for (int k = 0; k < 6; k++) blk[2 + k] = streams.p[L.s_aidx][i * 6 + k];
+        }
+        const uint8_t* p0 = L.sc ? streams.p[L.s_col] + i * 2 : streams.p[L.s_col] + i * 4;
+        const uint8_t* p1 = L.sc ? streams.p[L.s_c1] + i * 2 : p0 + 2;
+        uint32_t c = (uint32_t)p0[0] | ((uint32_t)p0[1] << 8) | ((uint32_t)p1[0] << 16) | ((uint32_t)p1[1] << 24);
+        c = recorrelate_rt(c, L.var);
+        blk[coff] = (uint8_t)c;
+        blk[coff + 1] = (uint8_t)(c >> 8);
+        blk[coff + 2] = (uint8_t)(c >> 16);
+        blk[coff + 3] = (uint8_t)(c >> 24);
+        for (int k = 0; k < 4; k++) blk[coff + 4 + k] = streams.p[L.s_idx][i * 4 + k];
+        for (int k = 0; k < bpb; k++) blocks_out[i * bpb + k] = blk[k];
+    }
+}
+
+template <int FMT, bool SA, bool SC>
+RtLayout make_rt_layout(int var) {
+    using L = Lay<FMT, SA, SC>;
+    RtLayout r{};
+    r.fmt = FMT;
+    r.var = var;
+    r.ns = L::NS;
+    for (int s = 0; s < L::NS; s++) r.w[s] = L::w(s);
+    r.s_alpha = L::sAlpha;
+    r.s_a1 = L::sA1;
+    r.s_aidx = L::sAIdx;
+    r.s_col = L::sCol;
+    r.s_c1 = L::sC1;
+    r.s_idx = L::sIdx;
+    r.sa = SA;
+    r.sc = SC;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host dispatch
+// ------------------------------------------------------------------------------------------------
+template <int FMT, bool SA, bool SC>
+bool tiled_ok(const void* blocks, const StreamPtrs& sp) {
+    using L = Lay<FMT, SA, SC>;
+    if (reinterpret_cast<uintptr_t>(blocks) & 15) return false;
+    for (int s = 0; s < L::NS; s++)
+        if (reinterpret_cast<uintptr_t>(sp.p[s]) & (uintptr_t)(stream_align(L::w(s)) - 1)) return false;
+    return true;
+}
+
+template <int FMT, bool SA, bool SC, int VAR>
+cudaError_t run(bool inverse, const uint8_t* blocks_in, uint8_t* blocks_out, const StreamPtrs& sp, uint64_t n,
+                cudaStream_t stream) {
+    using L = Lay<FMT, SA, SC>;
+    if (n == 0) return cudaSuccess;
+    const void* blocks = inverse ? (const void*)blocks_out : (const void*)blocks_in;
+    if (tiled_ok<FMT, SA, SC>(blocks, sp)) {
+        const uint64_t tiles = (n + L::T - 1) / L::T;
+        if (tiles > 0x7fffffffull) return cudaErrorInvalidValue;
+        if (!inverse) transform_tiled<FMT, SA, SC, VAR><<<(unsigned)tiles, kThreads, 0, stream>>>(blocks_in, sp, n);
+        else untransform_tiled<FMT, SA, SC, VAR><<<(unsigned)tiles, kThreads, 0, stream>>>(sp, blocks_out, n);
+    } else {
+        const uint64_t ctas = (n + kThreads - 1) / kThreads;
+        if (ctas > 0x7fffffffull) return cudaErrorInvalidValue;
+        bytewise_kernel<<<(unsigned)ctas, kThreads, 0, stream>>>(make_rt_layout<FMT, SA, SC>(VAR), inverse, blocks_in,
+                                                                 blocks_out, sp, n);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+template <int FMT, bool SA, bool SC>
+cudaError_t run_var(int var, bool inverse, const uint8_t* bi, uint8_t* bo, const StreamPtrs& sp, uint64_t n,
+                    cudaStream_t stream) {
+    switch (var) {
+        case kNone: return run<FMT, SA, SC, kNone>(inverse, bi, bo, sp, n, stream);
+        case kVariant1: return run<FMT, SA, SC, kVariant1>(inverse, bi, bo, sp, n, stream);
+        case kVariant2: return run<FMT, SA, SC, kVariant2>(inverse, bi, bo, sp, n, stream);
+        case kVariant3: return run<FMT, SA, SC, kVariant3>(inverse, bi, bo, sp, n, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t dispatch(const Settings& st, bool inverse, const uint8_t* bi, uint8_t* bo, const StreamPtrs& sp,
+                     uint64_t n, cudaStream_t stream) {
+    const bool sc = st.split_colour, sa = st.split_alpha;
+    switch (st.format) {
+        case 1:
+            return sc ? run_var<1, false, true>(st.variant, inverse, bi, bo, sp, n, stream)
+                      : run_var<1, false, false>(st.variant, inverse, bi, bo, sp, n, stream);
+        case 2:
+            return sc ? run_var<2, false, true>(st.variant, inverse, bi, bo, sp, n, stream)
+                      : run_var<2, false, false>(st.variant, inverse, bi, bo, sp, n, stream);
+        case 3:
+            if (sa) {
+                return sc ? run_var<3, true, true>(st.variant, inverse, bi, bo, sp, n, stream)
+                          : run_var<3, true, false>(st.variant, inverse, bi, bo, sp, n, stream);
+            }
+            return sc ? run_var<3, false, true>(st.variant, inverse, bi, bo, sp, n, stream)
+                      : run_var<3, false, false>(st.variant, inverse, bi, bo, sp, n, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_transform(const Settings& st, const uint8_t* in, const StreamPtrs& out, uint64_t nblocks,
+                             cudaStream_t stream) {
+    return dispatch(st, false, in, nullptr, out, nblocks, stream);
+}
+
+cudaError_t launch_untransform(const Settings& st, const StreamPtrs& in, uint8_t* out, uint64_t nblocks,
+                               cudaStream_t stream) {
+    return dispatch(st, true, nullptr, out, in, nblocks, stream);
+}
+
+uint64_t kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+}  // namespace dlt

@@ -1,0 +1,28 @@
+// bcn_kernels.h — host-side launch API of the BCn transform / untransform kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "bcn_layout.h"
+
+namespace dlt {
+
+// Transform `nblocks` BCn blocks starting at `in` (device pointer) into the per-stream device
+// pointers `out` (each already advanced to this range's first block).  Any pointer alignment is
+// accepted; 16-byte aligned `in` and naturally aligned streams take the tiled kernels, anything
+// else the byte-granular kernel.  Asynchronous on `stream`.
+cudaError_t launch_transform(const Settings& st, const uint8_t* in, const StreamPtrs& out, uint64_t nblocks,
+                             cudaStream_t stream);
+
+// Exact inverse: gathers the streams back into `nblocks` blocks at `out`.
+cudaError_t launch_untransform(const Settings& st, const StreamPtrs& in, uint8_t* out, uint64_t nblocks,
+                               cudaStream_t stream);
+
+// Number of kernel launches the two functions above have issued in this process (bench evidence).
+uint64_t kernel_launch_count();
+
+// Blocks per CTA tile of the tiled kernels (shard boundaries that are multiples of this keep every
+// per-stream slice 16-byte aligned when the stream base is).
+constexpr int kTileBytes = 16384;
+inline constexpr int tile_blocks(int fmt) { return kTileBytes / block_bytes(fmt); }
+
+}  // namespace dlt

@@ -1,0 +1,704 @@
+// cabi.cu — the C ABI of libdxt_lossless_transform_cuda.so.
+//
+// Three groups of symbols (declared in include/*.h, each with the reference file:line it replaces):
+//   1. the reference's cbindgen surface, same names / structs / enum values / check order:
+//        dltbc1_* , dltbc2_*          (api/dxt-lossless-transform-bc{1,2}-api/src/c_api/**)
+//        dltbc1core_*, dltbc2core_*   (core/dxt-lossless-transform-bc{1,2}/src/c_api/**)
+//        dltltu_*                     (extensions/estimators/dxt-lossless-transform-ltu/src/c_api.rs)
+//   2. dltbc3core_*: BC3 has no C ABI in the reference (only Rust functions); these mirror the core
+//      style for BC3 and are an additive extension.
+//   3. dltcuda_*: additive device-resident / sharding / pinned-memory entry points.
+// Nothing in here falls back to the CPU: without a usable CUDA device the calls return an error.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "auto_search.h"
+#include "bcn_kernels.h"
+#include "bcn_layout.h"
+#include "estimator.h"
+#include "host_pipeline.h"
+
+using namespace dlt;
+
+#define DLT_EXPORT extern "C" __attribute__((visibility("default")))
+
+// =================================================================================================
+// Shared types
+// =================================================================================================
+extern "C" {
+
+// api-common/src/c_api/size_estimation.rs:17-52
+typedef uint32_t (*DltMaxCompressedSizeFn)(void* context, size_t len_bytes, size_t* out_size);
+typedef uint32_t (*DltEstimateCompressedSizeFn)(void* context, const uint8_t* input_ptr, size_t len_bytes,
+                                                uint8_t* output_ptr, size_t output_len, size_t* out_size);
+struct DltSizeEstimator {
+    void* context;
+    DltMaxCompressedSizeFn max_compressed_size;
+    DltEstimateCompressedSizeFn estimate_compressed_size;
+};
+
+struct DltResult {  // Dltbc{1,2}Result in both crates: one repr(C) enum field
+    int32_t error_code;
+};
+
+// core crates: { bool split_colour_endpoints; YCoCgVariant(u8, internal numbering) }
+struct DltCoreSettings {
+    bool split_colour_endpoints;
+    uint8_t decorrelation_mode;
+};
+struct DltCoreAutoSettings {
+    bool use_all_modes;
+};
+// additive BC3 settings (core style)
+struct DltCoreBc3Settings {
+    bool split_alpha_endpoints;
+    bool split_colour_endpoints;
+    uint8_t decorrelation_mode;
+};
+// additive device API
+struct DltcudaSettings {
+    uint8_t format;              // 1, 2, 3
+    uint8_t decorrelation_mode;  // internal numbering: None=0, Variant1=1, Variant2=2, Variant3=3
+    bool split_alpha_endpoints;  // BC3 only
+    bool split_colour_endpoints;
+};
+
+}  // extern "C"
+
+namespace {
+
+// Stable API codes — api/dxt-lossless-transform-bc1-api/src/c_api/error.rs:12-39
+enum ApiCode : int32_t {
+    kApiSuccess = 0,
+    kApiInvalidLength = 1,
+    kApiOutputBufferTooSmall = 2,
+    kApiAllocationFailed = 3,
+    kApiSizeEstimationFailed = 4,
+    kApiNullDataPointer = 5,
+    kApiNullEstimatorPointer = 6,
+    kApiNullTransformSettingsPointer = 7,
+    kApiNullInputPointer = 8,
+    kApiNullOutputBufferPointer = 9,
+    kApiNullManualTransformBuilderPointer = 10,
+    kApiNullBuilderPointer = 11,
+    kApiNullManualBuilderOutputPointer = 12,
+};
+
+// Core codes — core/dxt-lossless-transform-bc1/src/c_api/transform_auto.rs:37-58
+enum CoreCode : int32_t {
+    kCoreSuccess = 0,
+    kCoreNullDataPointer = 1,
+    kCoreNullOutputBufferPointer = 2,
+    kCoreNullEstimatorPointer = 3,
+    kCoreNullTransformSettingsPointer = 4,
+    kCoreInvalidDataLength = 5,
+    kCoreOutputBufferTooSmall = 6,
+    kCoreSizeEstimationError = 7,
+    kCoreTransformationError = 8,
+};
+
+// Stable YCoCgVariant numbering (api-common/src/reexports/color_565.rs:65-85):
+// Variant1=0, Variant2=1, Variant3=2, None=3  <->  internal None=0, Variant1..3=1..3.
+inline int stable_to_internal(uint8_t v) { return v == 3 ? kNone : v + 1; }
+inline uint8_t internal_to_stable(int v) { return v == kNone ? 3 : (uint8_t)(v - 1); }
+
+// What a builder holds: Bc{1,2}ManualTransformBuilder { settings } (manual_transform_builder.rs).
+struct ManualBuilder {
+    int format;
+    int variant;  // internal numbering
+    bool split_colour;
+};
+struct AutoBuilder {
+    int format;
+    DltSizeEstimator estimator;  // a COPY, as in auto_transform_builder.rs:35-38
+    bool use_all;
+};
+
+enum class Outcome { kOk, kInvalidLength, kTooSmall, kDevice, kOutOfMemory, kEstimator, kHostAlloc };
+
+Outcome validate(size_t in_len, size_t out_len, int format) {
+    // safe/transform_with_settings.rs:88-105: length check first, then the output size.
+    if (in_len % (size_t)block_bytes(format) != 0) return Outcome::kInvalidLength;
+    if (out_len < in_len) return Outcome::kTooSmall;
+    return Outcome::kOk;
+}
+
+Outcome from_status(Status s) {
+    return s == Status::kOk ? Outcome::kOk : s == Status::kOutOfMemory ? Outcome::kOutOfMemory : Outcome::kDevice;
+}
+
+Outcome transform_host(const Settings& st, bool inverse, const uint8_t* in, size_t in_len, uint8_t* out,
+                       size_t out_len) {
+    Outcome v = validate(in_len, out_len, st.format);
+    if (v != Outcome::kOk) return v;
+    if (st.variant < kNone || st.variant > kVariant3) return Outcome::kDevice;
+    return from_status(run_host(st, inverse, in, out, in_len, -1));
+}
+
+int32_t api_code(Outcome o) {
+    switch (o) {
+        case Outcome::kOk: return kApiSuccess;
+        case Outcome::kInvalidLength: return kApiInvalidLength;
+        case Outcome::kTooSmall: return kApiOutputBufferTooSmall;
+        case Outcome::kEstimator: return kApiSizeEstimationFailed;
+        // The stable enum has no generic failure code; a CUDA failure reports as AllocationFailed.
+        default: return kApiAllocationFailed;
+    }
+}
+int32_t core_code(Outcome o) {
+    switch (o) {
+        case Outcome::kOk: return kCoreSuccess;
+        case Outcome::kInvalidLength: return kCoreInvalidDataLength;
+        case Outcome::kTooSmall: return kCoreOutputBufferTooSmall;
+        case Outcome::kEstimator: return kCoreSizeEstimationError;
+        default: return kCoreTransformationError;
+    }
+}
+
+// ---- the LTU estimator callbacks (host pointers in, GPU estimator underneath) -------------------
+uint32_t ltu_max_compressed_size(void* context, size_t, size_t* out_size) {
+    if (!context || !out_size) return 1;  // ltu/src/c_api.rs:113-115
+    *out_size = 0;                        // lib.rs:90-94: no scratch buffer needed
+    return 0;
+}
+
+uint32_t ltu_estimate_compressed_size(void* context, const uint8_t* input, size_t len, uint8_t*, size_t,
+                                      size_t* out_size) {
+    if (!context || !out_size) return 1;  // ltu/src/c_api.rs:137-139
+    if (!input || len == 0) {             // lib.rs:103-109
+        *out_size = 0;
+        return 0;
+    }
+    Status st;
+    Context* ctx = acquire_context(-1, &st);
+    if (!ctx) return 3;
+    uint32_t rc = 3;
+    if (ensure_device_buffers(ctx, len) == Status::kOk &&
+        cudaMemcpyAsync(ctx->d_in, input, len, cudaMemcpyHostToDevice, ctx->stream[0]) == cudaSuccess) {
+        LtuSegment seg{ctx->d_in, len};
+        uint64_t m = 0;
+        if (ltu_matches_device(ctx, &seg, 1, &m, ctx->stream[0]) == Status::kOk) {
+            *out_size = ltu_estimate_from_matches(len, m);
+            rc = 0;
+        }
+    }
+    release_context(ctx);
+    return rc;
+}
+
+bool is_gpu_ltu(const DltSizeEstimator& e) { return e.estimate_compressed_size == &ltu_estimate_compressed_size; }
+
+// ---- transform_bcN_auto on host pointers -----------------------------------------------------------
+Outcome auto_host(int format, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len,
+                  const DltSizeEstimator& est, bool use_all, Settings* best) {
+    Outcome v = validate(in_len, out_len, format);
+    if (v != Outcome::kOk) return v;
+    const size_t len = in_len;
+
+    // transform_auto.rs:215-227: scratch for the estimator sized by max_compressed_size(len/2 | len/4).
+    size_t max_comp = 0;
+    if (est.max_compressed_size(est.context, format == 1 ? len / 2 : len / 4, &max_comp) != 0) return Outcome::kEstimator;
+    uint8_t* comp = nullptr;
+    if (max_comp) {
+        if (posix_memalign(reinterpret_cast<void**>(&comp), 64, max_comp) != 0) return Outcome::kHostAlloc;
+    }
+    struct FreeComp {
+        uint8_t* p;
+        ~FreeComp() { std::free(p); }
+    } free_comp{comp};
+
+    Settings order[kMaxCandidates];
+    const int k = candidate_order(format, use_all, order);
+    EstimateRange ranges[2];
+    const int nr = estimate_ranges(format, len, ranges);
+
+    if (len == 0) {
+        // The reference still walks the candidates (estimating empty slices); first minimum wins.
+        Settings best_s = default_settings(format);
+        size_t best_size = SIZE_MAX;
+        for (int i = 0; i < k; i++) {
+            size_t total = 0;
+            for (int r = 0; r < nr; r++) {
+                size_t sz = 0;
+                if (est.estimate_compressed_size(est.context, out, 0, comp, max_comp, &sz) != 0) return Outcome::kEstimator;
+                total += sz;
+            }
+            if (total < best_size) best_size = total, best_s = order[i];
+        }
+        *best = best_s;
+        return Outcome::kOk;
+    }
+
+    Status st;
+    Context* ctx = acquire_context(-1, &st);
+    if (!ctx) return from_status(st);
+    struct Releaser {
+        Context* c;
+        ~Releaser() { release_context(c); }
+    } releaser{ctx};
+    if ((st = ensure_device_buffers(ctx, len)) != Status::kOk) return from_status(st);
+    cudaStream_t s = ctx->stream[0];
+    auto cuda_fail = [](cudaError_t e) {
+        note_cuda_error(e);
+        return e == cudaErrorMemoryAllocation ? Outcome::kOutOfMemory : Outcome::kDevice;
+    };
+    cudaError_t e = cudaMemcpyAsync(ctx->d_in, in, len, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return cuda_fail(e);
+    const size_t n = len / block_bytes(format);
+
+    Settings best_s = default_settings(format);
+    if (is_gpu_ltu(est)) {
+        // Whole search on the device; one D2H of the winner.
+        if ((st = auto_ltu_device(ctx, format, ctx->d_in, ctx->d_out, len, use_all, &best_s, nullptr, s)) != Status::kOk)
+            return from_status(st);
+    } else {
+        // Caller-supplied estimator: it sees host memory, exactly as in the reference — each
+        // candidate is transformed on the GPU and only the estimated ranges travel back.
+        size_t best_size = SIZE_MAX;
+        int best_i = -1;
+        for (int i = 0; i < k; i++) {
+            e = launch_transform(order[i], ctx->d_in, reference_layout(ctx->d_out, n, 0, order[i]), n, s);
+            for (int r = 0; r < nr && e == cudaSuccess; r++)
+                e = cudaMemcpyAsync(out + ranges[r].offset, ctx->d_out + ranges[r].offset, ranges[r].len,
+                                    cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) return cuda_fail(e);
+            size_t total = 0;
+            for (int r = 0; r < nr; r++) {
+                size_t sz = 0;
+                if (est.estimate_compressed_size(est.context, out + ranges[r].offset, ranges[r].len, comp, max_comp,
+                                                 &sz) != 0)
+                    return Outcome::kEstimator;
+                total += sz;
+            }
+            if (total < best_size) best_size = total, best_s = order[i], best_i = i;
+        }
+        if (best_i != k - 1) {
+            e = launch_transform(best_s, ctx->d_in, reference_layout(ctx->d_out, n, 0, best_s), n, s);
+            if (e != cudaSuccess) return cuda_fail(e);
+        }
+    }
+    e = cudaMemcpyAsync(out, ctx->d_out, len, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return cuda_fail(e);
+    *best = best_s;
+    return Outcome::kOk;
+}
+
+// ---- stable API bodies, shared by BC1 and BC2 ----------------------------------------------------
+ManualBuilder* new_manual(int format) {
+    // Bc1ManualTransformBuilder::new() = default settings (Variant1, split) — settings.rs:35-43
+    return new (std::nothrow) ManualBuilder{format, kVariant1, true};
+}
+
+DltResult api_manual_run(int format, bool inverse, const uint8_t* input, size_t input_len, uint8_t* output,
+                         size_t output_len, ManualBuilder* b) {
+    // manual_transform_builder.rs:256-287: input, output, builder null checks in this order.
+    if (!input) return {kApiNullDataPointer};
+    if (!output) return {kApiNullOutputBufferPointer};
+    if (!b) return {kApiNullManualTransformBuilderPointer};
+    const Settings st{format, b->variant, false, b->split_colour};
+    return {api_code(transform_host(st, inverse, input, input_len, output, output_len))};
+}
+
+DltResult api_auto_run(int format, AutoBuilder* b, const uint8_t* data, size_t data_len, uint8_t* output,
+                       size_t output_len, ManualBuilder** out_manual) {
+    // auto_transform_builder.rs:190-245: builder, data, output, out_manual_builder.
+    if (!b) return {kApiNullBuilderPointer};
+    if (!data) return {kApiNullDataPointer};
+    if (!output) return {kApiNullOutputBufferPointer};
+    if (!out_manual) return {kApiNullManualBuilderOutputPointer};
+    Settings best{};
+    const Outcome o = auto_host(format, data, data_len, output, output_len, b->estimator, b->use_all, &best);
+    if (o != Outcome::kOk) {
+        *out_manual = nullptr;
+        return {api_code(o)};
+    }
+    ManualBuilder* m = new (std::nothrow) ManualBuilder{format, best.variant, best.split_colour};
+    *out_manual = m;
+    return {m ? kApiSuccess : kApiAllocationFailed};
+}
+
+const char* api_error_message(int32_t code, int format) {
+    // error.rs:131-171 (BC2: "16 (BC2 block size)", Dltbc2* type names)
+    const bool b1 = format == 1;
+    switch (code) {
+        case kApiSuccess: return "Success";
+        case kApiInvalidLength:
+            return b1 ? "Invalid input length: Length must be divisible by 8 (BC1 block size)"
+                      : "Invalid input length: Length must be divisible by 16 (BC2 block size)";
+        case kApiOutputBufferTooSmall: return "Output buffer too small for the operation";
+        case kApiAllocationFailed: return "Memory allocation failed";
+        case kApiSizeEstimationFailed: return "Size estimation failed during transform optimization";
+        case kApiNullDataPointer: return "Null pointer provided for data parameter";
+        case kApiNullEstimatorPointer: return "Null pointer provided for DltSizeEstimator parameter";
+        case kApiNullTransformSettingsPointer:
+            return b1 ? "Null pointer provided for Dltbc1TransformSettings parameter"
+                      : "Null pointer provided for Dltbc2TransformSettings parameter";
+        case kApiNullInputPointer: return "Null pointer provided for input parameter";
+        case kApiNullOutputBufferPointer: return "Null pointer provided for output parameter";
+        case kApiNullManualTransformBuilderPointer:
+            return b1 ? "Null pointer provided for Dltbc1ManualTransformBuilder parameter"
+                      : "Null pointer provided for Dltbc2ManualTransformBuilder parameter";
+        case kApiNullBuilderPointer:
+            return b1 ? "Null pointer provided for Dltbc1EstimateSettingsBuilder parameter"
+                      : "Null pointer provided for Dltbc2EstimateSettingsBuilder parameter";
+        case kApiNullManualBuilderOutputPointer: return "Null pointer provided for manual builder output parameter";
+        default: return "Unknown error";
+    }
+}
+
+// ---- core API bodies -------------------------------------------------------------------------------
+DltResult core_run(int format, bool inverse, const uint8_t* input, size_t input_len, uint8_t* output,
+                   size_t output_len, int variant, bool split_alpha, bool split_colour) {
+    // core c_api/transform_with_settings.rs:73-100
+    if (!input) return {kCoreNullDataPointer};
+    if (!output) return {kCoreNullOutputBufferPointer};
+    const Settings st{format, variant, split_alpha, split_colour};
+    return {core_code(transform_host(st, inverse, input, input_len, output, output_len))};
+}
+
+DltResult core_auto(int format, const uint8_t* data, size_t data_len, uint8_t* output, size_t output_len,
+                    const DltSizeEstimator* estimator, bool use_all, void* out_details, Settings* best) {
+    // core c_api/transform_auto.rs:143-190
+    if (!data) return {kCoreNullDataPointer};
+    if (!output) return {kCoreNullOutputBufferPointer};
+    if (!estimator) return {kCoreNullEstimatorPointer};
+    if (!out_details) return {kCoreNullTransformSettingsPointer};
+    return {core_code(auto_host(format, data, data_len, output, output_len, *estimator, use_all, best))};
+}
+
+bool to_settings(const DltcudaSettings& s, Settings* out) {
+    if (s.format < 1 || s.format > 3 || s.decorrelation_mode > 3) return false;
+    *out = Settings{s.format, s.decorrelation_mode, s.format == 3 && s.split_alpha_endpoints, s.split_colour_endpoints};
+    return true;
+}
+
+}  // namespace
+
+// =================================================================================================
+// 1a. Stable API: dltbc1_* / dltbc2_*
+// =================================================================================================
+#define DLT_DEFINE_STABLE_API(N)                                                                                      \
+    DLT_EXPORT void* dltbc##N##_new_ManualTransformBuilder(void) { return new_manual(N); }                            \
+    DLT_EXPORT void dltbc##N##_free_ManualTransformBuilder(void* b) { delete static_cast<ManualBuilder*>(b); }        \
+    DLT_EXPORT void* dltbc##N##_clone_ManualTransformBuilder(const void* b) {                                         \
+        if (!b) return nullptr;                                                                                       \
+        return new (std::nothrow) ManualBuilder(*static_cast<const ManualBuilder*>(b));                               \
+    }                                                                                                                 \
+    DLT_EXPORT void dltbc##N##_ManualTransformBuilder_SetDecorrelationMode(void* b, uint8_t mode) {                   \
+        if (!b || mode > 3) return;                                                                                   \
+        static_cast<ManualBuilder*>(b)->variant = stable_to_internal(mode);                                           \
+    }                                                                                                                 \
+    DLT_EXPORT void dltbc##N##_ManualTransformBuilder_SetSplitColourEndpoints(void* b, bool split) {                  \
+        if (!b) return;                                                                                               \
+        static_cast<ManualBuilder*>(b)->split_colour = split;                                                         \
+    }                                                                                                                 \
+    DLT_EXPORT void dltbc##N##_ManualTransformBuilder_ResetToDefaults(void* b) {                                      \
+        if (!b) return;                                                                                               \
+        *static_cast<ManualBuilder*>(b) = ManualBuilder{N, kVariant1, true};                                          \
+    }                                                                                                                 \
+    DLT_EXPORT DltResult dltbc##N##_ManualTransformBuilder_Transform(const uint8_t* input, size_t input_len,          \
+                                                                     uint8_t* output, size_t output_len, void* b) {   \
+        return api_manual_run(N, false, input, input_len, output, output_len, static_cast<ManualBuilder*>(b));        \
+    }                                                                                                                 \
+    DLT_EXPORT DltResult dltbc##N##_ManualTransformBuilder_Untransform(const uint8_t* input, size_t input_len,        \
+                                                                       uint8_t* output, size_t output_len, void* b) { \
+        return api_manual_run(N, true, input, input_len, output, output_len, static_cast<ManualBuilder*>(b));         \
+    }                                                                                                                 \
+    DLT_EXPORT void* dltbc##N##_new_AutoTransformBuilder(const DltSizeEstimator* estimator) {                         \
+        if (!estimator) return nullptr;                                                                               \
+        return new (std::nothrow) AutoBuilder{N, *estimator, false};                                                  \
+    }                                                                                                                 \
+    DLT_EXPORT void dltbc##N##_free_AutoTransformBuilder(void* b) { delete static_cast<AutoBuilder*>(b); }            \
+    DLT_EXPORT DltResult dltbc##N##_AutoTransformBuilder_SetUseAllDecorrelationModes(void* b, bool use_all) {         \
+        if (!b) return {kApiNullBuilderPointer};                                                                      \
+        static_cast<AutoBuilder*>(b)->use_all = use_all;                                                              \
+        return {kApiSuccess};                                                                                         \
+    }                                                                                                                 \
+    DLT_EXPORT DltResult dltbc##N##_AutoTransformBuilder_Transform(void* b, const uint8_t* data, size_t data_len,     \
+                                                                   uint8_t* output, size_t output_len,                \
+                                                                   void** out_manual_builder) {                       \
+        return api_auto_run(N, static_cast<AutoBuilder*>(b), data, data_len, output, output_len,                      \
+                            reinterpret_cast<ManualBuilder**>(out_manual_builder));                                   \
+    }                                                                                                                 \
+    DLT_EXPORT const char* dltbc##N##_error_message(int32_t code) { return api_error_message(code, N); }
+
+DLT_DEFINE_STABLE_API(1)
+DLT_DEFINE_STABLE_API(2)
+
+// Introspection of a manual builder (additive; the reference exposes get_settings() only to Rust,
+// manual_transform_builder.rs `get_settings`).  mode uses the STABLE numbering.
+DLT_EXPORT int dltcuda_ManualTransformBuilder_GetSettings(const void* b, uint8_t* out_mode, bool* out_split) {
+    if (!b) return 1;
+    const ManualBuilder* m = static_cast<const ManualBuilder*>(b);
+    if (out_mode) *out_mode = internal_to_stable(m->variant);
+    if (out_split) *out_split = m->split_colour;
+    return 0;
+}
+
+// =================================================================================================
+// 1b. Core API: dltbc1core_* / dltbc2core_*   (+ 2. additive dltbc3core_*)
+// =================================================================================================
+#define DLT_DEFINE_CORE_API(N)                                                                                        \
+    DLT_EXPORT DltResult dltbc##N##core_transform(const uint8_t* input, size_t input_len, uint8_t* output,            \
+                                                  size_t output_len, DltCoreSettings details) {                       \
+        return core_run(N, false, input, input_len, output, output_len, details.decorrelation_mode, false,            \
+                        details.split_colour_endpoints);                                                              \
+    }                                                                                                                 \
+    DLT_EXPORT DltResult dltbc##N##core_untransform(const uint8_t* input, size_t input_len, uint8_t* output,          \
+                                                    size_t output_len, DltCoreSettings details) {                     \
+        return core_run(N, true, input, input_len, output, output_len, details.decorrelation_mode, false,             \
+                        details.split_colour_endpoints);                                                              \
+    }                                                                                                                 \
+    DLT_EXPORT DltResult dltbc##N##core_transform_auto(const uint8_t* data, size_t data_len, uint8_t* output,         \
+                                                       size_t output_len, const DltSizeEstimator* estimator,          \
+                                                       DltCoreAutoSettings settings, DltCoreSettings* out_details) {  \
+        Settings best{};                                                                                              \
+        DltResult r = core_auto(N, data, data_len, output, output_len, estimator, settings.use_all_modes,             \
+                                out_details, &best);                                                                  \
+        if (r.error_code == kCoreSuccess) *out_details = DltCoreSettings{best.split_colour, (uint8_t)best.variant};   \
+        return r;                                                                                                     \
+    }
+
+DLT_DEFINE_CORE_API(1)
+DLT_DEFINE_CORE_API(2)
+
+DLT_EXPORT DltResult dltbc3core_transform(const uint8_t* input, size_t input_len, uint8_t* output, size_t output_len,
+                                          DltCoreBc3Settings d) {
+    return core_run(3, false, input, input_len, output, output_len, d.decorrelation_mode, d.split_alpha_endpoints,
+                    d.split_colour_endpoints);
+}
+DLT_EXPORT DltResult dltbc3core_untransform(const uint8_t* input, size_t input_len, uint8_t* output,
+                                            size_t output_len, DltCoreBc3Settings d) {
+    return core_run(3, true, input, input_len, output, output_len, d.decorrelation_mode, d.split_alpha_endpoints,
+                    d.split_colour_endpoints);
+}
+DLT_EXPORT DltResult dltbc3core_transform_auto(const uint8_t* data, size_t data_len, uint8_t* output,
+                                               size_t output_len, const DltSizeEstimator* estimator,
+                                               DltCoreAutoSettings settings, DltCoreBc3Settings* out_details) {
+    Settings best{};
+    DltResult r = core_auto(3, data, data_len, output, output_len, estimator, settings.use_all_modes, out_details, &best);
+    if (r.error_code == kCoreSuccess)
+        *out_details = DltCoreBc3Settings{best.split_alpha, best.split_colour, (uint8_t)best.variant};
+    return r;
+}
+
+// =================================================================================================
+// 1c. LTU estimator factory (extensions/estimators/dxt-lossless-transform-ltu/src/c_api.rs:74-103)
+// =================================================================================================
+DLT_EXPORT DltSizeEstimator* dltltu_new_size_estimator(void) {
+    static char ltu_instance;  // LosslessTransformUtilsSizeEstimation is a stateless unit struct
+    DltSizeEstimator* e = new (std::nothrow) DltSizeEstimator;
+    if (!e) return nullptr;
+    e->context = &ltu_instance;
+    e->max_compressed_size = &ltu_max_compressed_size;
+    e->estimate_compressed_size = &ltu_estimate_compressed_size;
+    return e;
+}
+DLT_EXPORT void dltltu_free_size_estimator(DltSizeEstimator* e) { delete e; }
+
+// =================================================================================================
+// 3. Additive device API: dltcuda_*
+// =================================================================================================
+enum DltcudaStatus : int {
+    kDltcudaOk = 0,
+    kDltcudaInvalidLength = 1,
+    kDltcudaInvalidSettings = 2,
+    kDltcudaCudaError = 3,
+    kDltcudaNullPointer = 4,
+    kDltcudaOutOfMemory = 5,
+};
+
+static int dltcuda_status(cudaError_t e) {
+    if (e == cudaSuccess) return kDltcudaOk;
+    note_cuda_error(e);
+    return e == cudaErrorMemoryAllocation ? kDltcudaOutOfMemory : kDltcudaCudaError;
+}
+static int dltcuda_status(Status s) {
+    return s == Status::kOk ? kDltcudaOk : s == Status::kOutOfMemory ? kDltcudaOutOfMemory : kDltcudaCudaError;
+}
+
+DLT_EXPORT int dltcuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+DLT_EXPORT void dltcuda_set_device(int device) { set_thread_device(device); }
+DLT_EXPORT const char* dltcuda_last_error(void) { return last_error_string(); }
+DLT_EXPORT uint64_t dltcuda_kernel_launch_count(void) { return kernel_launch_count() + estimator_launch_count(); }
+
+DLT_EXPORT void* dltcuda_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    const int dev = thread_device();
+    if (dev >= 0 && cudaSetDevice(dev) != cudaSuccess) return nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+DLT_EXPORT void dltcuda_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// Whole payload, device-resident, reference single-buffer layout.  Asynchronous on `stream`.
+DLT_EXPORT int dltcuda_transform_device(const uint8_t* d_input, uint8_t* d_output, size_t len, DltcudaSettings s,
+                                        void* stream) {
+    Settings st;
+    if (!to_settings(s, &st)) return kDltcudaInvalidSettings;
+    if (len % (size_t)block_bytes(st.format)) return kDltcudaInvalidLength;
+    if (len == 0) return kDltcudaOk;
+    if (!d_input || !d_output) return kDltcudaNullPointer;
+    const size_t n = len / block_bytes(st.format);
+    return dltcuda_status(launch_transform(st, d_input, reference_layout(d_output, n, 0, st), n, (cudaStream_t)stream));
+}
+DLT_EXPORT int dltcuda_untransform_device(const uint8_t* d_input, uint8_t* d_output, size_t len, DltcudaSettings s,
+                                          void* stream) {
+    Settings st;
+    if (!to_settings(s, &st)) return kDltcudaInvalidSettings;
+    if (len % (size_t)block_bytes(st.format)) return kDltcudaInvalidLength;
+    if (len == 0) return kDltcudaOk;
+    if (!d_input || !d_output) return kDltcudaNullPointer;
+    const size_t n = len / block_bytes(st.format);
+    return dltcuda_status(launch_untransform(st, reference_layout(const_cast<uint8_t*>(d_input), n, 0, st), d_output, n,
+                                             (cudaStream_t)stream));
+}
+
+// Block-range shard of a payload of `total_blocks` blocks: blocks [first_block, first_block+num_blocks).
+//   transform  : d_blocks points at the shard's first block; d_streams_base is the base of the FULL
+//                transformed image (reference layout for total_blocks); only this shard's slice of
+//                every stream is written.
+//   untransform: the mirror.
+// No data crosses shards; the only shared quantities are total_blocks and first_block.
+DLT_EXPORT int dltcuda_transform_device_range(const uint8_t* d_blocks, uint8_t* d_streams_base, size_t total_blocks,
+                                              size_t first_block, size_t num_blocks, DltcudaSettings s, void* stream) {
+    Settings st;
+    if (!to_settings(s, &st)) return kDltcudaInvalidSettings;
+    if (first_block + num_blocks > total_blocks) return kDltcudaInvalidLength;
+    if (num_blocks == 0) return kDltcudaOk;
+    if (!d_blocks || !d_streams_base) return kDltcudaNullPointer;
+    return dltcuda_status(launch_transform(st, d_blocks, reference_layout(d_streams_base, total_blocks, first_block, st),
+                                           num_blocks, (cudaStream_t)stream));
+}
+DLT_EXPORT int dltcuda_untransform_device_range(const uint8_t* d_streams_base, uint8_t* d_blocks, size_t total_blocks,
+                                                size_t first_block, size_t num_blocks, DltcudaSettings s,
+                                                void* stream) {
+    Settings st;
+    if (!to_settings(s, &st)) return kDltcudaInvalidSettings;
+    if (first_block + num_blocks > total_blocks) return kDltcudaInvalidLength;
+    if (num_blocks == 0) return kDltcudaOk;
+    if (!d_blocks || !d_streams_base) return kDltcudaNullPointer;
+    return dltcuda_status(launch_untransform(
+        st, reference_layout(const_cast<uint8_t*>(d_streams_base), total_blocks, first_block, st), d_blocks, num_blocks,
+        (cudaStream_t)stream));
+}
+
+// Explicit per-stream pointers (bcn_layout.h stream order; 2..6 streams): what a rank uses when it
+// holds only its own shard, or when a caller wants every stream in its own allocation.
+DLT_EXPORT int dltcuda_transform_device_streams(const uint8_t* d_blocks, uint8_t* const* d_streams, size_t num_blocks,
+                                                DltcudaSettings s, void* stream) {
+    Settings st;
+    if (!to_settings(s, &st)) return kDltcudaInvalidSettings;
+    if (num_blocks == 0) return kDltcudaOk;
+    if (!d_blocks || !d_streams) return kDltcudaNullPointer;
+    StreamPtrs sp{};
+    for (int k = 0; k < num_streams(st.format, st.split_alpha, st.split_colour); k++) {
+        if (!d_streams[k]) return kDltcudaNullPointer;
+        sp.p[k] = d_streams[k];
+    }
+    return dltcuda_status(launch_transform(st, d_blocks, sp, num_blocks, (cudaStream_t)stream));
+}
+DLT_EXPORT int dltcuda_untransform_device_streams(const uint8_t* const* d_streams, uint8_t* d_blocks,
+                                                  size_t num_blocks, DltcudaSettings s, void* stream) {
+    Settings st;
+    if (!to_settings(s, &st)) return kDltcudaInvalidSettings;
+    if (num_blocks == 0) return kDltcudaOk;
+    if (!d_blocks || !d_streams) return kDltcudaNullPointer;
+    StreamPtrs sp{};
+    for (int k = 0; k < num_streams(st.format, st.split_alpha, st.split_colour); k++) {
+        if (!d_streams[k]) return kDltcudaNullPointer;
+        sp.p[k] = const_cast<uint8_t*>(d_streams[k]);
+    }
+    return dltcuda_status(launch_untransform(st, sp, d_blocks, num_blocks, (cudaStream_t)stream));
+}
+// Number of streams / element width of stream k for a settings combination (layout introspection).
+DLT_EXPORT int dltcuda_stream_count(DltcudaSettings s) {
+    Settings st;
+    return to_settings(s, &st) ? num_streams(st.format, st.split_alpha, st.split_colour) : 0;
+}
+DLT_EXPORT int dltcuda_stream_width(DltcudaSettings s, int k) {
+    Settings st;
+    if (!to_settings(s, &st) || k < 0 || k >= num_streams(st.format, st.split_alpha, st.split_colour)) return 0;
+    return stream_width(st.format, st.split_alpha, st.split_colour, k);
+}
+
+// First block of shard `shard` of `num_shards` (shard == num_shards gives total_blocks): contiguous
+// block ranges whose boundaries are multiples of the kernel tile, so every per-stream slice keeps
+// the alignment of its stream base.  This host-side prefix is the whole multi-GPU "exchange".
+DLT_EXPORT size_t dltcuda_shard_first_block(int format, size_t total_blocks, int shard, int num_shards) {
+    if (num_shards <= 0 || shard <= 0) return 0;
+    if (shard >= num_shards) return total_blocks;
+    const size_t tile = (size_t)tile_blocks(format == 1 ? 1 : 2);
+    const size_t tiles = (total_blocks + tile - 1) / tile;
+    const size_t first = tiles * (size_t)shard / (size_t)num_shards * tile;
+    return first < total_blocks ? first : total_blocks;
+}
+
+// LTU-semantics estimate of a device-resident byte range.  Synchronous.
+DLT_EXPORT int dltcuda_ltu_estimate_device(const uint8_t* d_data, size_t len, size_t* out_size) {
+    if (!out_size) return kDltcudaNullPointer;
+    if (!d_data || len == 0) {
+        *out_size = 0;
+        return kDltcudaOk;
+    }
+    Status st;
+    Context* ctx = acquire_context(-1, &st);
+    if (!ctx) return dltcuda_status(st);
+    LtuSegment seg{d_data, len};
+    uint64_t m = 0;
+    st = ltu_matches_device(ctx, &seg, 1, &m, ctx->stream[0]);
+    release_context(ctx);
+    if (st == Status::kOk) *out_size = ltu_estimate_from_matches(len, m);
+    return dltcuda_status(st);
+}
+
+// transform_bcN_auto with the GPU LTU estimator on device-resident buffers.  out_estimates (optional)
+// receives the per-candidate estimates in the reference's test order (4/8 for BC1,BC2; 8/16 for BC3).
+// Synchronous; d_output holds the winner's transform on return.
+DLT_EXPORT int dltcuda_transform_auto_device(int format, const uint8_t* d_input, uint8_t* d_output, size_t len,
+                                             bool use_all_modes, DltcudaSettings* out_settings, size_t* out_estimates) {
+    if (format < 1 || format > 3) return kDltcudaInvalidSettings;
+    if (len % (size_t)block_bytes(format)) return kDltcudaInvalidLength;
+    if (!out_settings || (len && (!d_input || !d_output))) return kDltcudaNullPointer;
+    Status st;
+    Context* ctx = acquire_context(-1, &st);
+    if (!ctx) return dltcuda_status(st);
+    Settings best{};
+    st = auto_ltu_device(ctx, format, d_input, d_output, len, use_all_modes, &best, out_estimates, ctx->stream[0]);
+    if (st == Status::kOk) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream[0]);
+        if (e != cudaSuccess) st = Status::kCudaError, note_cuda_error(e);
+    }
+    release_context(ctx);
+    if (st == Status::kOk)
+        *out_settings = DltcudaSettings{(uint8_t)format, (uint8_t)best.variant, best.split_alpha, best.split_colour};
+    return dltcuda_status(st);
+}
+
+// Candidate order of the search, for callers that want to label out_estimates.  Returns the count.
+DLT_EXPORT int dltcuda_auto_candidates(int format, bool use_all_modes, DltcudaSettings* out /* >= 16 entries */) {
+    if (format < 1 || format > 3 || !out) return 0;
+    Settings order[kMaxCandidates];
+    const int k = candidate_order(format, use_all_modes, order);
+    for (int i = 0; i < k; i++)
+        out[i] = DltcudaSettings{(uint8_t)format, (uint8_t)order[i].variant, order[i].split_alpha, order[i].split_colour};
+    return k;
+}

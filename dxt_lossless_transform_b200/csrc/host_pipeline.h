@@ -1,0 +1,61 @@
+// host_pipeline.h — the host-pointer path behind the reference-compatible entry points.
+//
+// The reference's functions are synchronous calls on caller-owned HOST buffers
+// (core/dxt-lossless-transform-bc1/src/transform/transform_with_settings.rs:31,92).  Here the same
+// call streams the payload through one GPU: the block range is cut into chunks, and for each chunk
+// H2D copy -> kernel -> per-stream D2H copies are queued on one of a few CUDA streams so that the
+// copy engines and the SMs overlap.  Caller memory that is already page-locked is copied directly;
+// pageable memory goes through a small ring of pinned staging slots.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "bcn_layout.h"
+
+namespace dlt {
+
+enum class Status : int { kOk = 0, kCudaError = 1, kOutOfMemory = 2 };
+
+constexpr int kStages = 3;                      // chunks in flight
+constexpr size_t kChunkBytes = 8u << 20;        // bytes of blocks per chunk (multiple of the 16 KiB tile)
+
+struct Context {
+    int device = -1;
+    cudaStream_t stream[kStages] = {};
+    cudaEvent_t done[kStages] = {};
+    uint8_t* d_in = nullptr;   // blocks (transform input / untransform output)
+    uint8_t* d_out = nullptr;  // streams in the reference layout
+    size_t d_cap = 0;
+    uint8_t* h_in[kStages] = {};   // pinned staging, kChunkBytes each, allocated on first pageable use
+    uint8_t* h_out[kStages] = {};
+    uint8_t* d_scratch = nullptr;  // estimator scratch (see estimator.h)
+    size_t d_scratch_cap = 0;
+    Context* next_free = nullptr;
+};
+
+// Borrow a context for `device` (-1 = the calling thread's current CUDA device).  Contexts are
+// pooled per device, so concurrent host threads each get their own streams and buffers.
+Context* acquire_context(int device, Status* st);
+void release_context(Context* ctx);
+
+Status ensure_device_buffers(Context* ctx, size_t len);
+Status ensure_scratch(Context* ctx, size_t bytes);
+Status ensure_staging(Context* ctx);
+
+// transform (inverse=false) or untransform (inverse=true) `len` bytes of host memory; blocks until
+// `out` holds the result.
+Status run_host(const Settings& st, bool inverse, const uint8_t* in, uint8_t* out, size_t len, int device);
+
+// The last CUDA error string seen by this thread (diagnostics only).
+const char* last_error_string();
+void note_cuda_error(cudaError_t e);
+
+// Thread-local device override used by the C ABI (dltcuda_set_device).
+void set_thread_device(int device);
+int thread_device();
+
+bool is_pinned_host(const void* p);
+
+}  // namespace dlt

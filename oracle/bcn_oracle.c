@@ -1,0 +1,415 @@
+/*
+ * bcn_oracle.c — CPU ORACLE (TEST INFRASTRUCTURE ONLY; see bcn_oracle.h).
+ *
+ * Scalar, little-endian restatement of the reference's ground-truth code paths.
+ * Reference paths are relative to /root/reference/src.  Every routine works on a
+ * block range [b0, b1) of a payload of n blocks so the multi-threaded CPU baseline
+ * and the single call share one body; section offsets are always functions of the
+ * WHOLE payload's n, exactly as in the reference dispatchers.
+ */
+#include "bcn_oracle.h"
+#include "ltu_params.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------
+ * Color565 YCoCg-R   (core/dxt-lossless-transform-common/src/color_565/decorrelate.rs)
+ * ---------------------------------------------------------------------------------------- */
+
+/* decorrelate_ycocg_r_var1/2/3: decorrelate.rs:101-127 / 187-214 / 274-300.  The arithmetic is
+ * shared; only the final packing differs per variant. */
+uint16_t orc_decorrelate(uint16_t v, int variant) {
+    if (variant == ORC_VARIANT_NONE) return v;
+    uint32_t r = (v >> 11) & 0x1F, g = (v >> 6) & 0x1F, gl = (v >> 5) & 1, b = v & 0x1F;
+    uint32_t co = (r - b) & 0x1F;
+    uint32_t t = (b + (co >> 1)) & 0x1F;
+    uint32_t cg = (g - t) & 0x1F;
+    uint32_t y = (t + (cg >> 1)) & 0x1F;
+    switch (variant) {
+    case ORC_VARIANT_1: return (uint16_t)((y << 11) | (co << 6) | (gl << 5) | cg);
+    case ORC_VARIANT_2: return (uint16_t)((gl << 15) | (y << 10) | (co << 5) | cg);
+    default: return (uint16_t)((y << 11) | (co << 6) | (cg << 1) | gl);
+    }
+}
+
+/* recorrelate_ycocg_r_var1/2/3: decorrelate.rs:148-171 / 235-258 / 321-344. */
+uint16_t orc_recorrelate(uint16_t v, int variant) {
+    uint32_t y, co, cg, gl;
+    switch (variant) {
+    case ORC_VARIANT_NONE: return v;
+    case ORC_VARIANT_1: y = (v >> 11) & 0x1F; co = (v >> 6) & 0x1F; gl = (v >> 5) & 1; cg = v & 0x1F; break;
+    case ORC_VARIANT_2: gl = v >> 15; y = (v >> 10) & 0x1F; co = (v >> 5) & 0x1F; cg = v & 0x1F; break;
+    default: y = (v >> 11) & 0x1F; co = (v >> 6) & 0x1F; cg = (v >> 1) & 0x1F; gl = v & 1; break;
+    }
+    uint32_t t = (y - (cg >> 1)) & 0x1F;
+    uint32_t g = (cg + t) & 0x1F;
+    uint32_t b = (t - (co >> 1)) & 0x1F;
+    uint32_t r = (b + co) & 0x1F;
+    return (uint16_t)((r << 11) | (g << 6) | (gl << 5) | b);
+}
+
+static inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+static inline void wr16(uint8_t *p, uint16_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+
+/* Colour part shared by BC1/BC2/BC3: `col` points at [c0:u16][c1:u16] of one block.
+ * no split → (c0,c1) pair at colours + 4*i; split → c0 at c0s + 2*i, c1 at c1s + 2*i.
+ * BC1 with_split_colour_and_recorr/transform/generic.rs:39-83, with_recorrelate/transform/generic.rs:38-83. */
+static inline void colour_fwd(const uint8_t *col, uint8_t *c0dst, uint8_t *c1dst, int variant) {
+    wr16(c0dst, orc_decorrelate(rd16(col), variant));
+    wr16(c1dst, orc_decorrelate(rd16(col + 2), variant));
+}
+static inline void colour_inv(const uint8_t *c0src, const uint8_t *c1src, uint8_t *col, int variant) {
+    wr16(col, orc_recorrelate(rd16(c0src), variant));
+    wr16(col + 2, orc_recorrelate(rd16(c1src), variant));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * BC1   (core/dxt-lossless-transform-bc1/src/transform/transform_with_settings.rs:31-135)
+ *   no split: colours[4n] @0 | indices[4n] @len/2      (standard/transform/portable32.rs:8-47)
+ *   split   : c0[2n] @0 | c1[2n] @len/4 | indices @len/2
+ * ---------------------------------------------------------------------------------------- */
+static void bc1_range(int inverse, const uint8_t *in, uint8_t *out, size_t n, size_t b0, size_t b1,
+                      int variant, int split) {
+    size_t len = n * 8;
+    for (size_t i = b0; i < b1; i++) {
+        size_t c0o = split ? 2 * i : 4 * i;
+        size_t c1o = split ? len / 4 + 2 * i : 4 * i + 2;
+        size_t ixo = len / 2 + 4 * i;
+        if (!inverse) {
+            const uint8_t *blk = in + 8 * i;
+            colour_fwd(blk, out + c0o, out + c1o, variant);
+            memcpy(out + ixo, blk + 4, 4);
+        } else {
+            uint8_t *blk = out + 8 * i;
+            colour_inv(in + c0o, in + c1o, blk, variant);
+            memcpy(blk + 4, in + ixo, 4);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * BC2   (core/dxt-lossless-transform-bc2/src/transform/transform_with_settings.rs:30-137)
+ *   alpha[8n] @0 | colours[4n] @len/2 (split: c0 @len/2, c1 @len/2+len/8) | indices @len/2+len/4
+ *   (standard/transform/portable32.rs:6-56)
+ * ---------------------------------------------------------------------------------------- */
+static void bc2_range(int inverse, const uint8_t *in, uint8_t *out, size_t n, size_t b0, size_t b1,
+                      int variant, int split) {
+    size_t len = n * 16;
+    for (size_t i = b0; i < b1; i++) {
+        size_t alo = 8 * i;
+        size_t c0o = len / 2 + (split ? 2 * i : 4 * i);
+        size_t c1o = split ? len / 2 + len / 8 + 2 * i : len / 2 + 4 * i + 2;
+        size_t ixo = len / 2 + len / 4 + 4 * i;
+        if (!inverse) {
+            const uint8_t *blk = in + 16 * i;
+            memcpy(out + alo, blk, 8);
+            colour_fwd(blk + 8, out + c0o, out + c1o, variant);
+            memcpy(out + ixo, blk + 12, 4);
+        } else {
+            uint8_t *blk = out + 16 * i;
+            memcpy(blk, in + alo, 8);
+            colour_inv(in + c0o, in + c1o, blk + 8, variant);
+            memcpy(blk + 12, in + ixo, 4);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * BC3   (core/dxt-lossless-transform-bc3/src/transform/transform_with_settings.rs:32-290)
+ *   alpha endpoints [0,2n): pairs, or split a0[n] @0 | a1[n] @n
+ *   alpha indices   [2n,8n): 6 B/block verbatim
+ *   colours         [8n,12n): pairs, or split c0[2n] @8n | c1[2n] @10n
+ *   colour indices  [12n,16n)
+ *   (standard/transform/portable32.rs:10-65; with_split_alphas_colour_and_recorr/transform/generic.rs:24-88)
+ * ---------------------------------------------------------------------------------------- */
+static void bc3_range(int inverse, const uint8_t *in, uint8_t *out, size_t n, size_t b0, size_t b1,
+                      int variant, int split_a, int split_c) {
+    for (size_t i = b0; i < b1; i++) {
+        size_t a0o = split_a ? i : 2 * i;
+        size_t a1o = split_a ? n + i : 2 * i + 1;
+        size_t aio = 2 * n + 6 * i;
+        size_t c0o = 8 * n + (split_c ? 2 * i : 4 * i);
+        size_t c1o = split_c ? 10 * n + 2 * i : 8 * n + 4 * i + 2;
+        size_t ixo = 12 * n + 4 * i;
+        if (!inverse) {
+            const uint8_t *blk = in + 16 * i;
+            out[a0o] = blk[0];
+            out[a1o] = blk[1];
+            memcpy(out + aio, blk + 2, 6);
+            colour_fwd(blk + 8, out + c0o, out + c1o, variant);
+            memcpy(out + ixo, blk + 12, 4);
+        } else {
+            uint8_t *blk = out + 16 * i;
+            blk[0] = in[a0o];
+            blk[1] = in[a1o];
+            memcpy(blk + 2, in + aio, 6);
+            colour_inv(in + c0o, in + c1o, blk + 8, variant);
+            memcpy(blk + 12, in + ixo, 4);
+        }
+    }
+}
+
+void orc_bc1_transform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc1_range(0, in, out, len / 8, 0, len / 8, v, s); }
+void orc_bc1_untransform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc1_range(1, in, out, len / 8, 0, len / 8, v, s); }
+void orc_bc2_transform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc2_range(0, in, out, len / 16, 0, len / 16, v, s); }
+void orc_bc2_untransform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc2_range(1, in, out, len / 16, 0, len / 16, v, s); }
+void orc_bc3_transform(const uint8_t *in, uint8_t *out, size_t len, int v, int sa, int sc) { bc3_range(0, in, out, len / 16, 0, len / 16, v, sa, sc); }
+void orc_bc3_untransform(const uint8_t *in, uint8_t *out, size_t len, int v, int sa, int sc) { bc3_range(1, in, out, len / 16, 0, len / 16, v, sa, sc); }
+
+/* split_color_endpoints: [c0 c1]×k → c0×k | c1×k
+ * (common/src/transforms/split_565_color_endpoints/portable32.rs:18-64). */
+void orc_split_color_endpoints(const uint8_t *in, uint8_t *out, size_t len_bytes) {
+    size_t pairs = len_bytes / 4;
+    for (size_t i = 0; i < pairs; i++) {
+        memcpy(out + 2 * i, in + 4 * i, 2);
+        memcpy(out + len_bytes / 2 + 2 * i, in + 4 * i + 2, 2);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * LTU estimator (restated; PARITY UNPINNED — see ltu_params.h)
+ * ---------------------------------------------------------------------------------------- */
+static inline uint32_t rd32(const uint8_t *p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+size_t orc_ltu_num_lz_matches(const uint8_t *data, size_t len) {
+    uint32_t *table = (uint32_t *)calloc((size_t)1 << LTU_HASH_BITS, sizeof(uint32_t));
+    if (!table) abort();
+    size_t end = len > LTU_TAIL_GUARD ? len - LTU_TAIL_GUARD : 0;
+    size_t matches = 0;
+    for (size_t i = 0; i < end; i += LTU_GROUP) {
+        uint32_t d[LTU_GROUP], idx[LTU_GROUP];
+        for (int k = 0; k < LTU_GROUP; k++) {
+            d[k] = rd32(data + i + k) & LTU_KEY_MASK;
+            idx[k] = (uint32_t)(d[k] * LTU_GOLDEN_RATIO) >> (32 - LTU_HASH_BITS);
+        }
+        for (int k = 0; k < LTU_GROUP; k++) matches += table[idx[k]] == d[k];
+        for (int k = 0; k < LTU_GROUP; k++) table[idx[k]] = d[k];
+    }
+    free(table);
+    return matches;
+}
+
+/* estimate_size / estimate_compressed_size: extensions/estimators/dxt-lossless-transform-ltu/src/lib.rs:67-119
+ * (null or empty → 0; otherwise len.saturating_sub(matches)). */
+size_t orc_ltu_estimate(const uint8_t *data, size_t len) {
+    if (!data || len == 0) return 0;
+    size_t m = orc_ltu_num_lz_matches(data, len);
+    return len > m ? len - m : 0;
+}
+
+static int ltu_cb(void *ctx, const uint8_t *data, size_t len, size_t *out) {
+    (void)ctx;
+    *out = orc_ltu_estimate(data, len);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * transform_bcN_auto  (brute-force search, strict '<', first in order wins ties, final
+ * re-transform if the winner was not the last candidate tested)
+ * ---------------------------------------------------------------------------------------- */
+
+/* bc1/src/transform/settings.rs:81-98 (BC2 settings.rs:81-98 is identical). */
+static const int BC12_FAST[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
+static const int BC12_ALL[8][2] = {{2, 0}, {0, 0}, {0, 1}, {3, 0}, {3, 1}, {2, 1}, {1, 0}, {1, 1}};
+/* bc3/src/transform/settings.rs:91-121: (variant, split_alpha, split_colour). */
+static const int BC3_FAST[8][3] = {{1, 1, 0}, {1, 1, 1}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 1}, {0, 0, 0}, {1, 0, 0}};
+static const int BC3_ALL[16][3] = {{2, 1, 0}, {2, 1, 1}, {3, 1, 1}, {3, 1, 0}, {1, 1, 0}, {3, 0, 1}, {1, 1, 1}, {2, 0, 1},
+                                   {2, 0, 0}, {3, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 1}, {0, 0, 0}, {1, 0, 0}};
+
+/* bc1/src/transform/transform_auto.rs:200-270 (estimate(out, len/2));
+ * bc2/src/transform/transform_auto.rs:196-272 (estimate(out+len/2, len/4)). */
+static int bc12_auto(int fmt, const uint8_t *in, uint8_t *out, size_t len, int use_all, orc_estimate_fn est,
+                     void *ctx, int *ov, int *os, size_t *sizes) {
+    const int(*order)[2] = use_all ? BC12_ALL : BC12_FAST;
+    int k = use_all ? 8 : 4;
+    if (!est) est = ltu_cb;
+    /* Bc1TransformSettings::default() = (Variant1, split) — settings.rs:35-43 */
+    int best_v = 1, best_s = 1, last_v = 1, last_s = 1;
+    size_t best = SIZE_MAX;
+    for (int c = 0; c < k; c++) {
+        int v = order[c][0], s = order[c][1];
+        size_t sz;
+        int rc;
+        if (fmt == 1) {
+            orc_bc1_transform(in, out, len, v, s);
+            rc = est(ctx, out, len / 2, &sz);
+        } else {
+            orc_bc2_transform(in, out, len, v, s);
+            rc = est(ctx, out + len / 2, len / 4, &sz);
+        }
+        last_v = v;
+        last_s = s;
+        if (rc) return rc;
+        if (sizes) sizes[c] = sz;
+        if (sz < best) {
+            best = sz;
+            best_v = v;
+            best_s = s;
+        }
+    }
+    if (best_v != last_v || best_s != last_s) {
+        if (fmt == 1) orc_bc1_transform(in, out, len, best_v, best_s);
+        else orc_bc2_transform(in, out, len, best_v, best_s);
+    }
+    if (ov) *ov = best_v;
+    if (os) *os = best_s;
+    return 0;
+}
+
+int orc_bc1_transform_auto(const uint8_t *in, uint8_t *out, size_t len, int use_all, orc_estimate_fn est, void *ctx,
+                           int *ov, int *os) {
+    return bc12_auto(1, in, out, len, use_all, est, ctx, ov, os, NULL);
+}
+int orc_bc2_transform_auto(const uint8_t *in, uint8_t *out, size_t len, int use_all, orc_estimate_fn est, void *ctx,
+                           int *ov, int *os) {
+    return bc12_auto(2, in, out, len, use_all, est, ctx, ov, os, NULL);
+}
+
+/* bc3/src/transform/transform_auto.rs:196-293: estimate(out, 2n) + estimate(out + len/2, 4n). */
+static int bc3_auto(const uint8_t *in, uint8_t *out, size_t len, int use_all, orc_estimate_fn est, void *ctx, int *ov,
+                    int *osa, int *osc, size_t *sizes) {
+    const int(*order)[3] = use_all ? BC3_ALL : BC3_FAST;
+    int k = use_all ? 16 : 8;
+    if (!est) est = ltu_cb;
+    /* Bc3TransformSettings::default() = (Variant1, split_alpha, split_colour) — settings.rs:39-48 */
+    int bv = 1, ba = 1, bc = 1, lv = 1, la = 1, lc = 1;
+    size_t best = SIZE_MAX, n = len / 16;
+    for (int c = 0; c < k; c++) {
+        int v = order[c][0], sa = order[c][1], sc = order[c][2];
+        orc_bc3_transform(in, out, len, v, sa, sc);
+        lv = v;
+        la = sa;
+        lc = sc;
+        size_t a_sz, c_sz;
+        int rc = est(ctx, out, n * 2, &a_sz);
+        if (rc) return rc;
+        rc = est(ctx, out + len / 2, n * 4, &c_sz);
+        if (rc) return rc;
+        size_t total = a_sz + c_sz;
+        if (sizes) sizes[c] = total;
+        if (total < best) {
+            best = total;
+            bv = v;
+            ba = sa;
+            bc = sc;
+        }
+    }
+    if (bv != lv || ba != la || bc != lc) orc_bc3_transform(in, out, len, bv, ba, bc);
+    if (ov) *ov = bv;
+    if (osa) *osa = ba;
+    if (osc) *osc = bc;
+    return 0;
+}
+
+int orc_bc3_transform_auto(const uint8_t *in, uint8_t *out, size_t len, int use_all, orc_estimate_fn est, void *ctx,
+                           int *ov, int *osa, int *osc) {
+    return bc3_auto(in, out, len, use_all, est, ctx, ov, osa, osc, NULL);
+}
+
+int orc_bc1_auto_estimates(const uint8_t *in, uint8_t *scratch, size_t len, int use_all, size_t *sizes) {
+    bc12_auto(1, in, scratch, len, use_all, NULL, NULL, NULL, NULL, sizes);
+    return use_all ? 8 : 4;
+}
+int orc_bc2_auto_estimates(const uint8_t *in, uint8_t *scratch, size_t len, int use_all, size_t *sizes) {
+    bc12_auto(2, in, scratch, len, use_all, NULL, NULL, NULL, NULL, sizes);
+    return use_all ? 8 : 4;
+}
+int orc_bc3_auto_estimates(const uint8_t *in, uint8_t *scratch, size_t len, int use_all, size_t *sizes) {
+    bc3_auto(in, scratch, len, use_all, NULL, NULL, NULL, NULL, NULL, sizes);
+    return use_all ? 16 : 8;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Reference test-data generators
+ * ---------------------------------------------------------------------------------------- */
+
+/* core/dxt-lossless-transform-bc1/src/test_prelude.rs:81-105 */
+void orc_generate_bc1_test_data(uint8_t *p, size_t num_blocks) {
+    uint8_t color = 0, index = 128;
+    for (size_t i = 0; i < num_blocks; i++, p += 8) {
+        for (int k = 0; k < 4; k++) p[k] = (uint8_t)(color + k);
+        color = (uint8_t)(color + 4);
+        for (int k = 0; k < 4; k++) p[4 + k] = (uint8_t)(index + k);
+        index = (uint8_t)(index + 4);
+    }
+}
+
+/* core/dxt-lossless-transform-bc2/src/test_prelude.rs:151-190 */
+void orc_generate_bc2_test_data(uint8_t *p, size_t num_blocks) {
+    uint8_t alpha = 0, color = 0x80, index = 0xC0;
+    for (size_t i = 0; i < num_blocks; i++, p += 16) {
+        for (int k = 0; k < 8; k++) p[k] = (uint8_t)(alpha + k);
+        alpha = (uint8_t)(alpha + 8);
+        for (int k = 0; k < 4; k++) p[8 + k] = (uint8_t)(color + k);
+        color = (uint8_t)(color + 4);
+        for (int k = 0; k < 4; k++) p[12 + k] = (uint8_t)(index + k);
+        index = (uint8_t)(index + 4);
+    }
+}
+
+/* core/dxt-lossless-transform-bc3/src/test_prelude.rs:45-101 (note the per-field wrap rules). */
+void orc_generate_bc3_test_data(uint8_t *p, size_t num_blocks) {
+    uint8_t alpha = 0, aidx = 32, color = 128, index = 192;
+    for (size_t i = 0; i < num_blocks; i++, p += 16) {
+        p[0] = alpha;
+        p[1] = (uint8_t)(alpha + 1);
+        alpha = (uint8_t)(alpha + 2);
+        if (alpha >= 32) alpha = (uint8_t)(alpha - 32);
+        for (int k = 0; k < 6; k++) p[2 + k] = (uint8_t)(aidx + k);
+        aidx = (uint8_t)(aidx + 6);
+        if (aidx >= 128) aidx = (uint8_t)(aidx - 96);
+        for (int k = 0; k < 4; k++) p[8 + k] = (uint8_t)(color + k);
+        color = (uint8_t)(color + 4);
+        if (color >= 192) color = (uint8_t)(color - 64);
+        for (int k = 0; k < 4; k++) p[12 + k] = (uint8_t)(index + k);
+        index = (uint8_t)(index + 4);
+        if (index < 192) index = (uint8_t)(index - 64);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-threaded driver (CPU baseline): contiguous block ranges, one per thread.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int format, direction, variant, split_a, split_c;
+    const uint8_t *in;
+    uint8_t *out;
+    size_t n, b0, b1;
+} mt_job;
+
+static void *mt_worker(void *arg) {
+    mt_job *j = (mt_job *)arg;
+    switch (j->format) {
+    case 1: bc1_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c); break;
+    case 2: bc2_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c); break;
+    default: bc3_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_a, j->split_c); break;
+    }
+    return NULL;
+}
+
+/* One contiguous block range [b0, b1) of a payload of len bytes (what one shard / one GPU owns). */
+void orc_bcn_run_range(int format, int direction, const uint8_t *in, uint8_t *out, size_t len, int variant,
+                       int split_a, int split_c, size_t b0, size_t b1) {
+    mt_job j = {format, direction, variant, split_a, split_c, in, out, len / (format == 1 ? 8 : 16), b0, b1};
+    mt_worker(&j);
+}
+
+void orc_bcn_run_mt(int format, int direction, const uint8_t *in, uint8_t *out, size_t len, int variant, int split_a,
+                    int split_c, int threads) {
+    size_t n = len / (format == 1 ? 8 : 16);
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t tid[256];
+    mt_job jobs[256];
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (mt_job){format, direction, variant, split_a, split_c, in, out, n, n * (size_t)t / (size_t)threads,
+                           n * (size_t)(t + 1) / (size_t)threads};
+        if (t + 1 < threads) pthread_create(&tid[t], NULL, mt_worker, &jobs[t]);
+    }
+    mt_worker(&jobs[threads - 1]);
+    for (int t = 0; t + 1 < threads; t++) pthread_join(tid[t], NULL);
+}

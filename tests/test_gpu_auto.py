@@ -1,0 +1,183 @@
+"""GPU tests of the LTU-semantics estimator and the best-settings search against the oracle.
+
+The estimator restates lossless-transform-utils 0.1.3 (not in the reference tree): these tests prove
+GPU == oracle restatement bit for bit; parity with the real crate is UNPINNED."""
+import ctypes as C
+import zlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def dlt():
+    import dxt_lossless_transform_b200 as m
+
+    return m
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+
+    return t
+
+
+def payload(fmt):
+    return np.frombuffer(zlib.decompress((GOLDEN / f"r2-256-bc{fmt}.payload.zlib").read_bytes()), np.uint8).copy()
+
+
+def estimator_inputs():
+    rng = np.random.default_rng(42)
+    yield "zeros64", np.zeros(64, np.uint8)
+    for n in range(0, 41):
+        yield f"zeros{n}", np.zeros(n, np.uint8)
+        yield f"rand{n}", rng.integers(0, 4, n, dtype=np.uint8)
+    yield "period4", np.tile(np.array([1, 2, 3, 4], np.uint8), 64)
+    yield "period3", np.tile(np.array([9, 8, 7], np.uint8), 1000)
+    yield "two_symbols", rng.integers(0, 2, 50_000, dtype=np.uint8)
+    yield "low_entropy", rng.integers(0, 8, 300_001, dtype=np.uint8)
+    yield "random", rng.integers(0, 256, 1 << 20, dtype=np.uint8)
+    runs = np.repeat(rng.integers(0, 256, 4000, dtype=np.uint8), rng.integers(1, 40, 4000))
+    yield "runs", runs
+    # many keys colliding in one bucket: keys k * 2^16 have equal low product bits patterns
+    yield "bc1_payload_colours", oracle.transform(1, payload(1), 1, False, True)[: 4096 * 4]
+    yield "bc3_payload_alpha", oracle.transform(3, payload(3), 0, True, True)[: 4096 * 2]
+
+
+def test_estimator_equals_oracle_on_host_buffers(dlt):
+    est = dlt.LosslessTransformUtilsSizeEstimation()
+    assert est.max_compressed_size(12345) == 0
+    for name, data in estimator_inputs():
+        assert est.estimate_compressed_size(data) == oracle.ltu_estimate(data), name
+
+
+def test_estimator_reference_inequalities(dlt):
+    # extensions/estimators/dxt-lossless-transform-ltu/src/lib.rs:125-225
+    est = dlt.LosslessTransformUtilsSizeEstimation()
+    assert est.estimate_compressed_size(np.zeros(64, np.uint8)) < 64
+    rng = np.random.default_rng(0)
+    rnd = rng.integers(0, 256, 4096, dtype=np.uint8)
+    rep = np.tile(np.arange(16, dtype=np.uint8), 256)
+    a, b = est.estimate_compressed_size(rep), est.estimate_compressed_size(rnd)
+    assert a <= b <= rnd.size
+    assert est.estimate_compressed_size(rnd) == b
+
+
+def test_estimator_device_pointer_any_alignment(dlt, torch):
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 6, 200_000, dtype=np.uint8)
+    d = torch.from_numpy(data).cuda()
+    for off in (0, 1, 2, 3, 7):
+        assert dlt.ltu_estimate_device(d.data_ptr() + off, data.size - off) == oracle.ltu_estimate(data[off:])
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+@pytest.mark.parametrize("use_all", [False, True])
+def test_auto_matches_oracle_choice_and_bytes(dlt, torch, fmt, use_all):
+    from dxt_lossless_transform_b200 import synth
+
+    cases = [payload(fmt), oracle.generate_test_data(fmt, 3000)]
+    for seed, smooth in ((1, 1.0), (2, 0.2), (3, 5.0)):
+        cases.append(synth.texture_blocks(fmt, 20_000 + seed, seed=seed, smooth=smooth))
+    cases.append(synth.random_blocks(fmt, 5000, seed=9))
+    Est = dlt.Bc1EstimateSettings
+    for data in cases:
+        want_out, want = oracle.auto(fmt, data, use_all)
+        # host path, core ABI
+        out = np.zeros_like(data)
+        best = {1: dlt.transform_bc1_auto, 2: dlt.transform_bc2_auto, 3: dlt.transform_bc3_auto}[fmt](
+            data, out, Est(dlt.LosslessTransformUtilsSizeEstimation(), use_all))
+        got = (int(best.decorrelation_mode), bool(getattr(best, "split_alpha_endpoints", False)), bool(best.split_colour_endpoints))
+        assert got == want
+        assert np.array_equal(out, want_out)
+        # device path + per-candidate estimates
+        d_in = torch.from_numpy(data).cuda()
+        d_out = torch.zeros_like(d_in)
+        torch.cuda.synchronize()
+        best_d, sizes = dlt.transform_auto_device(fmt, d_in.data_ptr(), d_out.data_ptr(), data.size, use_all)
+        assert sizes == oracle.auto_estimates(fmt, data, use_all)
+        assert best_d == best
+        assert np.array_equal(d_out.cpu().numpy(), want_out)
+
+
+@pytest.mark.parametrize("fmt,use_all,expect", [
+    (1, False, (0, False, False)), (1, True, (2, False, False)),
+    (2, False, (0, False, False)), (2, True, (2, False, False)),
+    (3, False, (1, True, False)), (3, True, (2, True, False)),
+])
+def test_auto_with_dummy_estimator_ties_pick_first_in_order(dlt, fmt, use_all, expect):
+    """DummyEstimator (core/dxt-lossless-transform-bc1/src/test_prelude.rs:44-62) returns len_bytes."""
+    data = oracle.generate_test_data(fmt, 333)
+    dummy = dlt.CallbackSizeEstimator(lambda a: a.size)
+    out = np.zeros_like(data)
+    best = {1: dlt.transform_bc1_auto, 2: dlt.transform_bc2_auto, 3: dlt.transform_bc3_auto}[fmt](
+        data, out, dlt.Bc1EstimateSettings(dummy, use_all))
+    got = (int(best.decorrelation_mode), bool(getattr(best, "split_alpha_endpoints", False)), bool(best.split_colour_endpoints))
+    assert got == expect
+    assert np.array_equal(out, oracle.transform(fmt, data, *expect))
+    n = data.size // 16
+    per = {1: [data.size // 2], 2: [data.size // 4], 3: [2 * n, 4 * n]}[fmt]
+    k = (16 if use_all else 8) if fmt == 3 else (8 if use_all else 4)
+    assert dummy.calls == per * k
+
+
+def test_auto_callback_sees_the_transformed_endpoint_streams(dlt):
+    """A caller-supplied estimator must see exactly the bytes the reference would show it."""
+    data = payload(1)
+    seen = []
+    est = dlt.CallbackSizeEstimator(lambda a: (seen.append(a.copy()), oracle.ltu_estimate(a.copy()))[1])
+    out = np.zeros_like(data)
+    best = dlt.transform_bc1_auto(data, out, dlt.Bc1EstimateSettings(est, True))
+    order = dlt.api.auto_candidates(1, True)
+    for s, view in zip(order, seen):
+        t = oracle.transform(1, data, int(s.decorrelation_mode), False, s.split_colour_endpoints)
+        assert np.array_equal(view, t[: data.size // 2])
+    want_out, want = oracle.auto(1, data, True)
+    assert (int(best.decorrelation_mode), False, best.split_colour_endpoints) == want
+    assert np.array_equal(out, want_out)
+
+
+def test_auto_failing_estimator_reports_size_estimation_error(dlt):
+    """FailingEstimator (core/dxt-lossless-transform-bc1/src/transform/mod.rs:119-138)."""
+    def boom(_a):
+        raise RuntimeError("nope")
+
+    data = oracle.generate_test_data(1, 64)
+    with pytest.raises(dlt.api.SizeEstimationError):
+        dlt.transform_bc1_auto(data, np.zeros_like(data), dlt.Bc1EstimateSettings(dlt.CallbackSizeEstimator(boom)))
+    with pytest.raises(dlt.api.BcnError) as e:
+        dlt.Bc2AutoTransformBuilder(dlt.CallbackSizeEstimator(boom)).transform(
+            oracle.generate_test_data(2, 8), np.zeros(128, np.uint8))
+    assert e.value.code == 4  # SizeEstimationFailed
+    with pytest.raises(dlt.api.SizeEstimationError):
+        dlt.transform_bc3_auto(oracle.generate_test_data(3, 8), np.zeros(128, np.uint8),
+                               dlt.Bc1EstimateSettings(dlt.CallbackSizeEstimator(lambda a: 1, lambda n: 1 // 0)))
+
+
+def test_stable_auto_builder_returns_configured_manual_builder(dlt):
+    for Auto, fmt in ((dlt.Bc1AutoTransformBuilder, 1), (dlt.Bc2AutoTransformBuilder, 2)):
+        data = payload(fmt)
+        for ultra in (False, True):
+            b = Auto.new_ultra(dlt.LosslessTransformUtilsSizeEstimation()) if ultra else Auto(dlt.LosslessTransformUtilsSizeEstimation())
+            out = np.zeros_like(data)
+            manual = b.transform(data, out)
+            want_out, want = oracle.auto(fmt, data, ultra)
+            s = manual.get_settings()
+            assert (int(s.decorrelation_mode), False, s.split_colour_endpoints) == want
+            assert np.array_equal(out, want_out)
+            back = np.zeros_like(data)
+            manual.untransform(out, back)
+            assert np.array_equal(back, data)
+
+
+def test_auto_empty_input(dlt):
+    best = dlt.transform_bc1_auto(np.zeros(0, np.uint8), np.zeros(0, np.uint8),
+                                  dlt.Bc1EstimateSettings(dlt.LosslessTransformUtilsSizeEstimation()))
+    assert (best.decorrelation_mode, best.split_colour_endpoints) == (dlt.YCoCgVariant.NONE, False)

@@ -1,0 +1,282 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle (bit-exact)."""
+import json
+import zlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+KNOWN = json.loads((GOLDEN / "known_answers.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def dlt():
+    import dxt_lossless_transform_b200 as m
+
+    return m
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+
+    assert t.cuda.is_available()
+    return t
+
+
+def bpb(fmt):
+    return 8 if fmt == 1 else 16
+
+
+def settings_list(dlt, fmt):
+    return list({1: dlt.Bc1TransformSettings, 2: dlt.Bc2TransformSettings, 3: dlt.Bc3TransformSettings}[fmt].all_combinations())
+
+
+def orc_args(s):
+    return int(s.decorrelation_mode), bool(getattr(s, "split_alpha_endpoints", False)), bool(s.split_colour_endpoints)
+
+
+def payload(fmt):
+    return np.frombuffer(zlib.decompress((GOLDEN / f"r2-256-bc{fmt}.payload.zlib").read_bytes()), np.uint8).copy()
+
+
+def rand_blocks(fmt, n, seed):
+    return np.random.default_rng(seed).integers(0, 256, n * bpb(fmt), dtype=np.uint8)
+
+
+# ---- host-pointer path (the reference's entry points) ------------------------------------------------
+def test_known_answer_vectors_through_the_cabi(dlt):
+    d1 = np.frombuffer(bytes.fromhex(KNOWN["generators"]["bc1"]), np.uint8).copy()
+    for key, expect in KNOWN["bc1_3blocks"].items():
+        v, s = map(int, key.split("/"))
+        out = np.zeros_like(d1)
+        dlt.transform_bc1_with_settings(d1, out, dlt.Bc1TransformSettings(dlt.YCoCgVariant(v), bool(s)))
+        assert out.tobytes().hex() == expect
+    d3 = oracle.generate_test_data(3, 2)
+    for key, expect in KNOWN["bc3_2blocks"].items():
+        v, sa, sc = map(int, key.split("/"))
+        out = np.zeros_like(d3)
+        dlt.transform_bc3_with_settings(d3, out, dlt.Bc3TransformSettings(dlt.YCoCgVariant(v), bool(sa), bool(sc)))
+        assert out.tobytes().hex() == expect
+    d2 = oracle.generate_test_data(2, 2)
+    out = np.zeros_like(d2)
+    dlt.transform_bc2_with_settings(d2, out, dlt.Bc2TransformSettings(dlt.YCoCgVariant.Variant1, True))
+    assert out.tobytes().hex() == KNOWN["bc2_2blocks"]["1/1"]
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_reference_generators_1_to_130_blocks_all_settings(dlt, fmt):
+    """The reference's per-ISA tests run 1..=2x the SIMD width; here 1..=130 blocks."""
+    for nb in list(range(1, 131)) + [2047, 2048, 2049, 4095, 4097]:
+        data = oracle.generate_test_data(fmt, nb)
+        for s in settings_list(dlt, fmt):
+            out = np.full(data.size + 8, 0xAA, np.uint8)  # output_len >= input_len: only the prefix is written
+            dlt.transform_with_settings(fmt, data, out, s)
+            assert np.array_equal(out[:data.size], oracle.transform(fmt, data, *orc_args(s))), (fmt, nb, s)
+            assert (out[data.size:] == 0xAA).all()
+            back = np.zeros_like(data)
+            dlt.untransform_with_settings(fmt, out[:data.size].copy(), back, s)
+            assert np.array_equal(back, data), (fmt, nb, s)
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_real_texture_payloads_all_settings(dlt, fmt):
+    data = payload(fmt)
+    for s in settings_list(dlt, fmt):
+        out = np.zeros_like(data)
+        dlt.transform_with_settings(fmt, data, out, s)
+        assert np.array_equal(out, oracle.transform(fmt, data, *orc_args(s)))
+        back = np.zeros_like(data)
+        dlt.untransform_with_settings(fmt, out, back, s)
+        assert np.array_equal(back, data)
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_misaligned_host_buffers(dlt, fmt):
+    """The reference tests every untransform with 1-byte misaligned buffers (test_prelude.rs:340-536)."""
+    nb = 777
+    data = rand_blocks(fmt, nb, 3)
+    for off_in, off_out in ((1, 0), (0, 1), (1, 1), (3, 5)):
+        src = np.zeros(data.size + 16, np.uint8)
+        src[off_in:off_in + data.size] = data
+        for s in settings_list(dlt, fmt)[::3]:
+            dst = np.zeros(data.size + 16, np.uint8)
+            dlt.transform_with_settings(fmt, src[off_in:off_in + data.size], dst[off_out:off_out + data.size], s)
+            t = oracle.transform(fmt, data, *orc_args(s))
+            assert np.array_equal(dst[off_out:off_out + data.size], t)
+            back = np.zeros(data.size + 16, np.uint8)
+            dlt.untransform_with_settings(fmt, dst[off_out:off_out + data.size], back[off_in:off_in + data.size], s)
+            assert np.array_equal(back[off_in:off_in + data.size], data)
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_multi_chunk_host_pipeline_pageable_and_pinned(dlt, fmt):
+    """> 3 chunks of 8 MiB so the staging ring wraps; ragged last chunk; pinned and pageable buffers."""
+    nb = (28 << 20) // bpb(fmt) + 12345
+    data = rand_blocks(fmt, nb, 11)
+    s = settings_list(dlt, fmt)[0]
+    expect = oracle.transform(fmt, data, *orc_args(s), threads=8)
+    out = np.zeros_like(data)
+    dlt.transform_with_settings(fmt, data, out, s)
+    assert np.array_equal(out, expect)
+    pin_in, pin_out = dlt.alloc_pinned(data.size), dlt.alloc_pinned(data.size)
+    pin_in.array[:] = data
+    dlt.transform_with_settings(fmt, pin_in.array, pin_out.array, s)
+    assert np.array_equal(pin_out.array, expect)
+    dlt.untransform_with_settings(fmt, pin_out.array, pin_in.array, s)
+    assert np.array_equal(pin_in.array, data)
+    back = np.zeros_like(data)
+    dlt.untransform_with_settings(fmt, out, back, s)
+    assert np.array_equal(back, data)
+    pin_in.free(), pin_out.free()
+
+
+def test_stable_builders_roundtrip(dlt):
+    for Builder, fmt in ((dlt.Bc1ManualTransformBuilder, 1), (dlt.Bc2ManualTransformBuilder, 2)):
+        data = rand_blocks(fmt, 1000, 5)
+        for v in dlt.YCoCgVariant:
+            for split in (False, True):
+                b = Builder().decorrelation_mode(v).split_colour_endpoints(split)
+                out, back = np.zeros_like(data), np.zeros_like(data)
+                b.transform(data, out)
+                assert np.array_equal(out, oracle.transform(fmt, data, int(v), False, split))
+                b.clone().untransform(out, back)
+                assert np.array_equal(back, data)
+
+
+# ---- device-resident path ---------------------------------------------------------------------------
+def dev(torch, a):
+    return torch.from_numpy(a).cuda()
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_device_resident_all_settings_odd_block_counts(dlt, torch, fmt):
+    """Odd N puts the stream bases of the reference layout at odd offsets: shifted staging path."""
+    for nb in (1, 2, 3, 15, 16, 17, 1023, 1025, 5463, 2048 * 3 + 1, 65537):
+        data = rand_blocks(fmt, nb, nb)
+        d_in = dev(torch, data)
+        for s in settings_list(dlt, fmt):
+            d_out = torch.zeros_like(d_in)
+            dlt.transform_device(fmt, d_in.data_ptr(), d_out.data_ptr(), data.size, s)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_out.cpu().numpy(), oracle.transform(fmt, data, *orc_args(s))), (fmt, nb, s)
+            d_back = torch.zeros_like(d_in)
+            dlt.untransform_device(fmt, d_out.data_ptr(), d_back.data_ptr(), data.size, s)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_back.cpu().numpy(), data), (fmt, nb, s)
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_device_pointers_of_any_alignment(dlt, torch, fmt):
+    """Block or stream pointers the tiled kernels cannot address take the byte-granular kernel."""
+    nb = 3001
+    data = rand_blocks(fmt, nb, 9)
+    for off_in, off_out in ((1, 0), (0, 1), (8, 0), (2, 6)):
+        d_in = torch.zeros(data.size + 32, dtype=torch.uint8, device="cuda")
+        d_in[off_in:off_in + data.size] = dev(torch, data)
+        for s in settings_list(dlt, fmt)[1::3]:
+            d_out = torch.zeros(data.size + 32, dtype=torch.uint8, device="cuda")
+            dlt.transform_device(fmt, d_in.data_ptr() + off_in, d_out.data_ptr() + off_out, data.size, s)
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy()
+            assert np.array_equal(got[off_out:off_out + data.size], oracle.transform(fmt, data, *orc_args(s)))
+            assert (got[:off_out] == 0).all() and (got[off_out + data.size:] == 0).all()
+            d_back = torch.zeros(data.size + 32, dtype=torch.uint8, device="cuda")
+            dlt.untransform_device(fmt, d_out.data_ptr() + off_out, d_back.data_ptr() + off_in, data.size, s)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_back.cpu().numpy()[off_in:off_in + data.size], data)
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_no_write_outside_the_output(dlt, torch, fmt):
+    nb = 2048 * 2 + 37
+    data = rand_blocks(fmt, nb, 1)
+    d_in = dev(torch, data)
+    guard = 4096
+    for s in settings_list(dlt, fmt)[::5]:
+        d_out = torch.full((data.size + 2 * guard,), 0x5A, dtype=torch.uint8, device="cuda")
+        dlt.transform_device(fmt, d_in.data_ptr(), d_out.data_ptr() + guard, data.size, s)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        assert (got[:guard] == 0x5A).all() and (got[guard + data.size:] == 0x5A).all()
+        assert np.array_equal(got[guard:guard + data.size], oracle.transform(fmt, data, *orc_args(s)))
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_block_range_shards_compose_to_the_whole(dlt, torch, fmt):
+    """shards share only (N, first_block); any partition gives the same bytes."""
+    from dxt_lossless_transform_b200 import sharding
+
+    nb = 100_003
+    data = rand_blocks(fmt, nb, 21)
+    d_in = dev(torch, data)
+    for s in settings_list(dlt, fmt)[::3]:
+        expect = oracle.transform(fmt, data, *orc_args(s))
+        for shards in (2, 3, 8):
+            d_out = torch.zeros_like(d_in)
+            for first, count in sharding.shard_ranges(fmt, nb, shards):
+                dlt.transform_device_range(fmt, d_in.data_ptr() + first * bpb(fmt), d_out.data_ptr(), nb, first, count, s)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_out.cpu().numpy(), expect)
+            d_back = torch.zeros_like(d_in)
+            for first, count in sharding.shard_ranges(fmt, nb, shards):
+                dlt.untransform_device_range(fmt, d_out.data_ptr(), d_back.data_ptr() + first * bpb(fmt), nb, first, count, s)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_back.cpu().numpy(), data)
+        # an arbitrary (odd) cut is legal too
+        d_out = torch.zeros_like(d_in)
+        for first, count in ((0, 777), (777, nb - 777)):
+            dlt.transform_device_range(fmt, d_in.data_ptr() + first * bpb(fmt), d_out.data_ptr(), nb, first, count, s)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), expect)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_exhaustive_colour_table_on_the_gpu(dlt, torch, variant):
+    """All 65,536 RGB565 values through the kernels' packed arithmetic vs the scalar oracle."""
+    colours = np.arange(65536, dtype=np.uint16)
+    blocks = np.zeros((65536, 4), np.uint16)
+    blocks[:, 0] = colours
+    blocks[:, 1] = colours[::-1]
+    data = blocks.view(np.uint8).reshape(-1).copy()
+    d_in = dev(torch, data)
+    d_out = torch.zeros_like(d_in)
+    s = dlt.Bc1TransformSettings(dlt.YCoCgVariant(variant), True)
+    dlt.transform_device(1, d_in.data_ptr(), d_out.data_ptr(), data.size, s)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    c0 = got[:131072].view(np.uint16)
+    expect = np.array([oracle.decorrelate(int(c), variant) for c in colours], np.uint16)
+    assert np.array_equal(c0, expect)
+    assert np.array_equal(got[131072:262144].view(np.uint16), expect[::-1])
+
+
+# ---- BASELINE.json full sizes: size-independent properties + a full oracle comparison ---------------
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_one_gib_device_resident(dlt, torch, fmt):
+    nbytes = 1 << 30
+    g = torch.Generator(device="cuda").manual_seed(1234 + fmt)
+    d_in = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device="cuda", generator=g)
+    d_out, d_back = torch.empty_like(d_in), torch.empty_like(d_in)
+    all_s = settings_list(dlt, fmt)
+    for s in all_s:
+        dlt.transform_device(fmt, d_in.data_ptr(), d_out.data_ptr(), nbytes, s)
+        dlt.untransform_device(fmt, d_out.data_ptr(), d_back.data_ptr(), nbytes, s)
+        torch.cuda.synchronize()
+        assert torch.equal(d_back, d_in), s
+        if int(s.decorrelation_mode) == 0:
+            # a pure permutation keeps the byte histogram
+            assert torch.equal(torch.bincount(d_out.view(torch.int64) & 0xFF, minlength=256),
+                               torch.bincount(d_in.view(torch.int64) & 0xFF, minlength=256))
+    # full byte-for-byte comparison against the oracle for the default settings
+    s = all_s[0].__class__()
+    dlt.transform_device(fmt, d_in.data_ptr(), d_out.data_ptr(), nbytes, s)
+    torch.cuda.synchronize()
+    host = d_in.cpu().numpy()
+    expect = oracle.transform(fmt, host, *orc_args(s), threads=16)
+    assert np.array_equal(d_out.cpu().numpy(), expect)
