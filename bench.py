@@ -266,6 +266,11 @@ def run_gpu_arm(args) -> None:
         except Exception:
             pass
 
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "ms_per_step": ms_per_step, "value": value, "roofline": roofline}))
+        return
+
     # ---- end to end through the reference-facing C ABI: pinned HOST buffers, H2D + D2H in the timed region
     host_t, host_back = dlt.alloc_pinned(shard_bytes), dlt.alloc_pinned(shard_bytes)
     dlt.set_device(local_rank)
@@ -330,6 +335,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gib-per-gpu", type=float, default=1.0)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="kernel-only run for ncu: skips the e2e and cpu_baseline legs (never a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
