@@ -59,32 +59,55 @@ Status auto_ltu_device(Context* ctx, int format, const uint8_t* d_in, uint8_t* d
     EstimateRange ranges[2];
     const int nr = estimate_ranges(format, len, ranges);
 
-    Settings best_s = default_settings(format);
-    size_t best_size = SIZE_MAX;
-    int best_i = -1;
-    for (int i = 0; i < k; i++) {
-        size_t total = 0;
-        if (len != 0) {
-            cudaError_t e = launch_transform(order[i], d_in, reference_layout(d_out, n, 0, order[i]), n, stream);
-            if (e != cudaSuccess) {
-                note_cuda_error(e);
-                return Status::kCudaError;
+    size_t totals[kMaxCandidates] = {};
+    if (len != 0) {
+        // Candidates are transformed into scratch images and estimated in batches, so that one set of
+        // estimator launches covers several candidates (small payloads fill the GPU, large ones stay
+        // within the scratch budget).  scratch = [m images][estimator sort buffers for m*nr segments]
+        const size_t img = (len + 255) / 256 * 256;
+        constexpr size_t kScratchBudget = (size_t)12 << 30;
+        LtuSegment segs[kMaxCandidates * 2];
+        auto scratch_for = [&](int m) {
+            for (int c = 0; c < m; c++)
+                for (int r = 0; r < nr; r++) segs[c * nr + r] = LtuSegment{nullptr, ranges[r].len};
+            return (size_t)m * img + ltu_scratch_bytes(segs, m * nr);
+        };
+        int m = k;
+        while (m > 1 && scratch_for(m) > kScratchBudget) m--;
+        Status st;
+        while ((st = ensure_scratch(ctx, scratch_for(m))) == Status::kOutOfMemory && m > 1) m = (m + 1) / 2;
+        if (st != Status::kOk) return st;
+        uint8_t* est_scratch = ctx->d_scratch + (size_t)m * img;
+        const size_t est_bytes = ctx->d_scratch_cap - (size_t)m * img;
+
+        for (int c0 = 0; c0 < k; c0 += m) {
+            const int mb = k - c0 < m ? k - c0 : m;
+            for (int c = 0; c < mb; c++) {
+                uint8_t* image = ctx->d_scratch + (size_t)c * img;
+                cudaError_t e = launch_transform(order[c0 + c], d_in, reference_layout(image, n, 0, order[c0 + c]), n, stream);
+                if (e != cudaSuccess) {
+                    note_cuda_error(e);
+                    return Status::kCudaError;
+                }
+                for (int r = 0; r < nr; r++) segs[c * nr + r] = LtuSegment{image + ranges[r].offset, ranges[r].len};
             }
-            LtuSegment segs[2];
-            uint64_t matches[2] = {0, 0};
-            for (int r = 0; r < nr; r++) segs[r] = LtuSegment{d_out + ranges[r].offset, ranges[r].len};
-            Status st = ltu_matches_device(ctx, segs, nr, matches, stream);
+            uint64_t matches[kMaxCandidates * 2] = {};
+            st = ltu_matches_device(segs, mb * nr, matches, stream, est_scratch, est_bytes);
             if (st != Status::kOk) return st;
-            for (int r = 0; r < nr; r++) total += ltu_estimate_from_matches(ranges[r].len, matches[r]);
-        }
-        if (sizes) sizes[i] = total;
-        if (total < best_size) {
-            best_size = total;
-            best_s = order[i];
-            best_i = i;
+            for (int c = 0; c < mb; c++)
+                for (int r = 0; r < nr; r++)
+                    totals[c0 + c] += ltu_estimate_from_matches(ranges[r].len, matches[c * nr + r]);
         }
     }
-    if (len != 0 && best_i != k - 1) {
+
+    // strict '<': the first candidate in test order wins ties (transform_auto.rs:257-260)
+    Settings best_s = default_settings(format);
+    size_t best_size = SIZE_MAX;
+    for (int i = 0; i < k; i++) {
+        if (sizes) sizes[i] = totals[i];
+        if (totals[i] < best_size) best_size = totals[i], best_s = order[i];
+    }
+    if (len != 0) {
         cudaError_t e = launch_transform(best_s, d_in, reference_layout(d_out, n, 0, best_s), n, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) {

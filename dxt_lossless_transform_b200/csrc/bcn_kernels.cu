@@ -14,8 +14,8 @@
 //     front, does the colour arithmetic on two RGB565 values packed in one 32-bit register, and
 //     scatters the fields into a shared-memory staging area that is laid out per stream; after one
 //     barrier the CTA streams each stream segment to HBM with 128-bit stores;
-//   * untransform mirrors it: 128-bit stream loads -> shared memory -> per-thread gather ->
-//     recorrelate -> one 128-bit block store per thread and vector.
+//   * untransform mirrors it: 16-byte cp.async (LDGSTS) stream copies straight into shared memory ->
+//     per-thread gather -> recorrelate -> one 128-bit block store per thread and vector.
 //   * stream bases need not be 16-byte aligned (in the reference layout they sit at N*k bytes, and
 //     real mip chains give odd N): the staging area of stream s is shifted by (address & 15) so
 //     shared and global addresses are congruent mod 16; the aligned interior moves as 128-bit
@@ -54,6 +54,11 @@ __device__ __forceinline__ void stg_stream16(void* p, const uint4& v) {
                  "r"(v.w)
                  : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void stg_stream8(void* p, const uint2& v) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
@@ -135,16 +140,6 @@ struct Lay {
     static constexpr int kStageBytes = kTileBytes + 16 * NS;
     // 128-bit chunks per stream segment of a full tile (+1 when the segment is shifted).
     DLT_HD static constexpr int iters(int s) { return (w(s) * T / 16 + 1 + kThreads - 1) / kThreads; }
-    DLT_HD static constexpr int total_iters() {
-        int a = 0;
-        for (int s = 0; s < NS; s++) a += iters(s);
-        return a;
-    }
-    DLT_HD static constexpr int iter_base(int s) {
-        int a = 0;
-        for (int i = 0; i < s; i++) a += iters(i);
-        return a;
-    }
     // Stream indices of the logical fields.
     static constexpr int sAlpha = 0;                          // BC2 alpha:8 / BC3 a0a1:2 or a0:1
     static constexpr int sA1 = 1;                             // BC3 split alpha only
@@ -296,21 +291,8 @@ __global__ void __launch_bounds__(kThreads, 4)
 #pragma unroll
     for (int s = 0; s < L::NS; s++) sh[s] = (int)(reinterpret_cast<uintptr_t>(in.p[s]) & 15);
 
-    // ---- phase 1: all 128-bit stream loads of the tile are issued before the first shared store
-    uint4 tmp[L::total_iters()];
-#pragma unroll
-    for (int s = 0; s < L::NS; s++) {
-        const int w = L::w(s);
-        const int lo_valid = sh[s], hi_valid = sh[s] + w * nb;
-        const uint8_t* gal = in.p[s] + (uint64_t)w * tile_first - sh[s];
-        const int nch = (hi_valid + 15) >> 4;
-#pragma unroll
-        for (int it = 0; it < L::iters(s); it++) {
-            const int k = it * kThreads + tid;
-            const int lo = k << 4;
-            if (k < nch && lo >= lo_valid && lo + 16 <= hi_valid) tmp[L::iter_base(s) + it] = ldg_stream16(gal + lo);
-        }
-    }
+    // ---- phase 1: every stream segment of the tile goes global -> shared with 16-byte cp.async
+    // (LDGSTS, L2-only caching): no staging registers, all copies of the tile in flight at once.
 #pragma unroll
     for (int s = 0; s < L::NS; s++) {
         const int w = L::w(s);
@@ -324,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 4)
             if (k < nch) {
                 const int lo = k << 4;
                 if (lo >= lo_valid && lo + 16 <= hi_valid) {
-                    sts<uint4>(reg + lo, tmp[L::iter_base(s) + it]);
+                    cp_async16(reg + lo, gal + lo);
                 } else {
                     const int a = lo > lo_valid ? lo : lo_valid;
                     const int b = lo + 16 < hi_valid ? lo + 16 : hi_valid;
@@ -333,6 +315,7 @@ __global__ void __launch_bounds__(kThreads, 4)
             }
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     // ---- phase 2: gather the fields of each block, recorrelate, one 128-bit block store per vector

@@ -27,9 +27,22 @@ struct LtuSegment {
     size_t len;
 };
 
+// Device scratch the call below needs for these segments (sort buffers: ~8.2 bytes per position).
+size_t ltu_scratch_bytes(const LtuSegment* segs, int nseg);
+
 // Number of LZ matches of each device-resident segment, written to host `matches[0..nseg)`.
-// Synchronises `stream` before returning.
-Status ltu_matches_device(Context* ctx, const LtuSegment* segs, int nseg, uint64_t* matches, cudaStream_t stream);
+// `scratch` is device memory of at least ltu_scratch_bytes().  Synchronises `stream` before returning.
+Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, cudaStream_t stream, uint8_t* scratch,
+                          size_t scratch_bytes);
+
+// Convenience: takes the scratch from the context (grows ctx->d_scratch as needed).
+inline Status ltu_matches_device(Context* ctx, const LtuSegment* segs, int nseg, uint64_t* matches,
+                                 cudaStream_t stream) {
+    const size_t need = ltu_scratch_bytes(segs, nseg);
+    const Status st = ensure_scratch(ctx, need);
+    if (st != Status::kOk) return st;
+    return ltu_matches_device(segs, nseg, matches, stream, ctx->d_scratch, ctx->d_scratch_cap);
+}
 
 inline size_t ltu_estimate_from_matches(size_t len, uint64_t matches) {
     return len == 0 ? 0 : (matches >= len ? 0 : len - (size_t)matches);
