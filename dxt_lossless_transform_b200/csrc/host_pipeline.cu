@@ -1,8 +1,13 @@
 // host_pipeline.cu — see host_pipeline.h.
 #include "host_pipeline.h"
 
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <algorithm>
+#include <vector>
 
 #include "bcn_kernels.h"
 
@@ -27,6 +32,73 @@ thread_local char t_error[256] = "";
         }                                                      \
     } while (0)
 
+// Staging copies for pageable caller memory: a few worker threads split each large memcpy so the
+// host side of the pipeline keeps up with the link (one thread tops out well below PCIe Gen5).
+class CopyPool {
+public:
+    static CopyPool& instance() {
+        static CopyPool* pool = new CopyPool;  // leaked on purpose: workers outlive static destruction
+        return *pool;
+    }
+    void copy(uint8_t* dst, const uint8_t* src, size_t n) {
+        constexpr size_t kMinPart = 512u << 10;
+        const size_t parts = std::min<size_t>(workers_.size() + 1, n / kMinPart);
+        if (parts <= 1) {
+            std::memcpy(dst, src, n);
+            return;
+        }
+        std::lock_guard<std::mutex> serial(call_mutex_);  // one parallel copy at a time
+        const size_t per = (n / parts + 63) & ~(size_t)63;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            dst_ = dst, src_ = src, n_ = n, per_ = per, next_ = 1, pending_ = parts - 1, total_parts_ = parts;
+            ++generation_;
+        }
+        cv_.notify_all();
+        std::memcpy(dst, src, std::min(per, n));
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+private:
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        unsigned n = hw >= 16 ? 7 : hw >= 8 ? 3 : hw >= 4 ? 1 : 0;
+        if (const char* v = std::getenv("DLTCUDA_COPY_THREADS")) {
+            const long t = std::atol(v);
+            if (t >= 1 && t <= 64) n = (unsigned)t - 1;
+        }
+        for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { run(); }), workers_.back().detach();
+    }
+    void run() {
+        uint64_t seen = 0;
+        for (;;) {
+            size_t part;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return generation_ != seen && next_ < total_parts_; });
+                part = next_++;
+                if (next_ >= total_parts_) seen = generation_;
+            }
+            const size_t off = part * per_;
+            if (off < n_) std::memcpy(dst_ + off, src_ + off, std::min(per_, n_ - off));
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_, call_mutex_;
+    std::condition_variable cv_, done_cv_;
+    uint8_t* dst_ = nullptr;
+    const uint8_t* src_ = nullptr;
+    size_t n_ = 0, per_ = 0, next_ = 0, pending_ = 0, total_parts_ = 0;
+    uint64_t generation_ = 0;
+};
+
+inline void staged_copy(uint8_t* dst, const uint8_t* src, size_t n) { CopyPool::instance().copy(dst, src, n); }
+
 Status create_context(int device, Context** out) {
     Context* c = new Context();
     c->device = device;
@@ -44,6 +116,27 @@ Status create_context(int device, Context** out) {
 }
 
 }  // namespace
+
+const HostPathConfig& host_path_config() {
+    static const HostPathConfig cfg = [] {
+        HostPathConfig c{kChunkBytes, kStages, true, (size_t)4 << 20};
+        if (const char* v = std::getenv("DLTCUDA_CHUNK_MIB")) {
+            const long mib = std::atol(v);
+            if (mib >= 1 && (size_t)mib << 20 <= kChunkBytes) c.chunk_bytes = (size_t)mib << 20;
+        }
+        if (const char* v = std::getenv("DLTCUDA_STAGES")) {
+            const long n = std::atol(v);
+            if (n >= 1 && n <= kStages) c.stages = (int)n;
+        }
+        if (const char* v = std::getenv("DLTCUDA_ZEROCOPY")) c.zero_copy = std::atol(v) != 0;
+        if (const char* v = std::getenv("DLTCUDA_ZEROCOPY_MAX_KIB")) {
+            const long kib = std::atol(v);
+            if (kib >= 0) c.zero_copy_max_bytes = (size_t)kib << 10;
+        }
+        return c;
+    }();
+    return cfg;
+}
 
 void note_cuda_error(cudaError_t e) {
     std::strncpy(t_error, cudaGetErrorString(e), sizeof(t_error) - 1);
@@ -169,13 +262,37 @@ Status run_host(const Settings& st, bool inverse, const uint8_t* in, uint8_t* ou
         ~Releaser() { release_context(c); }
     } releaser{ctx};
 
-    Slots slots;
-    if ((status = ensure_slots(ctx, &slots)) != Status::kOk) return status;
-
+    const HostPathConfig& cfg = host_path_config();
     const int bpb = block_bytes(st.format);
     const int ns = num_streams(st.format, st.split_alpha, st.split_colour);
     const size_t n = len / bpb;
-    const size_t chunk_blocks = kChunkBytes / bpb;
+    const bool in_pinned = is_pinned_host(in) && is_pinned_host(in + len - 1);
+    const bool out_pinned = is_pinned_host(out) && is_pinned_host(out + len - 1);
+
+    // Page-locked buffers on both sides: the kernel reads the blocks and writes the streams straight
+    // over the host link (mapped memory).  One launch, reads and writes overlap inside the kernel,
+    // the streams land at their final (possibly odd) offsets; nothing is staged in HBM.
+    if (cfg.zero_copy && len <= cfg.zero_copy_max_bytes && in_pinned && out_pinned) {
+        void *d_in = nullptr, *d_out = nullptr;
+        if (cudaHostGetDevicePointer(&d_in, const_cast<uint8_t*>(in), 0) == cudaSuccess &&
+            cudaHostGetDevicePointer(&d_out, out, 0) == cudaSuccess) {
+            cudaStream_t s = ctx->stream[0];
+            if (!inverse)
+                DLT_CUDA(launch_transform(st, static_cast<const uint8_t*>(d_in),
+                                          reference_layout(static_cast<uint8_t*>(d_out), n, 0, st), n, s));
+            else
+                DLT_CUDA(launch_untransform(st, reference_layout(static_cast<uint8_t*>(d_in), n, 0, st),
+                                            static_cast<uint8_t*>(d_out), n, s));
+            DLT_CUDA(cudaStreamSynchronize(s));
+            return Status::kOk;
+        }
+        (void)cudaGetLastError();
+    }
+
+    Slots slots;
+    if ((status = ensure_slots(ctx, &slots)) != Status::kOk) return status;
+    const int stages = cfg.stages;
+    const size_t chunk_blocks = cfg.chunk_bytes / bpb;
     const size_t nchunks = (n + chunk_blocks - 1) / chunk_blocks;
     int w[kMaxStreams], pre[kMaxStreams];
     for (int k = 0; k < ns; k++) {
@@ -183,8 +300,6 @@ Status run_host(const Settings& st, bool inverse, const uint8_t* in, uint8_t* ou
         pre[k] = stream_prefix(st.format, st.split_alpha, st.split_colour, k);
     }
 
-    const bool in_pinned = is_pinned_host(in) && is_pinned_host(in + len - 1);
-    const bool out_pinned = is_pinned_host(out) && is_pinned_host(out + len - 1);
     if (!in_pinned || !out_pinned)
         if ((status = ensure_staging(ctx)) != Status::kOk) return status;
 
@@ -194,7 +309,7 @@ Status run_host(const Settings& st, bool inverse, const uint8_t* in, uint8_t* ou
     auto slot_off = [&](int k) { return chunk_blocks * (size_t)pre[k]; };
 
     auto issue = [&](size_t c) -> Status {
-        const int slot = (int)(c % kStages);
+        const int slot = (int)(c % stages);
         cudaStream_t s = ctx->stream[slot];
         const size_t b0 = c * chunk_blocks;
         const size_t nb = n - b0 < chunk_blocks ? n - b0 : chunk_blocks;
@@ -203,7 +318,7 @@ Status run_host(const Settings& st, bool inverse, const uint8_t* in, uint8_t* ou
         if (!inverse) {
             const uint8_t* src = in + b0 * bpb;
             if (!in_pinned) {
-                std::memcpy(ctx->h_in[slot], src, nb * bpb);
+                staged_copy(ctx->h_in[slot], src, nb * bpb);
                 src = ctx->h_in[slot];
             }
             DLT_CUDA(cudaMemcpyAsync(slots.blocks[slot], src, nb * bpb, cudaMemcpyHostToDevice, s));
@@ -216,7 +331,7 @@ Status run_host(const Settings& st, bool inverse, const uint8_t* in, uint8_t* ou
             for (int k = 0; k < ns; k++) {
                 const uint8_t* src = in + host_off(k, b0);
                 if (!in_pinned) {
-                    std::memcpy(ctx->h_in[slot] + slot_off(k), src, (size_t)w[k] * nb);
+                    staged_copy(ctx->h_in[slot] + slot_off(k), src, (size_t)w[k] * nb);
                     src = ctx->h_in[slot] + slot_off(k);
                 }
                 DLT_CUDA(cudaMemcpyAsync(sp.p[k], src, (size_t)w[k] * nb, cudaMemcpyHostToDevice, s));
@@ -230,24 +345,35 @@ Status run_host(const Settings& st, bool inverse, const uint8_t* in, uint8_t* ou
     };
 
     auto finish = [&](size_t c) -> Status {
-        const int slot = (int)(c % kStages);
+        const int slot = (int)(c % stages);
         DLT_CUDA(cudaEventSynchronize(ctx->done[slot]));
         if (out_pinned) return Status::kOk;
         const size_t b0 = c * chunk_blocks;
         const size_t nb = n - b0 < chunk_blocks ? n - b0 : chunk_blocks;
         if (!inverse) {
             for (int k = 0; k < ns; k++)
-                std::memcpy(out + host_off(k, b0), ctx->h_out[slot] + slot_off(k), (size_t)w[k] * nb);
+                staged_copy(out + host_off(k, b0), ctx->h_out[slot] + slot_off(k), (size_t)w[k] * nb);
         } else {
-            std::memcpy(out + b0 * bpb, ctx->h_out[slot], nb * bpb);
+            staged_copy(out + b0 * bpb, ctx->h_out[slot], nb * bpb);
         }
         return Status::kOk;
     };
 
     Status result = Status::kOk;
-    for (size_t c = 0; c < nchunks + kStages; c++) {
-        if (c >= (size_t)kStages && c - kStages < nchunks) {
-            Status f = finish(c - kStages);
+    if (in_pinned && out_pinned) {
+        // Nothing for the host to stage: queue every chunk at once.  Chunk c shares its CUDA stream
+        // (= slot) with chunk c - stages, so slot reuse is ordered on the device and the copy engines
+        // never wait for the host.
+        for (size_t c = 0; c < nchunks && result == Status::kOk; c++) result = issue(c);
+        for (int i = 0; i < stages; i++) {
+            cudaError_t e = cudaStreamSynchronize(ctx->stream[i]);
+            if (e != cudaSuccess && result == Status::kOk) note_cuda_error(e), result = Status::kCudaError;
+        }
+        return result;
+    }
+    for (size_t c = 0; c < nchunks + stages; c++) {
+        if (c >= (size_t)stages && c - stages < nchunks) {
+            Status f = finish(c - stages);
             if (f != Status::kOk && result == Status::kOk) result = f;
         }
         if (c < nchunks && result == Status::kOk) {

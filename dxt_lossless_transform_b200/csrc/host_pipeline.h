@@ -18,8 +18,24 @@ namespace dlt {
 
 enum class Status : int { kOk = 0, kCudaError = 1, kOutOfMemory = 2 };
 
-constexpr int kStages = 3;                      // chunks in flight
-constexpr size_t kChunkBytes = 8u << 20;        // bytes of blocks per chunk (multiple of the 16 KiB tile)
+constexpr int kStages = 4;                      // chunk slots (chunks in flight)
+constexpr size_t kChunkBytes = 16u << 20;       // bytes of blocks per chunk (multiple of the 16 KiB tile)
+
+// Host-path tuning knobs, read once from the environment (diagnostics / benchmarking only):
+//   DLTCUDA_CHUNK_MIB  chunk size of the copy pipeline, 1..16 MiB (default 16)
+//   DLTCUDA_STAGES     chunks in flight, 1..4 (default 4)
+//   DLTCUDA_ZEROCOPY   1 (default): SMALL page-locked caller buffers are read and written by the
+//                      kernel directly over the host link (one launch, lowest latency); 0: always use
+//                      the H2D -> kernel -> D2H copy pipeline
+//   DLTCUDA_ZEROCOPY_MAX_KIB  largest payload that takes the zero-copy path (default 4096)
+//   DLTCUDA_COPY_THREADS      threads used for staging copies of pageable caller memory
+struct HostPathConfig {
+    size_t chunk_bytes;
+    int stages;
+    bool zero_copy;
+    size_t zero_copy_max_bytes;
+};
+const HostPathConfig& host_path_config();
 
 struct Context {
     int device = -1;
