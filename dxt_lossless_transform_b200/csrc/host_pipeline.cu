@@ -15,7 +15,8 @@ namespace dlt {
 namespace {
 
 constexpr int kMaxDevices = 64;
-constexpr size_t kSlotBytes = kChunkBytes + 256 * kMaxStreams;
+constexpr size_t kSlotPad = 256 * kMaxStreams;
+constexpr size_t kStagingSlotBytes = kStagedChunkBytes + kSlotPad;
 
 std::mutex g_pool_mutex;
 Context* g_free[kMaxDevices] = {};
@@ -119,7 +120,7 @@ Status create_context(int device, Context** out) {
 
 const HostPathConfig& host_path_config() {
     static const HostPathConfig cfg = [] {
-        HostPathConfig c{kChunkBytes, kStages, true, (size_t)4 << 20};
+        HostPathConfig c{(size_t)32 << 20, kStages, true, (size_t)4 << 20};
         if (const char* v = std::getenv("DLTCUDA_CHUNK_MIB")) {
             const long mib = std::atol(v);
             if (mib >= 1 && (size_t)mib << 20 <= kChunkBytes) c.chunk_bytes = (size_t)mib << 20;
@@ -214,8 +215,8 @@ Status ensure_scratch(Context* ctx, size_t bytes) {
 
 Status ensure_staging(Context* ctx) {
     for (int i = 0; i < kStages; i++) {
-        if (!ctx->h_in[i]) DLT_CUDA(cudaMallocHost(&ctx->h_in[i], kSlotBytes));
-        if (!ctx->h_out[i]) DLT_CUDA(cudaMallocHost(&ctx->h_out[i], kSlotBytes));
+        if (!ctx->h_in[i]) DLT_CUDA(cudaMallocHost(&ctx->h_in[i], kStagingSlotBytes));
+        if (!ctx->h_out[i]) DLT_CUDA(cudaMallocHost(&ctx->h_out[i], kStagingSlotBytes));
     }
     return Status::kOk;
 }
@@ -239,13 +240,14 @@ struct Slots {
     uint8_t* streams[kStages];
 };
 
-Status ensure_slots(Context* ctx, Slots* s) {
+Status ensure_slots(Context* ctx, Slots* s, size_t chunk_bytes) {
     // d_in / d_out double as the slot arena: kStages slots each.
-    Status st = ensure_device_buffers(ctx, kSlotBytes * kStages);
+    const size_t slot = chunk_bytes + kSlotPad;
+    Status st = ensure_device_buffers(ctx, slot * kStages);
     if (st != Status::kOk) return st;
     for (int i = 0; i < kStages; i++) {
-        s->blocks[i] = ctx->d_in + kSlotBytes * i;
-        s->streams[i] = ctx->d_out + kSlotBytes * i;
+        s->blocks[i] = ctx->d_in + slot * i;
+        s->streams[i] = ctx->d_out + slot * i;
     }
     return Status::kOk;
 }
@@ -289,10 +291,14 @@ Status run_host(const Settings& st, bool inverse, const uint8_t* in, uint8_t* ou
         (void)cudaGetLastError();
     }
 
+    // chunk: big for page-locked buffers (fewer, larger DMA copies), one staging slot otherwise;
+    // never larger than the payload (rounded up to the kernel tile)
+    size_t chunk_bytes = in_pinned && out_pinned ? cfg.chunk_bytes : std::min(cfg.chunk_bytes, kStagedChunkBytes);
+    chunk_bytes = std::min(chunk_bytes, (len + (size_t)kTileBytes - 1) / kTileBytes * kTileBytes);
     Slots slots;
-    if ((status = ensure_slots(ctx, &slots)) != Status::kOk) return status;
+    if ((status = ensure_slots(ctx, &slots, chunk_bytes)) != Status::kOk) return status;
     const int stages = cfg.stages;
-    const size_t chunk_blocks = cfg.chunk_bytes / bpb;
+    const size_t chunk_blocks = chunk_bytes / bpb;
     const size_t nchunks = (n + chunk_blocks - 1) / chunk_blocks;
     int w[kMaxStreams], pre[kMaxStreams];
     for (int k = 0; k < ns; k++) {

@@ -19,10 +19,11 @@ namespace dlt {
 enum class Status : int { kOk = 0, kCudaError = 1, kOutOfMemory = 2 };
 
 constexpr int kStages = 4;                      // chunk slots (chunks in flight)
-constexpr size_t kChunkBytes = 16u << 20;       // bytes of blocks per chunk (multiple of the 16 KiB tile)
+constexpr size_t kChunkBytes = 64u << 20;       // largest chunk of the copy pipeline (multiple of the 16 KiB tile)
+constexpr size_t kStagedChunkBytes = 16u << 20; // chunk when caller memory is pageable (size of a pinned staging slot)
 
 // Host-path tuning knobs, read once from the environment (diagnostics / benchmarking only):
-//   DLTCUDA_CHUNK_MIB  chunk size of the copy pipeline, 1..16 MiB (default 16)
+//   DLTCUDA_CHUNK_MIB  chunk size of the copy pipeline for page-locked buffers, 1..64 MiB (default 32)
 //   DLTCUDA_STAGES     chunks in flight, 1..4 (default 4)
 //   DLTCUDA_ZEROCOPY   1 (default): SMALL page-locked caller buffers are read and written by the
 //                      kernel directly over the host link (one launch, lowest latency); 0: always use

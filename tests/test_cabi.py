@@ -242,3 +242,34 @@ def test_no_gpu_means_a_loud_error_not_a_fallback():
         dlt.Bc2ManualTransformBuilder().transform(data, np.zeros_like(data))
     assert e.value.code == 3
     assert api.device_count() == 0
+
+
+def test_cpp_host_header_links_and_validates(tmp_path):
+    """include/dxt_lossless_transform.hpp (the compiled host layer above the C ABI) builds against the
+    shared library and reports the reference's validation errors (no GPU needed for those)."""
+    src = tmp_path / "host.cpp"
+    src.write_text(r'''
+#include "dxt_lossless_transform.hpp"
+#include <cstdio>
+#include <vector>
+namespace dlt = dxt_lossless_transform;
+int main() {
+    std::vector<uint8_t> in(64), out(64);
+    int ok = 0;
+    try { dlt::transform_bc1_with_settings(in.data(), 7, out.data(), 64); } catch (const dlt::InvalidLength& e) { ok += e.length == 7; }
+    try { dlt::untransform_bc3_with_settings(in.data(), 32, out.data(), 16); } catch (const dlt::OutputBufferTooSmall& e) { ok += e.needed == 32 && e.actual == 16; }
+    try { dlt::transform_bc2_auto(in.data(), 17, out.data(), 64, nullptr); } catch (const dlt::DeviceError& e) { ok += e.core_code == 3; }
+    dlt::transform_bc2_with_settings(in.data(), 0, out.data(), 0);  // len 0 is a no-op
+    dlt::Bc3TransformSettings d;
+    ok += d.decorrelation_mode == dlt::YCoCgVariant::Variant1 && d.split_alpha_endpoints && d.split_colour_endpoints;
+    dlt::LosslessTransformUtilsSizeEstimation ltu;
+    ok += ltu.estimate_compressed_size(nullptr, 0) == 0;
+    std::printf("%d\n", ok);
+    return ok == 5 ? 0 : 1;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = N.LIB_PATH.parent
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", f"-I{INCLUDE}", str(src), "-o", str(exe), f"-L{libdir}",
+                    "-ldxt_lossless_transform_cuda", f"-Wl,-rpath,{libdir}"], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
