@@ -271,6 +271,33 @@ def run_gpu_arm(args) -> None:
             print(json.dumps({"profile_mode": True, "ms_per_step": ms_per_step, "value": value, "roofline": roofline}))
         return
 
+    # ---- the host link of this box, measured in the same run (denominator of the e2e number)
+    def link_gbs():
+        nbytes = min(shard_bytes, GIB)
+        h_a, h_b = torch.from_numpy(host_in.array[:nbytes]), torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def timed(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return nbytes * reps / (time.perf_counter() - t0) / 1e9
+
+        def both():
+            with torch.cuda.stream(s1):
+                d_t[:nbytes].copy_(h_a, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_b.copy_(d_back[:nbytes], non_blocking=True)
+
+        return {"h2d_gbs": timed(lambda: d_t[:nbytes].copy_(h_a, non_blocking=True)),
+                "d2h_gbs": timed(lambda: h_b.copy_(d_back[:nbytes], non_blocking=True)),
+                "bidir_gbs_per_direction": timed(both)}
+
+    host_link = link_gbs()
+
     # ---- end to end through the reference-facing C ABI: pinned HOST buffers, H2D + D2H in the timed region
     host_t, host_back = dlt.alloc_pinned(shard_bytes), dlt.alloc_pinned(shard_bytes)
     dlt.set_device(local_rank)
@@ -299,6 +326,9 @@ def run_gpu_arm(args) -> None:
         "d2h_bytes_per_step": 2 * shard_bytes * len(settings) * world,
         "steps": e2e_steps, "ms_per_step": e2e_s_per_step * 1e3,
         "host_link_gbs_per_direction": 2 * shard_bytes * len(settings) * world / e2e_s_per_step / 1e9,
+        "host_link_measured": host_link,
+        "frac_of_bidirectional_link": (2 * shard_bytes * len(settings) / e2e_s_per_step / 1e9)
+        / host_link["bidir_gbs_per_direction"],
         "api": "dltbc1core_transform / dltbc1core_untransform on pinned host buffers",
     }
 

@@ -61,6 +61,10 @@ class DltcudaSettings(C.Structure):
     ]
 
 
+class DltcudaPayload(C.Structure):
+    _fields_ = [("input", C.c_void_p), ("output", C.c_void_p), ("len", C.c_size_t), ("settings", DltcudaSettings)]
+
+
 # Every exported symbol: name -> (restype, argtypes).  tests/test_cabi_symbols.py checks this table
 # against include/*.h and against the built library.
 _P = C.c_void_p
@@ -116,6 +120,8 @@ SIGNATURES.update(
         "dltcuda_untransform_device_streams": (C.c_int, [C.POINTER(_P), _P, _SZ, DltcudaSettings, _P]),
         "dltcuda_stream_count": (C.c_int, [DltcudaSettings]),
         "dltcuda_stream_width": (C.c_int, [DltcudaSettings, C.c_int]),
+        "dltcuda_transform_batch": (C.c_int, [C.POINTER(DltcudaPayload), _SZ, C.c_bool]),
+        "dltcuda_transform_batch_multi_gpu": (C.c_int, [C.POINTER(DltcudaPayload), _SZ, C.c_bool, C.POINTER(C.c_int), C.c_int]),
         "dltcuda_shard_first_block": (_SZ, [C.c_int, _SZ, C.c_int, C.c_int]),
         "dltcuda_ltu_estimate_device": (C.c_int, [_P, _SZ, C.POINTER(_SZ)]),
         "dltcuda_transform_auto_device": (

@@ -513,6 +513,29 @@ def untransform_device_streams(fmt, d_streams, d_blocks, num_blocks, settings, s
     _check_device(N.lib().dltcuda_untransform_device_streams(arr, d_blocks, num_blocks, _dsettings(fmt, settings), stream))
 
 
+def transform_batch(items, untransform: bool = False, devices=None) -> None:
+    """items: iterable of (fmt, input buffer, output buffer, settings).  One pipelined pass over the whole
+    batch on the current device, or dealt out over `devices` (payload-granular multi-GPU)."""
+    items = list(items)
+    arr = (N.DltcudaPayload * max(len(items), 1))()
+    keep = []
+    for i, (fmt, src, dst, settings) in enumerate(items):
+        ip, il, ka = _ro(src)
+        op, ol, kb = _rw(dst)
+        if ol < il:
+            raise OutputBufferTooSmall(il, ol)
+        keep += [ka, kb]
+        arr[i] = N.DltcudaPayload(ip, op, il, _dsettings(fmt, settings))
+    if devices is None:
+        rc = N.lib().dltcuda_transform_batch(arr, len(items), untransform)
+    else:
+        dev = (C.c_int * len(devices))(*devices)
+        rc = N.lib().dltcuda_transform_batch_multi_gpu(arr, len(items), untransform, dev, len(devices))
+    if rc == 1:
+        raise InvalidLength(-1)
+    _check_device(rc)
+
+
 def shard_first_block(fmt: int, total_blocks: int, shard: int, num_shards: int) -> int:
     return N.lib().dltcuda_shard_first_block(fmt, total_blocks, shard, num_shards)
 

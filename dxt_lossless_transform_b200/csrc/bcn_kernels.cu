@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 4)
     }
     __syncthreads();
 
-    // ---- phase 3: stream every segment out; interior as 128-bit vectors, ragged edges bytewise
+    // ---- phase 3: stream every segment out; the 16-byte aligned interior as 128-bit vectors ...
 #pragma unroll
     for (int s = 0; s < L::NS; s++) {
         const int w = L::w(s);
@@ -259,16 +259,26 @@ __global__ void __launch_bounds__(kThreads, 4)
 #pragma unroll
         for (int it = 0; it < L::iters(s); it++) {
             const int k = it * kThreads + tid;
-            if (k < nch) {
-                const int lo = k << 4;
-                if (lo >= lo_valid && lo + 16 <= hi_valid) {
-                    stg_stream16(gal + lo, lds<uint4>(reg + lo));
-                } else {
-                    const int a = lo > lo_valid ? lo : lo_valid;
-                    const int b = lo + 16 < hi_valid ? lo + 16 : hi_valid;
-                    for (int i = a; i < b; i++) gal[i] = reg[i];
-                }
-            }
+            const int lo = k << 4;
+            if (k < nch && lo >= lo_valid && lo + 16 <= hi_valid) stg_stream16(gal + lo, lds<uint4>(reg + lo));
+        }
+    }
+    // ... and the ragged head / tail (< 16 bytes each, only when a stream base is not 16-byte aligned
+    // or the tile is the last one): warp s serves stream s, one byte per lane.
+    {
+        const int s = tid >> 5, lane = tid & 31;
+        if (s < L::NS) {
+            int w = 0, shs = 0, region = 0;
+            uint8_t* base = nullptr;
+#pragma unroll
+            for (int k = 0; k < L::NS; k++)
+                if (k == s) w = L::w(k), shs = sh[k], region = L::region(k), base = out.p[k];
+            const int lo_valid = shs, hi_valid = shs + w * nb;
+            const int head_end = min(hi_valid, (lo_valid + 15) & ~15);
+            const int tail_start = max(head_end, hi_valid & ~15);
+            const int i = lane < 16 ? lo_valid + lane : tail_start + lane - 16;
+            const bool on = lane < 16 ? i < head_end : i < hi_valid;
+            if (on) (base + (uint64_t)w * tile_first - shs)[i] = stage[region + i];
         }
     }
 }
@@ -303,16 +313,25 @@ __global__ void __launch_bounds__(kThreads, 4)
 #pragma unroll
         for (int it = 0; it < L::iters(s); it++) {
             const int k = it * kThreads + tid;
-            if (k < nch) {
-                const int lo = k << 4;
-                if (lo >= lo_valid && lo + 16 <= hi_valid) {
-                    cp_async16(reg + lo, gal + lo);
-                } else {
-                    const int a = lo > lo_valid ? lo : lo_valid;
-                    const int b = lo + 16 < hi_valid ? lo + 16 : hi_valid;
-                    for (int i = a; i < b; i++) reg[i] = gal[i];
-                }
-            }
+            const int lo = k << 4;
+            if (k < nch && lo >= lo_valid && lo + 16 <= hi_valid) cp_async16(reg + lo, gal + lo);
+        }
+    }
+    // ragged head / tail of every segment: warp s serves stream s, one byte per lane (all loads in flight)
+    {
+        const int s = tid >> 5, lane = tid & 31;
+        if (s < L::NS) {
+            int w = 0, shs = 0, region = 0;
+            const uint8_t* base = nullptr;
+#pragma unroll
+            for (int k = 0; k < L::NS; k++)
+                if (k == s) w = L::w(k), shs = sh[k], region = L::region(k), base = in.p[k];
+            const int lo_valid = shs, hi_valid = shs + w * nb;
+            const int head_end = min(hi_valid, (lo_valid + 15) & ~15);
+            const int tail_start = max(head_end, hi_valid & ~15);
+            const int i = lane < 16 ? lo_valid + lane : tail_start + lane - 16;
+            const bool on = lane < 16 ? i < head_end : i < hi_valid;
+            if (on) stage[region + i] = (base + (uint64_t)w * tile_first - shs)[i];
         }
     }
     cp_async_wait_all();

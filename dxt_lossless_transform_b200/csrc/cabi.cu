@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "auto_search.h"
 #include "bcn_kernels.h"
@@ -60,11 +62,19 @@ struct DltCoreBc3Settings {
     uint8_t decorrelation_mode;
 };
 // additive device API
+struct DltcudaPayload;
 struct DltcudaSettings {
     uint8_t format;              // 1, 2, 3
     uint8_t decorrelation_mode;  // internal numbering: None=0, Variant1=1, Variant2=2, Variant3=3
     bool split_alpha_endpoints;  // BC3 only
     bool split_colour_endpoints;
+};
+
+struct DltcudaPayload {  // one independent host payload of a batch
+    const uint8_t* input;
+    uint8_t* output;
+    size_t len;
+    DltcudaSettings settings;
 };
 
 }  // extern "C"
@@ -650,6 +660,48 @@ DLT_EXPORT size_t dltcuda_shard_first_block(int format, size_t total_blocks, int
     const size_t tiles = (total_blocks + tile - 1) / tile;
     const size_t first = tiles * (size_t)shard / (size_t)num_shards * tile;
     return first < total_blocks ? first : total_blocks;
+}
+
+// A batch of independent host payloads (mixed formats / settings), pipelined through the device(s):
+// chunks of consecutive payloads overlap and there is one wait at the end.  With several devices the
+// payloads are dealt out whole, largest-remaining-capacity first (payload-granular sharding: nothing
+// is exchanged between devices); one host thread drives each device.
+static int batch_impl(const DltcudaPayload* payloads, size_t count, bool untransform, const int* devices,
+                      int num_devices) {
+    if (count == 0) return kDltcudaOk;
+    if (!payloads || num_devices < 1) return kDltcudaNullPointer;
+    std::vector<std::vector<HostJob>> jobs((size_t)num_devices);
+    std::vector<size_t> load((size_t)num_devices, 0);
+    for (size_t i = 0; i < count; i++) {
+        Settings st;
+        if (!to_settings(payloads[i].settings, &st)) return kDltcudaInvalidSettings;
+        if (payloads[i].len % (size_t)block_bytes(st.format)) return kDltcudaInvalidLength;
+        if (payloads[i].len && (!payloads[i].input || !payloads[i].output)) return kDltcudaNullPointer;
+        size_t d = 0;
+        for (size_t k = 1; k < load.size(); k++)
+            if (load[k] < load[d]) d = k;
+        load[d] += payloads[i].len;
+        jobs[d].push_back(HostJob{st, untransform, payloads[i].input, payloads[i].output, payloads[i].len});
+    }
+    if (num_devices == 1)
+        return dltcuda_status(run_host_batch(jobs[0].data(), jobs[0].size(), devices ? devices[0] : -1));
+    std::vector<Status> results((size_t)num_devices, Status::kOk);
+    std::vector<std::thread> threads;
+    for (int d = 0; d < num_devices; d++)
+        threads.emplace_back([&, d] { results[d] = run_host_batch(jobs[d].data(), jobs[d].size(), devices[d]); });
+    for (auto& t : threads) t.join();
+    for (Status r : results)
+        if (r != Status::kOk) return dltcuda_status(r);
+    return kDltcudaOk;
+}
+
+DLT_EXPORT int dltcuda_transform_batch(const DltcudaPayload* payloads, size_t count, bool untransform) {
+    return batch_impl(payloads, count, untransform, nullptr, 1);
+}
+DLT_EXPORT int dltcuda_transform_batch_multi_gpu(const DltcudaPayload* payloads, size_t count, bool untransform,
+                                                 const int* devices, int num_devices) {
+    if (!devices) return kDltcudaNullPointer;
+    return batch_impl(payloads, count, untransform, devices, num_devices);
 }
 
 // LTU-semantics estimate of a device-resident byte range.  Synchronous.

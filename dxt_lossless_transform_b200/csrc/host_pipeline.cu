@@ -254,143 +254,188 @@ Status ensure_slots(Context* ctx, Slots* s, size_t chunk_bytes) {
 
 }  // namespace
 
-Status run_host(const Settings& st, bool inverse, const uint8_t* in, uint8_t* out, size_t len, int device) {
-    if (len == 0) return Status::kOk;
-    Status status;
-    Context* ctx = acquire_context(device, &status);
-    if (!ctx) return status;
-    struct Releaser {
-        Context* c;
-        ~Releaser() { release_context(c); }
-    } releaser{ctx};
+namespace {
 
-    const HostPathConfig& cfg = host_path_config();
-    const int bpb = block_bytes(st.format);
-    const int ns = num_streams(st.format, st.split_alpha, st.split_colour);
-    const size_t n = len / bpb;
-    const bool in_pinned = is_pinned_host(in) && is_pinned_host(in + len - 1);
-    const bool out_pinned = is_pinned_host(out) && is_pinned_host(out + len - 1);
+// One pass of host payloads through a context: every payload is cut into chunks, chunk i uses slot
+// (= CUDA stream) i % stages, so slot reuse is ordered on the device; the host only waits where it
+// has to touch a pinned staging slot again.
+class HostPipeline {
+public:
+    explicit HostPipeline(Context* ctx) : ctx_(ctx), cfg_(host_path_config()) {}
 
-    // Page-locked buffers on both sides: the kernel reads the blocks and writes the streams straight
-    // over the host link (mapped memory).  One launch, reads and writes overlap inside the kernel,
-    // the streams land at their final (possibly odd) offsets; nothing is staged in HBM.
-    if (cfg.zero_copy && len <= cfg.zero_copy_max_bytes && in_pinned && out_pinned) {
-        void *d_in = nullptr, *d_out = nullptr;
-        if (cudaHostGetDevicePointer(&d_in, const_cast<uint8_t*>(in), 0) == cudaSuccess &&
-            cudaHostGetDevicePointer(&d_out, out, 0) == cudaSuccess) {
-            cudaStream_t s = ctx->stream[0];
-            if (!inverse)
-                DLT_CUDA(launch_transform(st, static_cast<const uint8_t*>(d_in),
-                                          reference_layout(static_cast<uint8_t*>(d_out), n, 0, st), n, s));
-            else
-                DLT_CUDA(launch_untransform(st, reference_layout(static_cast<uint8_t*>(d_in), n, 0, st),
-                                            static_cast<uint8_t*>(d_out), n, s));
-            DLT_CUDA(cudaStreamSynchronize(s));
-            return Status::kOk;
+    // Largest chunk a job will use (slots must be sized before the first submit()).
+    size_t chunk_bytes_for(const HostJob& job, bool* in_pinned, bool* out_pinned) const {
+        *in_pinned = is_pinned_host(job.in) && is_pinned_host(job.in + job.len - 1);
+        *out_pinned = is_pinned_host(job.out) && is_pinned_host(job.out + job.len - 1);
+        size_t c = *in_pinned && *out_pinned ? cfg_.chunk_bytes : std::min(cfg_.chunk_bytes, kStagedChunkBytes);
+        return std::min(c, (job.len + (size_t)kTileBytes - 1) / kTileBytes * kTileBytes);
+    }
+
+    Status prepare(const HostJob* jobs, size_t count) {
+        size_t max_chunk = 0;
+        bool staged = false;
+        for (size_t i = 0; i < count; i++) {
+            if (jobs[i].len == 0) continue;
+            bool ip, op;
+            const size_t c = chunk_bytes_for(jobs[i], &ip, &op);
+            if (cfg_.zero_copy && jobs[i].len <= cfg_.zero_copy_max_bytes && ip && op) continue;
+            max_chunk = std::max(max_chunk, c);
+            staged |= !ip || !op;
         }
-        (void)cudaGetLastError();
+        if (max_chunk) {
+            const Status st = ensure_slots(ctx_, &slots_, max_chunk);
+            if (st != Status::kOk) return st;
+        }
+        return staged ? ensure_staging(ctx_) : Status::kOk;
     }
 
-    // chunk: big for page-locked buffers (fewer, larger DMA copies), one staging slot otherwise;
-    // never larger than the payload (rounded up to the kernel tile)
-    size_t chunk_bytes = in_pinned && out_pinned ? cfg.chunk_bytes : std::min(cfg.chunk_bytes, kStagedChunkBytes);
-    chunk_bytes = std::min(chunk_bytes, (len + (size_t)kTileBytes - 1) / kTileBytes * kTileBytes);
-    Slots slots;
-    if ((status = ensure_slots(ctx, &slots, chunk_bytes)) != Status::kOk) return status;
-    const int stages = cfg.stages;
-    const size_t chunk_blocks = chunk_bytes / bpb;
-    const size_t nchunks = (n + chunk_blocks - 1) / chunk_blocks;
-    int w[kMaxStreams], pre[kMaxStreams];
-    for (int k = 0; k < ns; k++) {
-        w[k] = stream_width(st.format, st.split_alpha, st.split_colour, k);
-        pre[k] = stream_prefix(st.format, st.split_alpha, st.split_colour, k);
-    }
+    Status submit(const HostJob& job) {
+        if (job.len == 0) return Status::kOk;
+        const Settings& st = job.st;
+        const int bpb = block_bytes(st.format);
+        const int ns = num_streams(st.format, st.split_alpha, st.split_colour);
+        const size_t n = job.len / bpb;
+        bool in_pinned, out_pinned;
+        const size_t chunk_bytes = chunk_bytes_for(job, &in_pinned, &out_pinned);
 
-    if (!in_pinned || !out_pinned)
-        if ((status = ensure_staging(ctx)) != Status::kOk) return status;
-
-    // Host offset of stream k, block b of the payload (reference layout); slot offset of the same
-    // element inside a chunk that starts at block b0.
-    auto host_off = [&](int k, size_t b) { return n * (size_t)pre[k] + (size_t)w[k] * b; };
-    auto slot_off = [&](int k) { return chunk_blocks * (size_t)pre[k]; };
-
-    auto issue = [&](size_t c) -> Status {
-        const int slot = (int)(c % stages);
-        cudaStream_t s = ctx->stream[slot];
-        const size_t b0 = c * chunk_blocks;
-        const size_t nb = n - b0 < chunk_blocks ? n - b0 : chunk_blocks;
-        StreamPtrs sp{};
-        for (int k = 0; k < ns; k++) sp.p[k] = slots.streams[slot] + slot_off(k);
-        if (!inverse) {
-            const uint8_t* src = in + b0 * bpb;
-            if (!in_pinned) {
-                staged_copy(ctx->h_in[slot], src, nb * bpb);
-                src = ctx->h_in[slot];
+        // Small page-locked payloads: the kernel reads the blocks and writes the streams straight over
+        // the host link (mapped memory) — one launch, no staging copies, lowest latency.
+        if (cfg_.zero_copy && job.len <= cfg_.zero_copy_max_bytes && in_pinned && out_pinned) {
+            void *d_in = nullptr, *d_out = nullptr;
+            if (cudaHostGetDevicePointer(&d_in, const_cast<uint8_t*>(job.in), 0) == cudaSuccess &&
+                cudaHostGetDevicePointer(&d_out, job.out, 0) == cudaSuccess) {
+                const int slot = (int)(seq_++ % cfg_.stages);
+                cudaStream_t s = ctx_->stream[slot];
+                if (!job.inverse)
+                    DLT_CUDA(launch_transform(st, static_cast<const uint8_t*>(d_in),
+                                              reference_layout(static_cast<uint8_t*>(d_out), n, 0, st), n, s));
+                else
+                    DLT_CUDA(launch_untransform(st, reference_layout(static_cast<uint8_t*>(d_in), n, 0, st),
+                                                static_cast<uint8_t*>(d_out), n, s));
+                return Status::kOk;
             }
-            DLT_CUDA(cudaMemcpyAsync(slots.blocks[slot], src, nb * bpb, cudaMemcpyHostToDevice, s));
-            DLT_CUDA(launch_transform(st, slots.blocks[slot], sp, nb, s));
-            for (int k = 0; k < ns; k++) {
-                uint8_t* dst = out_pinned ? out + host_off(k, b0) : ctx->h_out[slot] + slot_off(k);
-                DLT_CUDA(cudaMemcpyAsync(dst, sp.p[k], (size_t)w[k] * nb, cudaMemcpyDeviceToHost, s));
-            }
-        } else {
-            for (int k = 0; k < ns; k++) {
-                const uint8_t* src = in + host_off(k, b0);
+            (void)cudaGetLastError();
+        }
+
+        const size_t chunk_blocks = chunk_bytes / bpb;
+        const size_t nchunks = (n + chunk_blocks - 1) / chunk_blocks;
+        int w[kMaxStreams], pre[kMaxStreams];
+        for (int k = 0; k < ns; k++) {
+            w[k] = stream_width(st.format, st.split_alpha, st.split_colour, k);
+            pre[k] = stream_prefix(st.format, st.split_alpha, st.split_colour, k);
+        }
+        // Host offset of stream k, block b of the payload (reference layout); slot offset of the
+        // same stream inside a chunk (streams 256-byte aligned: chunk_blocks is a tile multiple).
+        auto host_off = [&](int k, size_t b) { return n * (size_t)pre[k] + (size_t)w[k] * b; };
+        auto slot_off = [&](int k) { return chunk_blocks * (size_t)pre[k]; };
+
+        for (size_t c = 0; c < nchunks; c++) {
+            const int slot = (int)(seq_++ % cfg_.stages);
+            Status f = finish(slot);
+            if (f != Status::kOk) return f;
+            cudaStream_t s = ctx_->stream[slot];
+            const size_t b0 = c * chunk_blocks;
+            const size_t nb = n - b0 < chunk_blocks ? n - b0 : chunk_blocks;
+            StreamPtrs sp{};
+            for (int k = 0; k < ns; k++) sp.p[k] = slots_.streams[slot] + slot_off(k);
+            Pending& pend = pending_[slot];
+            pend = Pending{};
+            if (!job.inverse) {
+                const uint8_t* src = job.in + b0 * bpb;
                 if (!in_pinned) {
-                    staged_copy(ctx->h_in[slot] + slot_off(k), src, (size_t)w[k] * nb);
-                    src = ctx->h_in[slot] + slot_off(k);
+                    staged_copy(ctx_->h_in[slot], src, nb * bpb);
+                    src = ctx_->h_in[slot];
                 }
-                DLT_CUDA(cudaMemcpyAsync(sp.p[k], src, (size_t)w[k] * nb, cudaMemcpyHostToDevice, s));
+                DLT_CUDA(cudaMemcpyAsync(slots_.blocks[slot], src, nb * bpb, cudaMemcpyHostToDevice, s));
+                DLT_CUDA(launch_transform(st, slots_.blocks[slot], sp, nb, s));
+                for (int k = 0; k < ns; k++) {
+                    uint8_t* dst = out_pinned ? job.out + host_off(k, b0) : ctx_->h_out[slot] + slot_off(k);
+                    DLT_CUDA(cudaMemcpyAsync(dst, sp.p[k], (size_t)w[k] * nb, cudaMemcpyDeviceToHost, s));
+                    if (!out_pinned) pend.copy[pend.ncopy++] = {job.out + host_off(k, b0), dst, (size_t)w[k] * nb};
+                }
+            } else {
+                for (int k = 0; k < ns; k++) {
+                    const uint8_t* src = job.in + host_off(k, b0);
+                    if (!in_pinned) {
+                        staged_copy(ctx_->h_in[slot] + slot_off(k), src, (size_t)w[k] * nb);
+                        src = ctx_->h_in[slot] + slot_off(k);
+                    }
+                    DLT_CUDA(cudaMemcpyAsync(sp.p[k], src, (size_t)w[k] * nb, cudaMemcpyHostToDevice, s));
+                }
+                DLT_CUDA(launch_untransform(st, sp, slots_.blocks[slot], nb, s));
+                uint8_t* dst = out_pinned ? job.out + b0 * bpb : ctx_->h_out[slot];
+                DLT_CUDA(cudaMemcpyAsync(dst, slots_.blocks[slot], nb * bpb, cudaMemcpyDeviceToHost, s));
+                if (!out_pinned) pend.copy[pend.ncopy++] = {job.out + b0 * bpb, dst, nb * bpb};
             }
-            DLT_CUDA(launch_untransform(st, sp, slots.blocks[slot], nb, s));
-            uint8_t* dst = out_pinned ? out + b0 * bpb : ctx->h_out[slot];
-            DLT_CUDA(cudaMemcpyAsync(dst, slots.blocks[slot], nb * bpb, cudaMemcpyDeviceToHost, s));
-        }
-        DLT_CUDA(cudaEventRecord(ctx->done[slot], s));
-        return Status::kOk;
-    };
-
-    auto finish = [&](size_t c) -> Status {
-        const int slot = (int)(c % stages);
-        DLT_CUDA(cudaEventSynchronize(ctx->done[slot]));
-        if (out_pinned) return Status::kOk;
-        const size_t b0 = c * chunk_blocks;
-        const size_t nb = n - b0 < chunk_blocks ? n - b0 : chunk_blocks;
-        if (!inverse) {
-            for (int k = 0; k < ns; k++)
-                staged_copy(out + host_off(k, b0), ctx->h_out[slot] + slot_off(k), (size_t)w[k] * nb);
-        } else {
-            staged_copy(out + b0 * bpb, ctx->h_out[slot], nb * bpb);
+            // The host has to wait for this chunk only if it must touch the slot's staging memory again.
+            pend.host_wait = !in_pinned || !out_pinned;
+            if (pend.host_wait) DLT_CUDA(cudaEventRecord(ctx_->done[slot], s));
         }
         return Status::kOk;
-    };
+    }
 
-    Status result = Status::kOk;
-    if (in_pinned && out_pinned) {
-        // Nothing for the host to stage: queue every chunk at once.  Chunk c shares its CUDA stream
-        // (= slot) with chunk c - stages, so slot reuse is ordered on the device and the copy engines
-        // never wait for the host.
-        for (size_t c = 0; c < nchunks && result == Status::kOk; c++) result = issue(c);
-        for (int i = 0; i < stages; i++) {
-            cudaError_t e = cudaStreamSynchronize(ctx->stream[i]);
+    Status drain() {
+        Status result = Status::kOk;
+        for (int i = 0; i < cfg_.stages; i++) {
+            // oldest first: slots are used round-robin starting at seq_ % stages
+            const Status f = finish((int)((seq_ + i) % cfg_.stages));
+            if (f != Status::kOk && result == Status::kOk) result = f;
+        }
+        for (int i = 0; i < kStages; i++) {
+            const cudaError_t e = cudaStreamSynchronize(ctx_->stream[i]);
             if (e != cudaSuccess && result == Status::kOk) note_cuda_error(e), result = Status::kCudaError;
         }
         return result;
     }
-    for (size_t c = 0; c < nchunks + stages; c++) {
-        if (c >= (size_t)stages && c - stages < nchunks) {
-            Status f = finish(c - stages);
-            if (f != Status::kOk && result == Status::kOk) result = f;
-        }
-        if (c < nchunks && result == Status::kOk) {
-            Status f = issue(c);
-            if (f != Status::kOk) result = f;
-        }
+
+private:
+    struct Pending {
+        bool host_wait = false;
+        int ncopy = 0;
+        struct {
+            uint8_t* dst;
+            const uint8_t* src;
+            size_t n;
+        } copy[kMaxStreams] = {};
+    };
+
+    Status finish(int slot) {
+        Pending& p = pending_[slot];
+        if (!p.host_wait) return Status::kOk;
+        p.host_wait = false;
+        DLT_CUDA(cudaEventSynchronize(ctx_->done[slot]));
+        for (int i = 0; i < p.ncopy; i++) staged_copy(p.copy[i].dst, p.copy[i].src, p.copy[i].n);
+        p.ncopy = 0;
+        return Status::kOk;
     }
-    if (result != Status::kOk) {
-        for (int i = 0; i < kStages; i++) (void)cudaStreamSynchronize(ctx->stream[i]);
-    }
-    return result;
+
+    Context* ctx_;
+    const HostPathConfig& cfg_;
+    Slots slots_{};
+    Pending pending_[kStages];
+    size_t seq_ = 0;
+};
+
+}  // namespace
+
+Status run_host_batch(const HostJob* jobs, size_t count, int device) {
+    bool any = false;
+    for (size_t i = 0; i < count; i++) any |= jobs[i].len != 0;
+    if (!any) return Status::kOk;
+    Status status;
+    Context* ctx = acquire_context(device, &status);
+    if (!ctx) return status;
+    HostPipeline pipe(ctx);
+    status = pipe.prepare(jobs, count);
+    for (size_t i = 0; i < count && status == Status::kOk; i++) status = pipe.submit(jobs[i]);
+    const Status d = pipe.drain();
+    release_context(ctx);
+    return status != Status::kOk ? status : d;
+}
+
+Status run_host(const Settings& st, bool inverse, const uint8_t* in, uint8_t* out, size_t len, int device) {
+    const HostJob job{st, inverse, in, out, len};
+    return run_host_batch(&job, 1, device);
 }
 
 }  // namespace dlt

@@ -65,6 +65,17 @@ Status ensure_staging(Context* ctx);
 // `out` holds the result.
 Status run_host(const Settings& st, bool inverse, const uint8_t* in, uint8_t* out, size_t len, int device);
 
+// A batch of independent payloads (a directory of textures) through ONE pipeline on one device: the
+// chunks of consecutive payloads overlap, there is a single wait at the end.
+struct HostJob {
+    Settings st;
+    bool inverse;
+    const uint8_t* in;
+    uint8_t* out;
+    size_t len;
+};
+Status run_host_batch(const HostJob* jobs, size_t count, int device);
+
 // The last CUDA error string seen by this thread (diagnostics only).
 const char* last_error_string();
 void note_cuda_error(cudaError_t e);

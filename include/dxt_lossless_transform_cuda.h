@@ -91,6 +91,24 @@ int dltcuda_stream_width(DltcudaSettings settings, int k);
  * side prefix of shard offsets, rounded to the kernel tile. */
 size_t dltcuda_shard_first_block(int format, size_t total_blocks, int shard, int num_shards);
 
+/* ---- batches of host payloads ---------------------------------------------------------------------- */
+/* The reference's CLI transforms a directory one file per rayon task
+ * (tools/dxt-lossless-transform-cli/src/commands/transform/mod.rs:154-176).  Here a batch of independent
+ * payloads (any mix of formats and settings; host pointers, same rules as the with-settings calls)
+ * goes through one pipeline per device: chunks of consecutive payloads overlap, one wait at the end.
+ * untransform = false: transform_bcN_with_settings on every payload; true: untransform_... */
+typedef struct DltcudaPayload {
+  const uint8_t *input;
+  uint8_t *output;
+  size_t len;
+  DltcudaSettings settings;
+} DltcudaPayload;
+int dltcuda_transform_batch(const DltcudaPayload *payloads, size_t count, bool untransform);
+/* Same, dealt out over several GPUs of one box at payload granularity (whole payloads, least-loaded
+ * device first; one host thread per device; nothing is exchanged between devices). */
+int dltcuda_transform_batch_multi_gpu(const DltcudaPayload *payloads, size_t count, bool untransform,
+                                      const int *devices, int num_devices);
+
 /* ---- estimator / best-settings search, device resident ------------------------------------------ */
 /* LTU-semantics estimate (dxt_lossless_transform_ltu.h) of `len` device bytes.  Synchronous. */
 int dltcuda_ltu_estimate_device(const uint8_t *d_data, size_t len, size_t *out_size);

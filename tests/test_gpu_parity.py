@@ -288,3 +288,35 @@ def test_one_gib_device_resident(dlt, torch, fmt):
     host = d_in.cpu().numpy()
     expect = oracle.transform(fmt, host, *orc_args(s), threads=16)
     assert np.array_equal(d_out.cpu().numpy(), expect)
+
+
+def test_batch_of_mixed_payloads(dlt, torch):
+    """A directory's worth of independent payloads (mixed BC1/BC2/BC3, mixed settings, pinned and pageable,
+    tiny to multi-chunk) through one pipelined pass; and dealt out over the visible GPUs."""
+    rng = np.random.default_rng(99)
+    items, expect, keep = [], [], []
+    sizes = [1, 7, 100, 4096, 70_001, 300_000, (20 << 20) // 16 + 5, 0, 2048, 33]
+    for i, nb in enumerate(sizes):
+        fmt = (1, 3, 2)[i % 3]
+        s = settings_list(dlt, fmt)[(5 * i) % len(settings_list(dlt, fmt))]
+        data = rng.integers(0, 256, nb * bpb(fmt), dtype=np.uint8)
+        if i % 2:
+            pin_in, pin_out = dlt.alloc_pinned(data.size), dlt.alloc_pinned(data.size)
+            pin_in.array[:] = data
+            src, dst = pin_in.array, pin_out.array
+            keep += [pin_in, pin_out]
+        else:
+            src, dst = data, np.zeros_like(data)
+        items.append((fmt, src, dst, s))
+        expect.append(oracle.transform(fmt, data, *orc_args(s)) if nb else data)
+    dlt.transform_batch(items)
+    for (fmt, src, dst, s), want in zip(items, expect):
+        assert np.array_equal(dst, want), (fmt, s, dst.size)
+    # the way back, over every visible GPU
+    back_items = [(fmt, dst.copy() if not isinstance(dst, np.ndarray) else dst, np.zeros(dst.size, np.uint8), s)
+                  for fmt, src, dst, s in items]
+    dlt.transform_batch(back_items, untransform=True, devices=list(range(torch.cuda.device_count())))
+    for (fmt, src, dst, s), (_, _, back, _) in zip(items, back_items):
+        assert np.array_equal(back, np.asarray(src)), (fmt, s)
+    with pytest.raises(dlt.api.InvalidLength):
+        dlt.transform_batch([(1, np.zeros(12, np.uint8), np.zeros(12, np.uint8), dlt.Bc1TransformSettings())])
