@@ -17,9 +17,10 @@
 //   * untransform mirrors it: 16-byte cp.async (LDGSTS) stream copies straight into shared memory ->
 //     per-thread gather -> recorrelate -> one 128-bit block store per thread and vector.
 //   * stream bases need not be 16-byte aligned (in the reference layout they sit at N*k bytes, and
-//     real mip chains give odd N): the staging area of stream s is shifted by (address & 15) so
-//     shared and global addresses are congruent mod 16; the aligned interior moves as 128-bit
-//     vectors and only the (at most two) ragged edge chunks of a segment move bytewise.
+//     real mip chains give odd N): the staging area of stream s is shifted by (address & 127) so
+//     shared and global addresses are congruent mod 128; the 16-byte aligned interior moves as
+//     128-bit vectors in whole 128-byte lines per warp and only the (at most two) ragged edges of a
+//     segment (< 16 bytes each) move bytewise.
 #include "bcn_kernels.h"
 
 #include <atomic>
@@ -30,6 +31,10 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;  // 128-bit vectors per thread per tile
+// Staging of stream s is shifted by (global address & 127): shared and global addresses are then
+// congruent mod 128, so 16-byte chunk k of a segment is the same chunk on both sides AND a warp's 32
+// consecutive chunks cover four whole 128-byte lines (no partially written sectors inside a tile).
+constexpr int kShiftAlign = 128;
 static_assert(kThreads * kUnroll * 16 == kTileBytes, "tile geometry");
 
 std::atomic<uint64_t> g_launches{0};
@@ -135,11 +140,11 @@ struct Lay {
     static constexpr int T = kTileBytes / BPB;    // blocks per tile
     static constexpr int BPV = 16 / BPB;          // blocks per 128-bit vector
     DLT_HD static constexpr int w(int s) { return stream_width(FMT, SA, SC, s); }
-    // Staging region of stream s: w*T payload bytes + 16 bytes of slack for the alignment shift.
-    DLT_HD static constexpr int region(int s) { return T * stream_prefix(FMT, SA, SC, s) + 16 * s; }
-    static constexpr int kStageBytes = kTileBytes + 16 * NS;
+    // Staging region of stream s: w*T payload bytes + kShiftAlign bytes of slack for the alignment shift.
+    DLT_HD static constexpr int region(int s) { return T * stream_prefix(FMT, SA, SC, s) + kShiftAlign * s; }
+    static constexpr int kStageBytes = kTileBytes + kShiftAlign * NS;
     // 128-bit chunks per stream segment of a full tile (+1 when the segment is shifted).
-    DLT_HD static constexpr int iters(int s) { return (w(s) * T / 16 + 1 + kThreads - 1) / kThreads; }
+    DLT_HD static constexpr int iters(int s) { return (w(s) * T / 16 + kShiftAlign / 16 + kThreads - 1) / kThreads; }
     // Stream indices of the logical fields.
     static constexpr int sAlpha = 0;                          // BC2 alpha:8 / BC3 a0a1:2 or a0:1
     static constexpr int sA1 = 1;                             // BC3 split alpha only
@@ -172,10 +177,10 @@ __global__ void __launch_bounds__(kThreads, 4)
     const uint64_t left = nblocks - tile_first;
     const int nb = left < (uint64_t)L::T ? (int)left : L::T;
 
-    // (address & 15) of each stream segment; w*T is a multiple of 16 so it is tile-independent.
+    // (address & 127) of each stream segment; w*T is a multiple of 128 so it is tile-independent.
     int sh[L::NS];
 #pragma unroll
-    for (int s = 0; s < L::NS; s++) sh[s] = (int)(reinterpret_cast<uintptr_t>(out.p[s]) & 15);
+    for (int s = 0; s < L::NS; s++) sh[s] = (int)(reinterpret_cast<uintptr_t>(out.p[s]) & (kShiftAlign - 1));
 
     // ---- phase 1: 4 coalesced 128-bit loads in flight per thread
     const uint8_t* tin = in + tile_first * L::BPB;
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 
     int sh[L::NS];
 #pragma unroll
-    for (int s = 0; s < L::NS; s++) sh[s] = (int)(reinterpret_cast<uintptr_t>(in.p[s]) & 15);
+    for (int s = 0; s < L::NS; s++) sh[s] = (int)(reinterpret_cast<uintptr_t>(in.p[s]) & (kShiftAlign - 1));
 
     // ---- phase 1: every stream segment of the tile goes global -> shared with 16-byte cp.async
     // (LDGSTS, L2-only caching): no staging registers, all copies of the tile in flight at once.

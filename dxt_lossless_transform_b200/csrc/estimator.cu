@@ -115,12 +115,13 @@ __global__ void __launch_bounds__(32) ltu_scan_filter_kernel(const SmallBatch ba
 // =================================================================================================
 constexpr int kMaxSegs = 16;
 constexpr int kTile = 8192;              // records per CTA tile
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kPerWarp = kTile / kSortWarps;     // contiguous records per warp
+constexpr int kPerWarp = kTile / kSortWarps;     // contiguous records per warp (scatter: warp-striped)
 constexpr int kSteps = kPerWarp / 32;            // records per thread
 constexpr int kRadix = 256;
 constexpr int kScanBlockElems = 4096;            // elements per block of the offset scan
+static_assert(kSteps == 16 && kTile / kSortThreads == 16, "16 records per thread");
 
 struct SortBatch {
     LtuSegment seg[kMaxSegs];
@@ -156,39 +157,8 @@ __device__ __forceinline__ int stage_bytes(const uint8_t* src, int need, uint8_t
     return sh;
 }
 
-// The 32 records (in stream order) a thread owns in its tile: warp w, step t, lane l <-> tile
-// index w*kPerWarp + t*32 + l.  PASS 0 builds them from the byte stream, PASS 1 reads pass-0 output.
-template <int PASS>
-__device__ __forceinline__ void load_tile_records(const SortBatch& b, int seg, uint32_t tile, int nvalid,
-                                                  uint8_t* stage, uint32_t (&rec)[kSteps]) {
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if constexpr (PASS == 0) {
-        const uint8_t* src = b.seg[seg].d_ptr + (size_t)tile * kTile;
-        const int sh = stage_bytes(src, nvalid + 2, stage);  // key(p) = bytes p, p+1, p+2
-        __syncthreads();
-#pragma unroll
-        for (int t = 0; t < kSteps; t++) {
-            const int i = warp * kPerWarp + t * 32 + lane;
-            uint32_t key = 0;
-            if (i < nvalid) {
-                const int a = sh + i;
-                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(stage + (a & ~3));
-                const uint32_t w1 = *reinterpret_cast<const uint32_t*>(stage + (a & ~3) + 4);
-                key = __funnelshift_r(w0, w1, 8 * (a & 3)) & kRecKeyMask;
-            }
-            const uint32_t nskip = group_nskip(ltu_bucket(key), lane);  // nvalid is a multiple of 4
-            rec[t] = key | (nskip << 24);
-        }
-    } else {
-        const uint32_t* src = b.rec_a[seg] + (size_t)tile * kTile;
-#pragma unroll
-        for (int t = 0; t < kSteps; t++) {
-            const int i = warp * kPerWarp + t * 32 + lane;
-            rec[t] = i < nvalid ? __ldg(src + i) : 0u;
-        }
-    }
-}
-
+// ---- tile histograms: 16 CONSECUTIVE records per thread, run-length aggregated shared atomics ------
+// (no ordering needed here, so no match_any; a flat texture gives one atomic per thread, not 16)
 template <int PASS>
 __global__ void __launch_bounds__(kSortThreads) ltu_hist_kernel(const SortBatch b) {
     const int seg = blockIdx.y;
@@ -196,23 +166,54 @@ __global__ void __launch_bounds__(kSortThreads) ltu_hist_kernel(const SortBatch 
     if (tile >= b.ntiles[seg]) return;
     __shared__ uint32_t hist[kRadix];
     __shared__ __align__(16) uint8_t stage[PASS == 0 ? kTile + 48 : 16];
-    hist[threadIdx.x] = 0;
+    if (threadIdx.x < kRadix) hist[threadIdx.x] = 0;
     const uint32_t left = b.npos[seg] - tile * kTile;
     const int nvalid = left < (uint32_t)kTile ? (int)left : kTile;
-    uint32_t rec[kSteps];
-    __syncthreads();
-    load_tile_records<PASS>(b, seg, tile, nvalid, stage, rec);
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int first = threadIdx.x * 16;
+    uint32_t digit[16];
+    if constexpr (PASS == 0) {
+        const int sh = stage_bytes(b.seg[seg].d_ptr + (size_t)tile * kTile, nvalid + 2, stage);
+        __syncthreads();
+        // bytes [first, first + 18) of the tile -> five byte-aligned words -> 16 three-byte keys
+        const int a = sh + first;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(stage + (a & ~3));
+        uint32_t raw[6], w[5];
 #pragma unroll
-    for (int t = 0; t < kSteps; t++) {
-        const int i = warp * kPerWarp + t * 32 + lane;
-        const bool valid = i < nvalid;
-        const uint32_t d = digit_of<PASS>(rec[t]);
-        const unsigned mask = __match_any_sync(kFull, valid ? d : (0x80000000u | lane));
-        if (valid && (mask >> lane) == 1u) atomicAdd(&hist[d], (uint32_t)__popc(mask));
+        for (int k = 0; k < 6; k++) raw[k] = wp[k];
+#pragma unroll
+        for (int k = 0; k < 5; k++) w[k] = __funnelshift_r(raw[k], raw[k + 1], 8 * (a & 3));
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const uint32_t key = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], 8 * (j & 3)) & kRecKeyMask;
+            digit[j] = ltu_bucket(key) & 0xFFu;
+        }
+    } else {
+        const uint4* src = reinterpret_cast<const uint4*>(b.rec_a[seg] + (size_t)tile * kTile + first);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (first + 4 * q < nvalid) v = __ldg(src + q);  // nvalid is a multiple of 4
+            digit[4 * q + 0] = digit_of<1>(v.x);
+            digit[4 * q + 1] = digit_of<1>(v.y);
+            digit[4 * q + 2] = digit_of<1>(v.z);
+            digit[4 * q + 3] = digit_of<1>(v.w);
+        }
     }
+    uint32_t run = 0, cur = digit[0];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (first + j < nvalid) {
+            if (digit[j] != cur) {
+                atomicAdd(&hist[cur], run);
+                cur = digit[j], run = 0;
+            }
+            run++;
+        }
+    }
+    if (run) atomicAdd(&hist[cur], run);
     __syncthreads();
-    b.cnt[seg][(size_t)threadIdx.x * b.ntiles[seg] + tile] = hist[threadIdx.x];
+    if (threadIdx.x < kRadix) b.cnt[seg][(size_t)threadIdx.x * b.ntiles[seg] + tile] = hist[threadIdx.x];
 }
 
 // ---- exclusive scan of cnt[seg][0 .. kRadix*ntiles) in three small launches ----------------------
@@ -286,26 +287,55 @@ __global__ void __launch_bounds__(256) ltu_scan_apply_kernel(const SortBatch b) 
 }
 
 // ---- stable scatter of one tile by the pass's digit -------------------------------------------------
+// Warp-striped: warp w owns tile records [w*kPerWarp, (w+1)*kPerWarp), lane l of step t holds record
+// w*kPerWarp + t*32 + l, so lane order inside a step is stream order and __match_any_sync ranks are stable.
 template <int PASS>
-__global__ void __launch_bounds__(kSortThreads) ltu_scatter_kernel(const SortBatch b) {
+__global__ void __launch_bounds__(kSortThreads, 2) ltu_scatter_kernel(const SortBatch b) {
     const int seg = blockIdx.y;
     const uint32_t tile = blockIdx.x;
     if (tile >= b.ntiles[seg]) return;
-    __shared__ uint32_t sorted[kTile];                  // the tile in digit order
-    __shared__ uint16_t warp_cnt[kSortWarps][kRadix];   // per-warp digit counts -> per-warp bases
+    // the byte staging of pass 0 is dead once the records are in registers: it shares `sorted`
+    __shared__ __align__(16) uint32_t sorted[kTile];     // the tile in digit order
+    __shared__ uint16_t warp_cnt[kSortWarps][kRadix];    // per-warp digit counts -> per-warp bases
     __shared__ uint32_t bin_start[kRadix], gofs[kRadix];
-    __shared__ uint32_t wsum[kSortWarps];
-    __shared__ __align__(16) uint8_t stage[PASS == 0 ? kTile + 48 : 16];
+    __shared__ uint32_t wsum[kRadix / 32];
+    uint8_t* stage = reinterpret_cast<uint8_t*>(sorted);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&warp_cnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < kSortWarps * kRadix / 2; i += kSortThreads)
+        reinterpret_cast<uint32_t*>(&warp_cnt[0][0])[i] = 0;
     const uint32_t left = b.npos[seg] - tile * kTile;
     const int nvalid = left < (uint32_t)kTile ? (int)left : kTile;
-    uint32_t rec[kSteps];
-    uint16_t rank[kSteps];
-    __syncthreads();
-    load_tile_records<PASS>(b, seg, tile, nvalid, stage, rec);
 
-    // rank of every record among the records of its warp with the same digit (stream order)
+    uint32_t rec[kSteps];
+    if constexpr (PASS == 0) {
+        const int sh = stage_bytes(b.seg[seg].d_ptr + (size_t)tile * kTile, nvalid + 2, stage);  // key(p) = bytes p..p+2
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < kSteps; t++) {
+            const int i = warp * kPerWarp + t * 32 + lane;
+            uint32_t key = 0;
+            if (i < nvalid) {
+                const int a = sh + i;
+                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(stage + (a & ~3));
+                const uint32_t w1 = *reinterpret_cast<const uint32_t*>(stage + (a & ~3) + 4);
+                key = __funnelshift_r(w0, w1, 8 * (a & 3)) & kRecKeyMask;
+            }
+            rec[t] = key | (group_nskip(ltu_bucket(key), lane) << 24);  // nvalid is a multiple of 4
+        }
+        __syncthreads();  // everyone is done reading `stage` before `sorted` is written
+    } else {
+        const uint32_t* src = b.rec_a[seg] + (size_t)tile * kTile;
+#pragma unroll
+        for (int t = 0; t < kSteps; t++) {
+            const int i = warp * kPerWarp + t * 32 + lane;
+            rec[t] = i < nvalid ? __ldg(src + i) : 0u;
+        }
+        __syncthreads();
+    }
+
+    // rank of every record among the records of its warp with the same digit (stream order);
+    // meta = digit | rank << 8
+    uint32_t meta[kSteps];
 #pragma unroll
     for (int t = 0; t < kSteps; t++) {
         const int i = warp * kPerWarp + t * 32 + lane;
@@ -313,34 +343,36 @@ __global__ void __launch_bounds__(kSortThreads) ltu_scatter_kernel(const SortBat
         const uint32_t d = digit_of<PASS>(rec[t]);
         const unsigned mask = __match_any_sync(kFull, valid ? d : (0x80000000u | lane));
         const uint32_t before = valid ? warp_cnt[warp][d] : 0;
-        rank[t] = (uint16_t)(before + __popc(mask & ((1u << lane) - 1u)));
+        meta[t] = d | ((before + __popc(mask & ((1u << lane) - 1u))) << 8);
         __syncwarp();
         if (valid && (mask >> lane) == 1u) warp_cnt[warp][d] = (uint16_t)(before + __popc(mask));
         __syncwarp();
     }
     __syncthreads();
 
-    // thread d: per-warp bases of digit d, the tile's digit histogram and its exclusive scan
-    {
+    // thread d < 256: per-warp bases of digit d, the tile's digit histogram and its exclusive scan
+    uint32_t tot = 0, inc = 0;
+    if (threadIdx.x < kRadix) {
         const int d = threadIdx.x;
-        uint32_t tot = 0;
 #pragma unroll
         for (int w = 0; w < kSortWarps; w++) {
             const uint32_t c = warp_cnt[w][d];
             warp_cnt[w][d] = (uint16_t)tot;
             tot += c;
         }
-        uint32_t inc = tot;
+        inc = tot;
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t up = __shfl_up_sync(kFull, inc, o);
             if ((int)lane >= o) inc += up;
         }
         if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x < kRadix) {
         uint32_t off = inc - tot;
         for (int w = 0; w < (int)warp; w++) off += wsum[w];
-        bin_start[d] = off;
-        gofs[d] = b.cnt[seg][(size_t)d * b.ntiles[seg] + tile];
+        bin_start[threadIdx.x] = off;
+        gofs[threadIdx.x] = b.cnt[seg][(size_t)threadIdx.x * b.ntiles[seg] + tile];
     }
     __syncthreads();
 
@@ -348,8 +380,8 @@ __global__ void __launch_bounds__(kSortThreads) ltu_scatter_kernel(const SortBat
     for (int t = 0; t < kSteps; t++) {
         const int i = warp * kPerWarp + t * 32 + lane;
         if (i < nvalid) {
-            const uint32_t d = digit_of<PASS>(rec[t]);
-            sorted[bin_start[d] + warp_cnt[warp][d] + rank[t]] = rec[t];
+            const uint32_t d = meta[t] & 0xFFu;
+            sorted[bin_start[d] + warp_cnt[warp][d] + (meta[t] >> 8)] = rec[t];
         }
     }
     __syncthreads();
@@ -369,15 +401,20 @@ __global__ void __launch_bounds__(256) ltu_compare_kernel(const SortBatch b, uns
     const uint32_t n = b.npos[seg];
     const uint32_t* rec = b.rec_b[seg];
     uint32_t count = 0;
-    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
-        const uint32_t r = __ldg(rec + i);
-        const uint32_t key = r & kRecKeyMask, nskip = r >> 24;
+    const unsigned lane = threadIdx.x & 31;
+    // warp-uniform trip count; the predecessor (<= 4 records back) comes from a lower lane by shuffle,
+    // only the first lanes of a warp go back to memory
+    for (uint32_t base = blockIdx.x * 256u + (threadIdx.x & ~31u); base < n; base += gridDim.x * 256u) {
+        const uint32_t i = base + lane;
+        const uint32_t r = i < n ? __ldg(rec + i) : 0u;
+        const uint32_t key = r & kRecKeyMask, back = (r >> 24) + 1u;
+        uint32_t q = __shfl_sync(kFull, r, (lane - back) & 31u);
+        bool have = i < n && i >= back;
+        if (have && lane < back) q = __ldg(rec + (i - back));
+        q &= kRecKeyMask;
         uint32_t cmp = 0;  // an untouched bucket holds 0
-        if (i > nskip) {
-            const uint32_t q = __ldg(rec + (i - 1u - nskip)) & kRecKeyMask;
-            if (ltu_bucket(q) == ltu_bucket(key)) cmp = q;
-        }
-        count += key == cmp;
+        if (have && ltu_bucket(q) == ltu_bucket(key)) cmp = q;
+        count += (i < n) && key == cmp;
     }
     for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(kFull, count, o);
     __shared__ uint32_t ws[8];
