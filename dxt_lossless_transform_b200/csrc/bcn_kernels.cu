@@ -167,7 +167,7 @@ __device__ __forceinline__ T lds(const uint8_t* p) {
 // Tiled transform kernel
 // ------------------------------------------------------------------------------------------------
 template <int FMT, bool SA, bool SC, int VAR>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 6)
     transform_tiled(const uint8_t* __restrict__ in, const StreamPtrs out, const uint64_t nblocks) {
     using L = Lay<FMT, SA, SC>;
     __shared__ __align__(16) uint8_t stage[L::kStageBytes];
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 // Tiled untransform kernel
 // ------------------------------------------------------------------------------------------------
 template <int FMT, bool SA, bool SC, int VAR>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 6)
     untransform_tiled(const StreamPtrs in, uint8_t* __restrict__ out, const uint64_t nblocks) {
     using L = Lay<FMT, SA, SC>;
     __shared__ __align__(16) uint8_t stage[L::kStageBytes];

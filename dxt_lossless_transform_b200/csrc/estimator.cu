@@ -10,7 +10,7 @@
 // next to each other in stream order:
 //   record(p) = key(p) | nskip(p) << 24,   nskip = same-bucket positions before p inside p's group of 4
 //   stable sort of the records by bucket (LSD radix, 2 x 8 bits, hand-written: per-tile shared-memory
-//   histograms, warp-aggregated ranks with __match_any_sync, one exclusive scan per pass)
+//   histograms, stable warp ranks from ballot-built match masks, one exclusive scan per pass)
 //   match(i) <=> key(rec[i]) == (bucket(rec[i-1-nskip]) == bucket(rec[i]) ? key(rec[i-1-nskip]) : 0)
 // which is embarrassingly parallel and has no data-dependent skew (a flat texture puts every
 // position in one bucket; a per-bucket sequential consumer would serialise on it).
@@ -20,6 +20,7 @@
 // implementation in the tests.
 #include "estimator.h"
 
+#include <algorithm>
 #include <atomic>
 
 namespace dlt {
@@ -37,6 +38,21 @@ __host__ __device__ inline size_t ltu_positions(size_t len) {
 }
 
 __device__ __forceinline__ uint32_t ltu_bucket(uint32_t key) { return (key * kLtuGoldenRatio) >> (32 - kLtuHashBits); }
+
+// Lanes that are valid and hold the same BITS-bit value as the calling lane.  Built from BITS ballots:
+// constant cost, whereas MATCH.ANY slows down with the number of distinct values in the warp (measured:
+// ~400 cycles per call on random 8-bit digits, which made the first version of the scatter 15x slower).
+template <int BITS>
+__device__ __forceinline__ unsigned match_bits(uint32_t v, bool valid) {
+    unsigned mask = __ballot_sync(kFull, valid);
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const bool bit = (v >> b) & 1u;
+        const unsigned bal = __ballot_sync(kFull, bit);
+        mask &= bit ? bal : ~bal;
+    }
+    return mask;
+}
 
 // nskip for the 32 consecutive positions held by a warp (groups of 4 are lane-aligned).
 __device__ __forceinline__ uint32_t group_nskip(uint32_t bucket, unsigned lane) {
@@ -57,11 +73,16 @@ struct SmallBatch {
     LtuSegment s[kMaxSegsSmall];
 };
 
+constexpr int kScanGroups = 64;
+constexpr int kScanBucketBits = kLtuHashBits - 6;
+constexpr int kScanBuckets = 1 << kScanBucketBits;
+static_assert(kScanGroups * kScanBuckets == (1 << kLtuHashBits), "bucket groups");
+
 // One warp step over up to 32 positions of this warp's bucket range, in stream order by lane.
 __device__ __forceinline__ int consume_step(bool valid, uint32_t b, uint32_t key, int nskip, uint32_t* t_last,
                                             uint32_t* t_base) {
     const unsigned lane = threadIdx.x & 31;
-    const unsigned mask = __match_any_sync(kFull, valid ? b : (0x80000000u | lane));
+    const unsigned mask = match_bits<kScanBucketBits>(b, valid);
     const unsigned lower = mask & ((1u << lane) - 1u);
     const int r = __popc(lower);
     unsigned m = lower;
@@ -84,8 +105,6 @@ __device__ __forceinline__ int consume_step(bool valid, uint32_t b, uint32_t key
     return __popc(__ballot_sync(kFull, match));
 }
 
-constexpr int kScanGroups = 64;
-constexpr int kScanBuckets = (1 << kLtuHashBits) / kScanGroups;
 
 __global__ void __launch_bounds__(32) ltu_scan_filter_kernel(const SmallBatch batch, unsigned long long* matches) {
     __shared__ uint32_t t_last[kScanBuckets], t_base[kScanBuckets];
@@ -288,7 +307,7 @@ __global__ void __launch_bounds__(256) ltu_scan_apply_kernel(const SortBatch b) 
 
 // ---- stable scatter of one tile by the pass's digit -------------------------------------------------
 // Warp-striped: warp w owns tile records [w*kPerWarp, (w+1)*kPerWarp), lane l of step t holds record
-// w*kPerWarp + t*32 + l, so lane order inside a step is stream order and __match_any_sync ranks are stable.
+// w*kPerWarp + t*32 + l, so lane order inside a step is stream order and the match-mask ranks are stable.
 template <int PASS>
 __global__ void __launch_bounds__(kSortThreads, 2) ltu_scatter_kernel(const SortBatch b) {
     const int seg = blockIdx.y;
@@ -341,7 +360,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) ltu_scatter_kernel(const Sort
         const int i = warp * kPerWarp + t * 32 + lane;
         const bool valid = i < nvalid;
         const uint32_t d = digit_of<PASS>(rec[t]);
-        const unsigned mask = __match_any_sync(kFull, valid ? d : (0x80000000u | lane));
+        const unsigned mask = match_bits<8>(d, valid);
         const uint32_t before = valid ? warp_cnt[warp][d] : 0;
         meta[t] = d | ((before + __popc(mask & ((1u << lane) - 1u))) << 8);
         __syncwarp();
@@ -516,7 +535,7 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
                 b.cnt[k] = reinterpret_cast<uint32_t*>(p), p += pl.cnt_bytes;
                 b.blk[k] = reinterpret_cast<uint32_t*>(p), p += pl.blk_bytes;
                 const uint32_t sblk = (uint32_t)((pl.ntiles * kRadix + kScanBlockElems - 1) / kScanBlockElems);
-                const uint32_t cblk = (uint32_t)((pl.npos + 1023) / 1024);  // 4 records per thread
+                const uint32_t cblk = (uint32_t)std::min<size_t>((pl.npos + 255) / 256, 148 * 8);  // grid-stride
                 max_tiles = pl.ntiles > max_tiles ? (uint32_t)pl.ntiles : max_tiles;
                 max_scan_blocks = sblk > max_scan_blocks ? sblk : max_scan_blocks;
                 max_cmp_blocks = cblk > max_cmp_blocks ? cblk : max_cmp_blocks;
