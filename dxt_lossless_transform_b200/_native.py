@@ -120,6 +120,8 @@ SIGNATURES.update(
         "dltcuda_untransform_device_streams": (C.c_int, [C.POINTER(_P), _P, _SZ, DltcudaSettings, _P]),
         "dltcuda_stream_count": (C.c_int, [DltcudaSettings]),
         "dltcuda_stream_width": (C.c_int, [DltcudaSettings, C.c_int]),
+        "dltcuda_split_color_endpoints_device": (C.c_int, [_P, _P, _SZ, _P]),
+        "dltcuda_split_color_endpoints": (C.c_int, [_P, _P, _SZ]),
         "dltcuda_transform_batch": (C.c_int, [C.POINTER(DltcudaPayload), _SZ, C.c_bool]),
         "dltcuda_transform_batch_multi_gpu": (C.c_int, [C.POINTER(DltcudaPayload), _SZ, C.c_bool, C.POINTER(C.c_int), C.c_int]),
         "dltcuda_shard_first_block": (_SZ, [C.c_int, _SZ, C.c_int, C.c_int]),

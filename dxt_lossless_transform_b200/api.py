@@ -513,6 +513,22 @@ def untransform_device_streams(fmt, d_streams, d_blocks, num_blocks, settings, s
     _check_device(N.lib().dltcuda_untransform_device_streams(arr, d_blocks, num_blocks, _dsettings(fmt, settings), stream))
 
 
+def split_color_endpoints(colors, colors_out) -> None:
+    """split_565_color_endpoints::split_color_endpoints on host buffers: [c0 c1] x n -> c0 x n | c1 x n."""
+    ip, il, _ka = _ro(colors)
+    op, ol, _kb = _rw(colors_out)
+    if ol < il:
+        raise OutputBufferTooSmall(il, ol)
+    rc = N.lib().dltcuda_split_color_endpoints(ip, op, il)
+    if rc == 1:
+        raise InvalidLength(il)
+    _check_device(rc)
+
+
+def split_color_endpoints_device(d_colors: int, d_colors_out: int, nbytes: int, stream: int = 0) -> None:
+    _check_device(N.lib().dltcuda_split_color_endpoints_device(d_colors, d_colors_out, nbytes, stream))
+
+
 def transform_batch(items, untransform: bool = False, devices=None) -> None:
     """items: iterable of (fmt, input buffer, output buffer, settings).  One pipelined pass over the whole
     batch on the current device, or dealt out over `devices` (payload-granular multi-GPU)."""

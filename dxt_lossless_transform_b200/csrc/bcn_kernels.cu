@@ -470,6 +470,29 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// split_color_endpoints: [c0 c1] x n  ->  c0 x n | c1 x n
+// (common/src/transforms/split_565_color_endpoints/portable32.rs:18-64; the colour part of the BC1
+// split layout on its own).  One 128-bit load = 4 pairs per thread, two coalesced 64-bit stores.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    split_endpoints_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ c0, uint8_t* __restrict__ c1,
+                           const uint64_t npairs, const bool vector_ok) {
+    const uint64_t q = (uint64_t)blockIdx.x * kThreads + threadIdx.x;  // group of 4 pairs
+    const uint64_t first = q * 4;
+    if (first >= npairs) return;
+    if (vector_ok && first + 4 <= npairs) {
+        const uint4 v = ldg_stream16(in + first * 4);
+        stg_stream8(c0 + first * 2, make_uint2(__byte_perm(v.x, v.y, 0x5410), __byte_perm(v.z, v.w, 0x5410)));
+        stg_stream8(c1 + first * 2, make_uint2(__byte_perm(v.x, v.y, 0x7632), __byte_perm(v.z, v.w, 0x7632)));
+    } else {
+        for (uint64_t i = first; i < first + 4 && i < npairs; i++) {
+            c0[2 * i] = in[4 * i], c0[2 * i + 1] = in[4 * i + 1];
+            c1[2 * i] = in[4 * i + 2], c1[2 * i + 1] = in[4 * i + 3];
+        }
+    }
+}
+
 template <int FMT, bool SA, bool SC>
 RtLayout make_rt_layout(int var) {
     using L = Lay<FMT, SA, SC>;
@@ -565,6 +588,19 @@ cudaError_t launch_transform(const Settings& st, const uint8_t* in, const Stream
 cudaError_t launch_untransform(const Settings& st, const StreamPtrs& in, uint8_t* out, uint64_t nblocks,
                                cudaStream_t stream) {
     return dispatch(st, true, nullptr, out, in, nblocks, stream);
+}
+
+cudaError_t launch_split_color_endpoints(const uint8_t* in, uint8_t* out, uint64_t len_bytes, cudaStream_t stream) {
+    const uint64_t npairs = len_bytes / 4;
+    if (npairs == 0) return cudaSuccess;
+    uint8_t* c1 = out + len_bytes / 2;
+    const bool vector_ok = !(reinterpret_cast<uintptr_t>(in) & 15) && !(reinterpret_cast<uintptr_t>(out) & 7) &&
+                           !(reinterpret_cast<uintptr_t>(c1) & 7);
+    const uint64_t ctas = ((npairs + 3) / 4 + kThreads - 1) / kThreads;
+    if (ctas > 0x7fffffffull) return cudaErrorInvalidValue;
+    split_endpoints_kernel<<<(unsigned)ctas, kThreads, 0, stream>>>(in, out, c1, npairs, vector_ok);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
 }
 
 uint64_t kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }

@@ -17,6 +17,9 @@ cudaError_t launch_transform(const Settings& st, const uint8_t* in, const Stream
 cudaError_t launch_untransform(const Settings& st, const StreamPtrs& in, uint8_t* out, uint64_t nblocks,
                                cudaStream_t stream);
 
+// split_color_endpoints: [c0 c1] x n (len_bytes = 4n) -> c0 x n | c1 x n at out and out + len_bytes/2.
+cudaError_t launch_split_color_endpoints(const uint8_t* in, uint8_t* out, uint64_t len_bytes, cudaStream_t stream);
+
 // Number of kernel launches the two functions above have issued in this process (bench evidence).
 uint64_t kernel_launch_count();
 

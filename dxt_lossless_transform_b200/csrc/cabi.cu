@@ -662,6 +662,35 @@ DLT_EXPORT size_t dltcuda_shard_first_block(int format, size_t total_blocks, int
     return first < total_blocks ? first : total_blocks;
 }
 
+// split_color_endpoints on device-resident colour pairs (len_bytes % 4 == 0).  Asynchronous on `stream`.
+DLT_EXPORT int dltcuda_split_color_endpoints_device(const uint8_t* d_colors, uint8_t* d_colors_out, size_t len_bytes,
+                                                    void* stream) {
+    if (len_bytes % 4) return kDltcudaInvalidLength;
+    if (len_bytes == 0) return kDltcudaOk;
+    if (!d_colors || !d_colors_out) return kDltcudaNullPointer;
+    return dltcuda_status(launch_split_color_endpoints(d_colors, d_colors_out, len_bytes, (cudaStream_t)stream));
+}
+// The same on host buffers (synchronous).
+DLT_EXPORT int dltcuda_split_color_endpoints(const uint8_t* colors, uint8_t* colors_out, size_t len_bytes) {
+    if (len_bytes % 4) return kDltcudaInvalidLength;
+    if (len_bytes == 0) return kDltcudaOk;
+    if (!colors || !colors_out) return kDltcudaNullPointer;
+    Status st;
+    Context* ctx = acquire_context(-1, &st);
+    if (!ctx) return dltcuda_status(st);
+    st = ensure_device_buffers(ctx, len_bytes);
+    cudaError_t e = cudaSuccess;
+    if (st == Status::kOk) {
+        cudaStream_t s = ctx->stream[0];
+        e = cudaMemcpyAsync(ctx->d_in, colors, len_bytes, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = launch_split_color_endpoints(ctx->d_in, ctx->d_out, len_bytes, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(colors_out, ctx->d_out, len_bytes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    release_context(ctx);
+    return st != Status::kOk ? dltcuda_status(st) : dltcuda_status(e);
+}
+
 // A batch of independent host payloads (mixed formats / settings), pipelined through the device(s):
 // chunks of consecutive payloads overlap and there is one wait at the end.  With several devices the
 // payloads are dealt out whole, largest-remaining-capacity first (payload-granular sharding: nothing

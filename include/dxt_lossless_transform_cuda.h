@@ -91,6 +91,14 @@ int dltcuda_stream_width(DltcudaSettings settings, int k);
  * side prefix of shard offsets, rounded to the kernel tile. */
 size_t dltcuda_shard_first_block(int format, size_t total_blocks, int shard, int num_shards);
 
+/* ---- split_color_endpoints ----------------------------------------------------------------------- */
+/* split_color_endpoints (core/dxt-lossless-transform-common/src/transforms/split_565_color_endpoints/mod.rs,
+ * portable32.rs:18-64): [c0 c1] x n -> c0 x n | c1 x n; len_bytes = 4n.  Device pointers + stream, or
+ * host pointers (synchronous). */
+int dltcuda_split_color_endpoints_device(const uint8_t *d_colors, uint8_t *d_colors_out,
+                                         size_t len_bytes, void *stream);
+int dltcuda_split_color_endpoints(const uint8_t *colors, uint8_t *colors_out, size_t len_bytes);
+
 /* ---- batches of host payloads ---------------------------------------------------------------------- */
 /* The reference's CLI transforms a directory one file per rayon task
  * (tools/dxt-lossless-transform-cli/src/commands/transform/mod.rs:154-176).  Here a batch of independent

@@ -320,3 +320,30 @@ def test_batch_of_mixed_payloads(dlt, torch):
         assert np.array_equal(back, np.asarray(src)), (fmt, s)
     with pytest.raises(dlt.api.InvalidLength):
         dlt.transform_batch([(1, np.zeros(12, np.uint8), np.zeros(12, np.uint8), dlt.Bc1TransformSettings())])
+
+
+def test_split_color_endpoints(dlt, torch):
+    """common/src/transforms/split_565_color_endpoints/tests.rs: golden vector, 1..=512 pairs aligned and
+    unaligned against the portable reference implementation."""
+    src = np.frombuffer(bytes.fromhex(KNOWN["split_565"]["in"]), np.uint8).copy()
+    dst = np.zeros_like(src)
+    dlt.split_color_endpoints(src, dst)
+    assert dst.tobytes().hex() == KNOWN["split_565"]["out"]
+    rng = np.random.default_rng(4)
+    for pairs in list(range(1, 513)) + [100_001]:
+        data = rng.integers(0, 256, pairs * 4, dtype=np.uint8)
+        want = np.zeros_like(data)
+        oracle.lib().orc_split_color_endpoints(data.ctypes.data, want.ctypes.data, data.size)
+        got = np.zeros_like(data)
+        dlt.split_color_endpoints(data, got)
+        assert np.array_equal(got, want), pairs
+        if pairs % 37 == 0 or pairs > 512:
+            for off in (0, 1):
+                d_in = torch.zeros(data.size + 16, dtype=torch.uint8, device="cuda")
+                d_in[off:off + data.size] = torch.from_numpy(data).cuda()
+                d_out = torch.zeros(data.size + 16, dtype=torch.uint8, device="cuda")
+                dlt.split_color_endpoints_device(d_in.data_ptr() + off, d_out.data_ptr() + off, data.size)
+                torch.cuda.synchronize()
+                assert np.array_equal(d_out.cpu().numpy()[off:off + data.size], want)
+    with pytest.raises(dlt.api.InvalidLength):
+        dlt.split_color_endpoints(np.zeros(6, np.uint8), np.zeros(6, np.uint8))
