@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libdxt_lossless_transform_cuda.so"
+import os
+
+# DLT_LIB_PATH lets experiments load an alternative build of the same library (never a CPU fallback).
+LIB_PATH = Path(os.environ.get("DLT_LIB_PATH") or Path(__file__).resolve().parent / "libdxt_lossless_transform_cuda.so")
 
 _lib = None
 

@@ -29,12 +29,18 @@
 namespace dlt {
 namespace {
 
+#ifndef DLT_MIN_CTAS
+#define DLT_MIN_CTAS 6  // resident CTAs per SM the tiled kernels are compiled for (register cap 40)
+#endif
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;  // 128-bit vectors per thread per tile
 // Staging of stream s is shifted by (global address & 127): shared and global addresses are then
 // congruent mod 128, so 16-byte chunk k of a segment is the same chunk on both sides AND a warp's 32
 // consecutive chunks cover four whole 128-byte lines (no partially written sectors inside a tile).
-constexpr int kShiftAlign = 128;
+#ifndef DLT_SHIFT_ALIGN
+#define DLT_SHIFT_ALIGN 128
+#endif
+constexpr int kShiftAlign = DLT_SHIFT_ALIGN;
 static_assert(kThreads * kUnroll * 16 == kTileBytes, "tile geometry");
 
 std::atomic<uint64_t> g_launches{0};
@@ -166,8 +172,11 @@ __device__ __forceinline__ T lds(const uint8_t* p) {
 // ------------------------------------------------------------------------------------------------
 // Tiled transform kernel
 // ------------------------------------------------------------------------------------------------
-template <int FMT, bool SA, bool SC, int VAR>
-__global__ void __launch_bounds__(kThreads, 6)
+// RAGGED = false is compiled without the head / tail pass: legal when every stream base is 16-byte
+// aligned and every stream's total length is a multiple of 16 (measured: merely carrying that pass
+// costs the 16-byte-block formats up to 20 % even when it stores nothing).
+template <int FMT, bool SA, bool SC, int VAR, bool RAGGED>
+__global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
     transform_tiled(const uint8_t* __restrict__ in, const StreamPtrs out, const uint64_t nblocks) {
     using L = Lay<FMT, SA, SC>;
     __shared__ __align__(16) uint8_t stage[L::kStageBytes];
@@ -268,22 +277,17 @@ __global__ void __launch_bounds__(kThreads, 6)
             if (k < nch && lo >= lo_valid && lo + 16 <= hi_valid) stg_stream16(gal + lo, lds<uint4>(reg + lo));
         }
     }
-    // ... and the ragged head / tail (< 16 bytes each, only when a stream base is not 16-byte aligned
-    // or the tile is the last one): warp s serves stream s, one byte per lane.
-    {
-        const int s = tid >> 5, lane = tid & 31;
-        if (s < L::NS) {
-            int w = 0, shs = 0, region = 0;
-            uint8_t* base = nullptr;
+    // ... and the ragged head / tail (< 16 bytes each; only when a stream base is not 16-byte aligned or
+    // the tile is the last one): warp 0, lanes 0-15 the head bytes, lanes 16-31 the tail bytes.
+    if constexpr (RAGGED) if (tid < 32) {
 #pragma unroll
-            for (int k = 0; k < L::NS; k++)
-                if (k == s) w = L::w(k), shs = sh[k], region = L::region(k), base = out.p[k];
-            const int lo_valid = shs, hi_valid = shs + w * nb;
+        for (int s = 0; s < L::NS; s++) {
+            const int lo_valid = sh[s], hi_valid = sh[s] + L::w(s) * nb;
             const int head_end = min(hi_valid, (lo_valid + 15) & ~15);
             const int tail_start = max(head_end, hi_valid & ~15);
-            const int i = lane < 16 ? lo_valid + lane : tail_start + lane - 16;
-            const bool on = lane < 16 ? i < head_end : i < hi_valid;
-            if (on) (base + (uint64_t)w * tile_first - shs)[i] = stage[region + i];
+            const int i = tid < 16 ? lo_valid + tid : tail_start + tid - 16;
+            if (tid < 16 ? i < head_end : i < hi_valid)
+                (out.p[s] + (uint64_t)L::w(s) * tile_first - sh[s])[i] = stage[L::region(s) + i];
         }
     }
 }
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 6)
 // Tiled untransform kernel
 // ------------------------------------------------------------------------------------------------
 template <int FMT, bool SA, bool SC, int VAR>
-__global__ void __launch_bounds__(kThreads, 6)
+__global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
     untransform_tiled(const StreamPtrs in, uint8_t* __restrict__ out, const uint64_t nblocks) {
     using L = Lay<FMT, SA, SC>;
     __shared__ __align__(16) uint8_t stage[L::kStageBytes];
@@ -322,21 +326,16 @@ __global__ void __launch_bounds__(kThreads, 6)
             if (k < nch && lo >= lo_valid && lo + 16 <= hi_valid) cp_async16(reg + lo, gal + lo);
         }
     }
-    // ragged head / tail of every segment: warp s serves stream s, one byte per lane (all loads in flight)
-    {
-        const int s = tid >> 5, lane = tid & 31;
-        if (s < L::NS) {
-            int w = 0, shs = 0, region = 0;
-            const uint8_t* base = nullptr;
+    // ragged head / tail of every segment (< 16 bytes each): warp 0, lanes 0-15 head, lanes 16-31 tail
+    if (tid < 32) {
 #pragma unroll
-            for (int k = 0; k < L::NS; k++)
-                if (k == s) w = L::w(k), shs = sh[k], region = L::region(k), base = in.p[k];
-            const int lo_valid = shs, hi_valid = shs + w * nb;
+        for (int s = 0; s < L::NS; s++) {
+            const int lo_valid = sh[s], hi_valid = sh[s] + L::w(s) * nb;
             const int head_end = min(hi_valid, (lo_valid + 15) & ~15);
             const int tail_start = max(head_end, hi_valid & ~15);
-            const int i = lane < 16 ? lo_valid + lane : tail_start + lane - 16;
-            const bool on = lane < 16 ? i < head_end : i < hi_valid;
-            if (on) stage[region + i] = (base + (uint64_t)w * tile_first - shs)[i];
+            const int i = tid < 16 ? lo_valid + tid : tail_start + tid - 16;
+            if (tid < 16 ? i < head_end : i < hi_valid)
+                stage[L::region(s) + i] = (in.p[s] + (uint64_t)L::w(s) * tile_first - sh[s])[i];
         }
     }
     cp_async_wait_all();
@@ -533,7 +532,13 @@ cudaError_t run(bool inverse, const uint8_t* blocks_in, uint8_t* blocks_out, con
     if (tiled_ok<FMT, SA, SC>(blocks, sp)) {
         const uint64_t tiles = (n + L::T - 1) / L::T;
         if (tiles > 0x7fffffffull) return cudaErrorInvalidValue;
-        if (!inverse) transform_tiled<FMT, SA, SC, VAR><<<(unsigned)tiles, kThreads, 0, stream>>>(blocks_in, sp, n);
+        bool ragged = false;
+        for (int s = 0; s < L::NS; s++)
+            ragged |= ((reinterpret_cast<uintptr_t>(sp.p[s]) | ((uint64_t)L::w(s) * n)) & 15) != 0;
+        if (!inverse && ragged)
+            transform_tiled<FMT, SA, SC, VAR, true><<<(unsigned)tiles, kThreads, 0, stream>>>(blocks_in, sp, n);
+        else if (!inverse)
+            transform_tiled<FMT, SA, SC, VAR, false><<<(unsigned)tiles, kThreads, 0, stream>>>(blocks_in, sp, n);
         else untransform_tiled<FMT, SA, SC, VAR><<<(unsigned)tiles, kThreads, 0, stream>>>(sp, blocks_out, n);
     } else {
         const uint64_t ctas = (n + kThreads - 1) / kThreads;

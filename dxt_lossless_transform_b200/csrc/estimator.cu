@@ -415,25 +415,36 @@ __global__ void __launch_bounds__(kSortThreads, 2) ltu_scatter_kernel(const Sort
 }
 
 // ---- compare every record with its bucket predecessor --------------------------------------------
+// Four consecutive records per thread (one 128-bit load); the predecessor of a record is at most 4
+// records back, i.e. in the thread's own vector or in the previous lane's (shuffle; lane 0 reloads).
 __global__ void __launch_bounds__(256) ltu_compare_kernel(const SortBatch b, unsigned long long* matches) {
     const int seg = blockIdx.y;
-    const uint32_t n = b.npos[seg];
-    const uint32_t* rec = b.rec_b[seg];
-    uint32_t count = 0;
+    const uint32_t n = b.npos[seg];  // a multiple of 4
+    const uint4* rec4 = reinterpret_cast<const uint4*>(b.rec_b[seg]);
+    const uint32_t nvec = n / 4;
     const unsigned lane = threadIdx.x & 31;
-    // warp-uniform trip count; the predecessor (<= 4 records back) comes from a lower lane by shuffle,
-    // only the first lanes of a warp go back to memory
-    for (uint32_t base = blockIdx.x * 256u + (threadIdx.x & ~31u); base < n; base += gridDim.x * 256u) {
-        const uint32_t i = base + lane;
-        const uint32_t r = i < n ? __ldg(rec + i) : 0u;
-        const uint32_t key = r & kRecKeyMask, back = (r >> 24) + 1u;
-        uint32_t q = __shfl_sync(kFull, r, (lane - back) & 31u);
-        bool have = i < n && i >= back;
-        if (have && lane < back) q = __ldg(rec + (i - back));
-        q &= kRecKeyMask;
-        uint32_t cmp = 0;  // an untouched bucket holds 0
-        if (have && ltu_bucket(q) == ltu_bucket(key)) cmp = q;
-        count += (i < n) && key == cmp;
+    uint32_t count = 0;
+    for (uint32_t vbase = blockIdx.x * 256u + (threadIdx.x & ~31u); vbase < nvec; vbase += gridDim.x * 256u) {
+        const uint32_t v = vbase + lane;
+        const bool in = v < nvec;
+        const uint4 cur = in ? __ldg(rec4 + v) : make_uint4(0, 0, 0, 0);
+        uint4 prev;
+        prev.x = __shfl_up_sync(kFull, cur.x, 1);
+        prev.y = __shfl_up_sync(kFull, cur.y, 1);
+        prev.z = __shfl_up_sync(kFull, cur.z, 1);
+        prev.w = __shfl_up_sync(kFull, cur.w, 1);
+        if (lane == 0 && in && v > 0) prev = __ldg(rec4 + v - 1);
+        const uint32_t w[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t r = w[4 + k];
+            const uint32_t key = r & kRecKeyMask, back = (r >> 24) + 1u;  // 1..4
+            const uint32_t q = (back == 1 ? w[3 + k] : back == 2 ? w[2 + k] : back == 3 ? w[1 + k] : w[k]) & kRecKeyMask;
+            const bool have = (uint64_t)v * 4 + k >= back;  // a predecessor index exists at all
+            uint32_t cmp = 0;                               // an untouched bucket holds 0
+            if (have && ltu_bucket(q) == ltu_bucket(key)) cmp = q;
+            count += in && key == cmp;
+        }
     }
     for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(kFull, count, o);
     __shared__ uint32_t ws[8];
@@ -535,7 +546,7 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
                 b.cnt[k] = reinterpret_cast<uint32_t*>(p), p += pl.cnt_bytes;
                 b.blk[k] = reinterpret_cast<uint32_t*>(p), p += pl.blk_bytes;
                 const uint32_t sblk = (uint32_t)((pl.ntiles * kRadix + kScanBlockElems - 1) / kScanBlockElems);
-                const uint32_t cblk = (uint32_t)std::min<size_t>((pl.npos + 255) / 256, 148 * 8);  // grid-stride
+                const uint32_t cblk = (uint32_t)std::min<size_t>((pl.npos / 4 + 255) / 256, 148 * 8);  // grid-stride, 4 records per thread
                 max_tiles = pl.ntiles > max_tiles ? (uint32_t)pl.ntiles : max_tiles;
                 max_scan_blocks = sblk > max_scan_blocks ? sblk : max_scan_blocks;
                 max_cmp_blocks = cblk > max_cmp_blocks ? cblk : max_cmp_blocks;
