@@ -151,6 +151,74 @@ static void bc3_range(int inverse, const uint8_t *in, uint8_t *out, size_t n, si
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Word-wise BC1 path for the CPU BASELINE timing (bench.py): the same bytes as bc1_range, but
+ * written the way the reference's SIMD tiers work (two colours per 32-bit lane, SWAR YCoCg-R as in
+ * common/src/intrinsics/color_565/decorrelate/avx512bw.rs:42-96) so that gcc -O3 auto-vectorises
+ * it.  tests/test_oracle.py checks it against bc1_range for every settings combination.
+ * ---------------------------------------------------------------------------------------- */
+static inline uint32_t decorr2(uint32_t v, int variant) {
+    const uint32_t M5 = 0x001F001Fu, M4 = 0x000F000Fu, M1 = 0x00010001u, B = 0x00200020u;
+    uint32_t r = (v >> 11) & M5, g = (v >> 6) & M5, gl = (v >> 5) & M1, b = v & M5;
+    uint32_t co = (r + B - b) & M5;
+    uint32_t t = (b + ((co >> 1) & M4)) & M5;
+    uint32_t cg = (g + B - t) & M5;
+    uint32_t y = (t + ((cg >> 1) & M4)) & M5;
+    if (variant == ORC_VARIANT_1) return (y << 11) | (co << 6) | (gl << 5) | cg;
+    if (variant == ORC_VARIANT_2) return (gl << 15) | (y << 10) | (co << 5) | cg;
+    return (y << 11) | (co << 6) | (cg << 1) | gl;
+}
+static inline uint32_t recorr2(uint32_t v, int variant) {
+    const uint32_t M5 = 0x001F001Fu, M4 = 0x000F000Fu, M1 = 0x00010001u, B = 0x00200020u;
+    uint32_t y, co, cg, gl;
+    if (variant == ORC_VARIANT_1) { y = (v >> 11) & M5; co = (v >> 6) & M5; gl = (v >> 5) & M1; cg = v & M5; }
+    else if (variant == ORC_VARIANT_2) { gl = (v >> 15) & M1; y = (v >> 10) & M5; co = (v >> 5) & M5; cg = v & M5; }
+    else { y = (v >> 11) & M5; co = (v >> 6) & M5; cg = (v >> 1) & M5; gl = v & M1; }
+    uint32_t t = (y + B - ((cg >> 1) & M4)) & M5;
+    uint32_t g = (cg + t) & M5;
+    uint32_t b = (t + B - ((co >> 1) & M4)) & M5;
+    uint32_t r = (b + co) & M5;
+    return (r << 11) | (g << 6) | (gl << 5) | b;
+}
+
+#define BC1_FAST_LOOP(VARIANT)                                                                      \
+    for (size_t i = b0; i < b1; i++) {                                                              \
+        uint32_t c, x;                                                                              \
+        if (!inverse) {                                                                             \
+            memcpy(&c, in + 8 * i, 4);                                                              \
+            memcpy(&x, in + 8 * i + 4, 4);                                                          \
+            if (VARIANT) c = decorr2(c, VARIANT);                                                   \
+            if (split) {                                                                            \
+                uint16_t lo = (uint16_t)c, hi = (uint16_t)(c >> 16);                                \
+                memcpy(out + 2 * i, &lo, 2);                                                        \
+                memcpy(out + len / 4 + 2 * i, &hi, 2);                                              \
+            } else memcpy(out + 4 * i, &c, 4);                                                      \
+            memcpy(out + len / 2 + 4 * i, &x, 4);                                                   \
+        } else {                                                                                    \
+            if (split) {                                                                            \
+                uint16_t lo, hi;                                                                    \
+                memcpy(&lo, in + 2 * i, 2);                                                         \
+                memcpy(&hi, in + len / 4 + 2 * i, 2);                                               \
+                c = (uint32_t)lo | ((uint32_t)hi << 16);                                            \
+            } else memcpy(&c, in + 4 * i, 4);                                                       \
+            memcpy(&x, in + len / 2 + 4 * i, 4);                                                    \
+            if (VARIANT) c = recorr2(c, VARIANT);                                                   \
+            memcpy(out + 8 * i, &c, 4);                                                             \
+            memcpy(out + 8 * i + 4, &x, 4);                                                         \
+        }                                                                                           \
+    }
+
+static void bc1_range_fast(int inverse, const uint8_t *restrict in, uint8_t *restrict out, size_t n, size_t b0,
+                           size_t b1, int variant, int split) {
+    const size_t len = n * 8;
+    switch (variant) {
+    case ORC_VARIANT_NONE: BC1_FAST_LOOP(0) break;
+    case ORC_VARIANT_1: BC1_FAST_LOOP(1) break;
+    case ORC_VARIANT_2: BC1_FAST_LOOP(2) break;
+    default: BC1_FAST_LOOP(3) break;
+    }
+}
+
 void orc_bc1_transform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc1_range(0, in, out, len / 8, 0, len / 8, v, s); }
 void orc_bc1_untransform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc1_range(1, in, out, len / 8, 0, len / 8, v, s); }
 void orc_bc2_transform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc2_range(0, in, out, len / 16, 0, len / 16, v, s); }
@@ -384,7 +452,7 @@ typedef struct {
 static void *mt_worker(void *arg) {
     mt_job *j = (mt_job *)arg;
     switch (j->format) {
-    case 1: bc1_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c); break;
+    case 1: bc1_range_fast(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c); break;
     case 2: bc2_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c); break;
     default: bc3_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_a, j->split_c); break;
     }
