@@ -262,7 +262,11 @@ def run_gpu_arm(args) -> None:
     ncu_traffic = ROOT / "profiles" / "dram_traffic.json"
     if ncu_traffic.exists():
         try:
-            roofline["traffic"] = json.loads(ncu_traffic.read_text()).get("bytes_per_launch_1gib")
+            doc = json.loads(ncu_traffic.read_text())
+            per_gib = doc.get("per_kernel", {}).get(dominant, doc.get("bytes_per_launch_1gib"))
+            # ncu capture of the same kernels on 1 GiB (profiles/README.md); traffic is linear in the payload
+            roofline["traffic"] = per_gib * shard_bytes / GIB if per_gib else None
+            roofline["traffic_source"] = doc.get("source")
         except Exception:
             pass
 
