@@ -68,6 +68,18 @@ class DltcudaPayload(C.Structure):
     _fields_ = [("input", C.c_void_p), ("output", C.c_void_p), ("len", C.c_size_t), ("settings", DltcudaSettings)]
 
 
+class DltffResult(C.Structure):  # dxt_lossless_transform_file_formats.h
+    _fields_ = [("error_code", C.c_int32), ("detail_a", C.c_size_t), ("detail_b", C.c_size_t)]
+
+
+class DdsInfo(C.Structure):  # dds/parse_dds.rs:36-42
+    _fields_ = [("format", C.c_uint8), ("data_offset", C.c_uint8), ("data_length", C.c_uint32)]
+
+
+class DltddsFile(C.Structure):
+    _fields_ = [("input", C.c_void_p), ("input_len", C.c_size_t), ("output", C.c_void_p), ("output_len", C.c_size_t)]
+
+
 # Every exported symbol: name -> (restype, argtypes).  tests/test_cabi_symbols.py checks this table
 # against include/*.h and against the built library.
 _P = C.c_void_p
@@ -134,6 +146,41 @@ SIGNATURES.update(
             [C.c_int, _P, _P, _SZ, C.c_bool, C.POINTER(DltcudaSettings), C.POINTER(_SZ)],
         ),
         "dltcuda_auto_candidates": (C.c_int, [C.c_int, C.c_bool, C.POINTER(DltcudaSettings)]),
+    }
+)
+
+
+_U32 = C.c_uint32
+SIGNATURES.update(
+    {
+        "dltff_error_message": (C.c_char_p, [C.c_int32]),
+        "dltff_TransformHeader_new": (_U32, [C.c_int32, _U32]),
+        "dltff_TransformHeader_format": (C.c_bool, [_U32, C.POINTER(C.c_int32)]),
+        "dltff_TransformHeader_format_data": (_U32, [_U32]),
+        "dltff_TransformHeader_read": (_U32, [_P]),
+        "dltff_TransformHeader_write": (None, [_U32, _P]),
+        "dltff_bc1_header_from_settings": (_U32, [C.c_uint8, C.c_bool]),
+        "dltff_bc2_header_from_settings": (_U32, [C.c_uint8, C.c_bool]),
+        "dltff_bc1_settings_from_header": (DltffResult, [_U32, C.POINTER(C.c_uint8), C.POINTER(C.c_bool)]),
+        "dltff_bc2_settings_from_header": (DltffResult, [_U32, C.POINTER(C.c_uint8), C.POINTER(C.c_bool)]),
+        "dltff_new_TransformBundle": (_P, []),
+        "dltff_TransformBundle_default_all": (_P, []),
+        "dltff_free_TransformBundle": (None, [_P]),
+        "dltff_TransformBundle_with_bc1_manual": (DltffResult, [_P, _P]),
+        "dltff_TransformBundle_with_bc1_auto": (DltffResult, [_P, _P]),
+        "dltff_TransformBundle_with_bc2_manual": (DltffResult, [_P, _P]),
+        "dltff_TransformBundle_with_bc2_auto": (DltffResult, [_P, _P]),
+        "dltff_dispatch_transform": (DltffResult, [C.c_int32, _P, _SZ, _P, _SZ, _P, C.POINTER(_U32)]),
+        "dltff_dispatch_untransform": (DltffResult, [_U32, _P, _SZ, _P, _SZ]),
+        "is_dds": (C.c_bool, [_P, _SZ]),
+        "parse_dds": (DdsInfo, [_P, _SZ]),
+        "dltdds_parse_dds_ignore_magic": (DdsInfo, [_P, _SZ]),
+        "dltdds_can_handle": (C.c_bool, [_P, _SZ, C.c_char_p]),
+        "dltdds_can_handle_untransform": (C.c_bool, [_P, _SZ, C.c_char_p]),
+        "dltdds_transform_bundle": (DltffResult, [_P, _SZ, _P, _SZ, _P]),
+        "dltdds_untransform": (DltffResult, [_P, _SZ, _P, _SZ]),
+        "dltdds_transform_bundle_batch": (C.c_int, [C.POINTER(DltddsFile), _SZ, _P, C.POINTER(DltffResult), C.POINTER(C.c_int), C.c_int]),
+        "dltdds_untransform_batch": (C.c_int, [C.POINTER(DltddsFile), _SZ, C.POINTER(DltffResult), C.POINTER(C.c_int), C.c_int]),
     }
 )
 

@@ -19,84 +19,18 @@
 #include <vector>
 
 #include "auto_search.h"
+#include "cabi_internal.h"
 #include "bcn_kernels.h"
 #include "bcn_layout.h"
 #include "estimator.h"
 #include "host_pipeline.h"
 
 using namespace dlt;
+using namespace dlt::cabi;
 
 #define DLT_EXPORT extern "C" __attribute__((visibility("default")))
 
-// =================================================================================================
-// Shared types
-// =================================================================================================
-extern "C" {
-
-// api-common/src/c_api/size_estimation.rs:17-52
-typedef uint32_t (*DltMaxCompressedSizeFn)(void* context, size_t len_bytes, size_t* out_size);
-typedef uint32_t (*DltEstimateCompressedSizeFn)(void* context, const uint8_t* input_ptr, size_t len_bytes,
-                                                uint8_t* output_ptr, size_t output_len, size_t* out_size);
-struct DltSizeEstimator {
-    void* context;
-    DltMaxCompressedSizeFn max_compressed_size;
-    DltEstimateCompressedSizeFn estimate_compressed_size;
-};
-
-struct DltResult {  // Dltbc{1,2}Result in both crates: one repr(C) enum field
-    int32_t error_code;
-};
-
-// core crates: { bool split_colour_endpoints; YCoCgVariant(u8, internal numbering) }
-struct DltCoreSettings {
-    bool split_colour_endpoints;
-    uint8_t decorrelation_mode;
-};
-struct DltCoreAutoSettings {
-    bool use_all_modes;
-};
-// additive BC3 settings (core style)
-struct DltCoreBc3Settings {
-    bool split_alpha_endpoints;
-    bool split_colour_endpoints;
-    uint8_t decorrelation_mode;
-};
-// additive device API
-struct DltcudaPayload;
-struct DltcudaSettings {
-    uint8_t format;              // 1, 2, 3
-    uint8_t decorrelation_mode;  // internal numbering: None=0, Variant1=1, Variant2=2, Variant3=3
-    bool split_alpha_endpoints;  // BC3 only
-    bool split_colour_endpoints;
-};
-
-struct DltcudaPayload {  // one independent host payload of a batch
-    const uint8_t* input;
-    uint8_t* output;
-    size_t len;
-    DltcudaSettings settings;
-};
-
-}  // extern "C"
-
 namespace {
-
-// Stable API codes — api/dxt-lossless-transform-bc1-api/src/c_api/error.rs:12-39
-enum ApiCode : int32_t {
-    kApiSuccess = 0,
-    kApiInvalidLength = 1,
-    kApiOutputBufferTooSmall = 2,
-    kApiAllocationFailed = 3,
-    kApiSizeEstimationFailed = 4,
-    kApiNullDataPointer = 5,
-    kApiNullEstimatorPointer = 6,
-    kApiNullTransformSettingsPointer = 7,
-    kApiNullInputPointer = 8,
-    kApiNullOutputBufferPointer = 9,
-    kApiNullManualTransformBuilderPointer = 10,
-    kApiNullBuilderPointer = 11,
-    kApiNullManualBuilderOutputPointer = 12,
-};
 
 // Core codes — core/dxt-lossless-transform-bc1/src/c_api/transform_auto.rs:37-58
 enum CoreCode : int32_t {
@@ -109,23 +43,6 @@ enum CoreCode : int32_t {
     kCoreOutputBufferTooSmall = 6,
     kCoreSizeEstimationError = 7,
     kCoreTransformationError = 8,
-};
-
-// Stable YCoCgVariant numbering (api-common/src/reexports/color_565.rs:65-85):
-// Variant1=0, Variant2=1, Variant3=2, None=3  <->  internal None=0, Variant1..3=1..3.
-inline int stable_to_internal(uint8_t v) { return v == 3 ? kNone : v + 1; }
-inline uint8_t internal_to_stable(int v) { return v == kNone ? 3 : (uint8_t)(v - 1); }
-
-// What a builder holds: Bc{1,2}ManualTransformBuilder { settings } (manual_transform_builder.rs).
-struct ManualBuilder {
-    int format;
-    int variant;  // internal numbering
-    bool split_colour;
-};
-struct AutoBuilder {
-    int format;
-    DltSizeEstimator estimator;  // a COPY, as in auto_transform_builder.rs:35-38
-    bool use_all;
 };
 
 enum class Outcome { kOk, kInvalidLength, kTooSmall, kDevice, kOutOfMemory, kEstimator, kHostAlloc };
@@ -305,7 +222,7 @@ ManualBuilder* new_manual(int format) {
     return new (std::nothrow) ManualBuilder{format, kVariant1, true};
 }
 
-DltResult api_manual_run(int format, bool inverse, const uint8_t* input, size_t input_len, uint8_t* output,
+DltResult manual_run_impl(int format, bool inverse, const uint8_t* input, size_t input_len, uint8_t* output,
                          size_t output_len, ManualBuilder* b) {
     // manual_transform_builder.rs:256-287: input, output, builder null checks in this order.
     if (!input) return {kApiNullDataPointer};
@@ -315,7 +232,7 @@ DltResult api_manual_run(int format, bool inverse, const uint8_t* input, size_t 
     return {api_code(transform_host(st, inverse, input, input_len, output, output_len))};
 }
 
-DltResult api_auto_run(int format, AutoBuilder* b, const uint8_t* data, size_t data_len, uint8_t* output,
+DltResult auto_run_impl(int format, AutoBuilder* b, const uint8_t* data, size_t data_len, uint8_t* output,
                        size_t output_len, ManualBuilder** out_manual) {
     // auto_transform_builder.rs:190-245: builder, data, output, out_manual_builder.
     if (!b) return {kApiNullBuilderPointer};
@@ -390,6 +307,22 @@ bool to_settings(const DltcudaSettings& s, Settings* out) {
 
 }  // namespace
 
+namespace dlt {
+namespace cabi {
+DltResult api_manual_run(int format, bool inverse, const uint8_t* input, size_t input_len, uint8_t* output,
+                         size_t output_len, ManualBuilder* b) {
+    return manual_run_impl(format, inverse, input, input_len, output, output_len, b);
+}
+DltResult api_auto_settings(int format, const AutoBuilder* b, const uint8_t* data, size_t data_len, uint8_t* output,
+                            size_t output_len, Settings* best) {
+    if (!b) return {kApiNullBuilderPointer};
+    if (!data) return {kApiNullDataPointer};
+    if (!output) return {kApiNullOutputBufferPointer};
+    return {api_code(auto_host(format, data, data_len, output, output_len, b->estimator, b->use_all, best))};
+}
+}  // namespace cabi
+}  // namespace dlt
+
 // =================================================================================================
 // 1a. Stable API: dltbc1_* / dltbc2_*
 // =================================================================================================
@@ -414,11 +347,11 @@ bool to_settings(const DltcudaSettings& s, Settings* out) {
     }                                                                                                                 \
     DLT_EXPORT DltResult dltbc##N##_ManualTransformBuilder_Transform(const uint8_t* input, size_t input_len,          \
                                                                      uint8_t* output, size_t output_len, void* b) {   \
-        return api_manual_run(N, false, input, input_len, output, output_len, static_cast<ManualBuilder*>(b));        \
+        return manual_run_impl(N, false, input, input_len, output, output_len, static_cast<ManualBuilder*>(b));        \
     }                                                                                                                 \
     DLT_EXPORT DltResult dltbc##N##_ManualTransformBuilder_Untransform(const uint8_t* input, size_t input_len,        \
                                                                        uint8_t* output, size_t output_len, void* b) { \
-        return api_manual_run(N, true, input, input_len, output, output_len, static_cast<ManualBuilder*>(b));         \
+        return manual_run_impl(N, true, input, input_len, output, output_len, static_cast<ManualBuilder*>(b));         \
     }                                                                                                                 \
     DLT_EXPORT void* dltbc##N##_new_AutoTransformBuilder(const DltSizeEstimator* estimator) {                         \
         if (!estimator) return nullptr;                                                                               \
@@ -433,7 +366,7 @@ bool to_settings(const DltcudaSettings& s, Settings* out) {
     DLT_EXPORT DltResult dltbc##N##_AutoTransformBuilder_Transform(void* b, const uint8_t* data, size_t data_len,     \
                                                                    uint8_t* output, size_t output_len,                \
                                                                    void** out_manual_builder) {                       \
-        return api_auto_run(N, static_cast<AutoBuilder*>(b), data, data_len, output, output_len,                      \
+        return auto_run_impl(N, static_cast<AutoBuilder*>(b), data, data_len, output, output_len,                      \
                             reinterpret_cast<ManualBuilder**>(out_manual_builder));                                   \
     }                                                                                                                 \
     DLT_EXPORT const char* dltbc##N##_error_message(int32_t code) { return api_error_message(code, N); }

@@ -6,6 +6,7 @@
     - the SURVEY.md §8c known answers (an independent restatement of decorrelate.rs and the
       dispatcher offsets made during the survey).
   They are written out literally below; the oracle is CHECKED against them in tests/test_oracle.py.
+    - the headers of the reference's DDS fixtures (src/assets/tests/r2-256-bc{1,2,3,7}.dds),
 * r2-256-bc{1,2,3}.payload.zlib — the block payloads (4096 blocks, DDS header stripped) of the
   reference's real-texture fixtures src/assets/tests/r2-256-bc{1,2,3}.dds, zlib-compressed.
 """
@@ -49,6 +50,11 @@ KNOWN = {
 }
 
 if __name__ == "__main__":
+    # headers of the reference's DDS fixtures (128 bytes; 148 for the DX10 one) + their file sizes
+    KNOWN["dds_fixtures"] = {}
+    for name, hdr in (("bc1", 128), ("bc2", 128), ("bc3", 128), ("bc7", 148)):
+        dds = (REF / f"assets/tests/r2-256-{name}.dds").read_bytes()
+        KNOWN["dds_fixtures"][name] = {"header": dds[:hdr].hex(), "file_len": len(dds)}
     (HERE / "known_answers.json").write_text(json.dumps(KNOWN, indent=1) + "\n")
     for n, bpb in ((1, 8), (2, 16), (3, 16)):
         dds = (REF / f"assets/tests/r2-256-bc{n}.dds").read_bytes()
