@@ -130,33 +130,71 @@ __global__ void __launch_bounds__(32) ltu_scan_filter_kernel(const SmallBatch ba
 }
 
 // =================================================================================================
-// Large-input path: LSD radix sort of the records by bucket, then a parallel compare
+// Large-input path: ONE stable partition pass by the low kPartBits bucket bits, then per-piece sequential compare
 // =================================================================================================
+//   1. hist + scan + scatter : stable partition of the records by bucket & (kParts - 1) (hand-written radix pass:
+//      per-tile shared-memory histograms, ballot-built stable ranks, tile staged in shared memory so every
+//      partition's run leaves as one contiguous write).  Inside a partition the records are in stream order and a
+//      bucket is identified by its CLASS = bucket >> kPartBits (kClasses of them).
+//   2. plan    : the partitioned array is cut into pieces of <= L records (L-aligned slots, never across a partition
+//      boundary); one small kernel numbers them.
+//   3. runs    : ONE THREAD owns a piece and walks it sequentially with a private kClasses-entry "last key of this
+//      class" table in shared memory (table[class][lane]: conflict-free); record loads are double-buffered 128-byte
+//      vectors, the interior is processed four records at a time without branches.  No cross-lane traffic: ~30
+//      instructions per record instead of the ~165 of a second radix pass + neighbour compare.  A record whose
+//      table entry is still unknown (first touch of the class in the piece) cannot be decided locally: its key is
+//      parked in dkey[] and the piece publishes its final table (state[]).
+//      kPartBits = 10 keeps the table at 256 bytes per thread, so ~20 warps of piece-threads are resident per SM
+//      (the kernel is a chain of dependent shared-memory round trips: it lives off warp-level parallelism).
+//   4. resolve : chunks of 32 pieces; per class the parked keys are compared against the last key written by an
+//      earlier piece of the same partition (or 0 at the partition start).  The in-state of a chunk is fetched lazily
+//      from per-chunk summaries, so a flat texture (everything in one partition, one class) costs one step and
+//      nothing is sequential across the whole array.
+// Same-group semantics (4 positions compared before the 4 updates): every record carries nskip; a record with
+// nskip > 0 ("follower") sees what the first same-bucket record of its group ("leader") saw, which the thread keeps
+// in a three-record history.  A follower belongs to the piece that owns its leader, so pieces hand over cleanly: a
+// piece skips leading followers of a foreign leader and processes up to three trailing followers of its own.
 constexpr int kMaxSegs = 16;
-constexpr int kTile = 8192;              // records per CTA tile
+constexpr int kTile = 8192;              // records per CTA tile of the partition pass
 constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kPerWarp = kTile / kSortWarps;     // contiguous records per warp (scatter: warp-striped)
 constexpr int kSteps = kPerWarp / 32;            // records per thread
-constexpr int kRadix = 256;
+constexpr int kPartBits = 10;
+constexpr int kParts = 1 << kPartBits;           // partitions = radix of the scatter pass
+constexpr int kClassBits = kLtuHashBits - kPartBits;
+constexpr int kClasses = 1 << kClassBits;        // buckets per partition
 constexpr int kScanBlockElems = 4096;            // elements per block of the offset scan
+constexpr int kChunkPieces = 32;                 // pieces per resolve chunk
+constexpr uint32_t kMinRunLen = 128;             // shortest piece (records); always a multiple of 32
+constexpr int kRunsWarpsPerSm = 20;              // resident piece-warps per SM (register cap 102)
+constexpr uint32_t kTargetPieces = 148 * kRunsWarpsPerSm * 32 * 9 / 10;  // one resident wave of piece-threads, 10 % slack
+constexpr uint32_t kUnknown = 0x80000000u;       // table / seen: no record of this class yet in this piece
+constexpr uint32_t kForeign = 0x40000000u;       // seen: the record belongs to a neighbouring piece
+constexpr uint32_t kParkedMask = 0x07000000u;    // state word bits 24-26: number of parked keys (0..4)
 static_assert(kSteps == 16 && kTile / kSortThreads == 16, "16 records per thread");
+static_assert(kClasses % 4 == 0 && kClasses >= 32, "class table layout");
 
 struct SortBatch {
     LtuSegment seg[kMaxSegs];
-    uint32_t* rec_a[kMaxSegs];   // records after pass 0
-    uint32_t* rec_b[kMaxSegs];   // records after pass 1 (sorted by bucket, stable)
-    uint32_t* cnt[kMaxSegs];     // [kRadix][ntiles] tile histograms -> exclusive offsets
-    uint32_t* blk[kMaxSegs];     // block sums of the scan
+    uint32_t* rec[kMaxSegs];        // records, partitioned by bucket & (kParts - 1) (stable)
+    uint32_t* cnt[kMaxSegs];        // [kParts][ntiles] tile histograms -> exclusive offsets
+    uint32_t* blk[kMaxSegs];        // block sums of the scan
+    uint32_t* part_off[kMaxSegs];   // [kParts + 1]: first record of every partition
+    uint32_t* piece_base[kMaxSegs]; // [kParts + 1]: first piece of every partition; [kParts] = number of pieces
+    uint16_t* part[kMaxSegs];       // [piece]: partition of the piece
+    uint32_t* state[kMaxSegs];      // [piece][class]: last key | parked count << 24 | kUnknown
+    uint32_t* dkey[kMaxSegs];       // [piece][4][class]: parked keys
+    uint32_t* sum_word[kMaxSegs];   // [chunk][class]: state word of the last piece of the chunk that touched the class
+    uint16_t* sum_part[kMaxSegs];   // [chunk][class]: partition of that piece
     uint32_t npos[kMaxSegs];
     uint32_t ntiles[kMaxSegs];
+    uint32_t run_len;               // L: records per piece slot (multiple of 32)
 };
 
-template <int PASS>
-__device__ __forceinline__ uint32_t digit_of(uint32_t rec) {
-    const uint32_t b = ltu_bucket(rec & kRecKeyMask);
-    return PASS == 0 ? (b & 0xFFu) : (b >> 8);
-}
+__device__ __forceinline__ uint32_t digit_of_bucket(uint32_t bucket) { return bucket & (kParts - 1); }
+__device__ __forceinline__ uint32_t digit_of(uint32_t rec) { return digit_of_bucket(ltu_bucket(rec & kRecKeyMask)); }
+__device__ __forceinline__ uint32_t class_of(uint32_t rec) { return ltu_bucket(rec & kRecKeyMask) >> kPartBits; }
 
 // Stage `need` bytes starting at `src` (any alignment) so that stage[(src & 15) + i] == src[i].
 // Interior as 128-bit loads, ragged edges bytewise; never reads outside [src, src + need).
@@ -177,47 +215,32 @@ __device__ __forceinline__ int stage_bytes(const uint8_t* src, int need, uint8_t
 }
 
 // ---- tile histograms: 16 CONSECUTIVE records per thread, run-length aggregated shared atomics ------
-// (no ordering needed here, so no match_any; a flat texture gives one atomic per thread, not 16)
-template <int PASS>
+// (no ordering needed here, so no match masks; a flat texture gives one atomic per thread, not 16)
 __global__ void __launch_bounds__(kSortThreads) ltu_hist_kernel(const SortBatch b) {
     const int seg = blockIdx.y;
     const uint32_t tile = blockIdx.x;
     if (tile >= b.ntiles[seg]) return;
-    __shared__ uint32_t hist[kRadix];
-    __shared__ __align__(16) uint8_t stage[PASS == 0 ? kTile + 48 : 16];
-    if (threadIdx.x < kRadix) hist[threadIdx.x] = 0;
+    __shared__ uint32_t hist[kParts];
+    __shared__ __align__(16) uint8_t stage[kTile + 48];
+    for (int d = threadIdx.x; d < kParts; d += kSortThreads) hist[d] = 0;
     const uint32_t left = b.npos[seg] - tile * kTile;
     const int nvalid = left < (uint32_t)kTile ? (int)left : kTile;
     const int first = threadIdx.x * 16;
     uint32_t digit[16];
-    if constexpr (PASS == 0) {
-        const int sh = stage_bytes(b.seg[seg].d_ptr + (size_t)tile * kTile, nvalid + 2, stage);
-        __syncthreads();
-        // bytes [first, first + 18) of the tile -> five byte-aligned words -> 16 three-byte keys
-        const int a = sh + first;
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(stage + (a & ~3));
-        uint32_t raw[6], w[5];
+    const int sh = stage_bytes(b.seg[seg].d_ptr + (size_t)tile * kTile, nvalid + 2, stage);
+    __syncthreads();
+    // bytes [first, first + 18) of the tile -> five byte-aligned words -> 16 three-byte keys
+    const int a = sh + first;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(stage + (a & ~3));
+    uint32_t raw[6], w[5];
 #pragma unroll
-        for (int k = 0; k < 6; k++) raw[k] = wp[k];
+    for (int k = 0; k < 6; k++) raw[k] = wp[k];
 #pragma unroll
-        for (int k = 0; k < 5; k++) w[k] = __funnelshift_r(raw[k], raw[k + 1], 8 * (a & 3));
+    for (int k = 0; k < 5; k++) w[k] = __funnelshift_r(raw[k], raw[k + 1], 8 * (a & 3));
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const uint32_t key = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], 8 * (j & 3)) & kRecKeyMask;
-            digit[j] = ltu_bucket(key) & 0xFFu;
-        }
-    } else {
-        const uint4* src = reinterpret_cast<const uint4*>(b.rec_a[seg] + (size_t)tile * kTile + first);
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (first + 4 * q < nvalid) v = __ldg(src + q);  // nvalid is a multiple of 4
-            digit[4 * q + 0] = digit_of<1>(v.x);
-            digit[4 * q + 1] = digit_of<1>(v.y);
-            digit[4 * q + 2] = digit_of<1>(v.z);
-            digit[4 * q + 3] = digit_of<1>(v.w);
-        }
+    for (int j = 0; j < 16; j++) {
+        const uint32_t key = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], 8 * (j & 3)) & kRecKeyMask;
+        digit[j] = digit_of_bucket(ltu_bucket(key));
     }
     uint32_t run = 0, cur = digit[0];
 #pragma unroll
@@ -232,13 +255,13 @@ __global__ void __launch_bounds__(kSortThreads) ltu_hist_kernel(const SortBatch 
     }
     if (run) atomicAdd(&hist[cur], run);
     __syncthreads();
-    if (threadIdx.x < kRadix) b.cnt[seg][(size_t)threadIdx.x * b.ntiles[seg] + tile] = hist[threadIdx.x];
+    for (int d = threadIdx.x; d < kParts; d += kSortThreads) b.cnt[seg][(size_t)d * b.ntiles[seg] + tile] = hist[d];
 }
 
-// ---- exclusive scan of cnt[seg][0 .. kRadix*ntiles) in three small launches ----------------------
+// ---- exclusive scan of cnt[seg][0 .. kParts*ntiles) in three small launches ----------------------
 __global__ void __launch_bounds__(256) ltu_scan_sums_kernel(const SortBatch b) {
     const int seg = blockIdx.y;
-    const uint32_t n = kRadix * b.ntiles[seg];
+    const uint32_t n = kParts * b.ntiles[seg];
     const uint32_t base = blockIdx.x * kScanBlockElems;
     if (base >= n) return;
     uint32_t s = 0;
@@ -256,7 +279,7 @@ __global__ void __launch_bounds__(256) ltu_scan_sums_kernel(const SortBatch b) {
 
 __global__ void __launch_bounds__(32) ltu_scan_blocks_kernel(const SortBatch b) {
     const int seg = blockIdx.x;
-    const uint32_t n = kRadix * b.ntiles[seg];
+    const uint32_t n = kParts * b.ntiles[seg];
     const uint32_t nblk = (n + kScanBlockElems - 1) / kScanBlockElems;
     const unsigned lane = threadIdx.x;
     uint32_t carry = 0;
@@ -275,7 +298,7 @@ __global__ void __launch_bounds__(32) ltu_scan_blocks_kernel(const SortBatch b) 
 
 __global__ void __launch_bounds__(256) ltu_scan_apply_kernel(const SortBatch b) {
     const int seg = blockIdx.y;
-    const uint32_t n = kRadix * b.ntiles[seg];
+    const uint32_t n = kParts * b.ntiles[seg];
     const uint32_t base = blockIdx.x * kScanBlockElems;
     if (base >= n) return;
     constexpr int kPer = kScanBlockElems / 256;  // consecutive elements per thread
@@ -305,154 +328,462 @@ __global__ void __launch_bounds__(256) ltu_scan_apply_kernel(const SortBatch b) 
     }
 }
 
-// ---- stable scatter of one tile by the pass's digit -------------------------------------------------
-// Warp-striped: warp w owns tile records [w*kPerWarp, (w+1)*kPerWarp), lane l of step t holds record
-// w*kPerWarp + t*32 + l, so lane order inside a step is stream order and the match-mask ranks are stable.
-template <int PASS>
-__global__ void __launch_bounds__(kSortThreads, 2) ltu_scatter_kernel(const SortBatch b) {
-    const int seg = blockIdx.y;
-    const uint32_t tile = blockIdx.x;
-    if (tile >= b.ntiles[seg]) return;
-    // the byte staging of pass 0 is dead once the records are in registers: it shares `sorted`
-    __shared__ __align__(16) uint32_t sorted[kTile];     // the tile in digit order
-    __shared__ uint16_t warp_cnt[kSortWarps][kRadix];    // per-warp digit counts -> per-warp bases
-    __shared__ uint32_t bin_start[kRadix], gofs[kRadix];
-    __shared__ uint32_t wsum[kRadix / 32];
-    uint8_t* stage = reinterpret_cast<uint8_t*>(sorted);
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < kSortWarps * kRadix / 2; i += kSortThreads)
-        reinterpret_cast<uint32_t*>(&warp_cnt[0][0])[i] = 0;
-    const uint32_t left = b.npos[seg] - tile * kTile;
-    const int nvalid = left < (uint32_t)kTile ? (int)left : kTile;
+// ---- stable scatter of one tile by bucket & (kParts - 1) ---------------------------------------------
+// Tile-local LSD sort in shared memory, two rounds of kSubBits, entirely THREAD-SEQUENTIAL: a thread owns 32
+// consecutive records and a private row of 32 counters per round (cnt[bin][thread]); count -> block-wide exclusive
+// scan in (bin, thread) order -> the counters become write cursors.  No ballots, no shuffles in the ranking: ~35
+// instructions per record for the 10-bit digit instead of ~75 with warp match masks, and flat data costs the same
+// as random data.  Records of a digit then leave the tile as one contiguous, coalesced run.
+//   smem: sorted[] and cnt[] are both indexed through pad(): 4 words of padding per 32, so that a thread reading its
+//   32 consecutive words with 128-bit loads is conflict-free (lane stride 36 words) and cnt[bin][thread] stays
+//   conflict-free too.
+constexpr int kPThreads = 256;
+constexpr int kPPer = kTile / kPThreads;         // consecutive records per thread
+constexpr int kSubBits = kPartBits / 2;
+constexpr int kSubBins = 1 << kSubBits;
+constexpr int kPaddedTile = kTile + kTile / 8;
+constexpr int kScatterSmemBytes = 2 * kPaddedTile * 4 + 128;
+static_assert(kPPer == 32 && kSubBits * 2 == kPartBits && kSubBins * kPThreads == kTile, "scatter geometry");
+static_assert(kParts == 4 * kPThreads, "four digits per thread in the offset phase");
+static_assert(kTile + 48 <= kPaddedTile * 4 && 2 * kParts * 4 <= kPaddedTile * 4, "aliases of the counter area");
 
-    uint32_t rec[kSteps];
-    if constexpr (PASS == 0) {
-        const int sh = stage_bytes(b.seg[seg].d_ptr + (size_t)tile * kTile, nvalid + 2, stage);  // key(p) = bytes p..p+2
-        __syncthreads();
+__device__ __forceinline__ int pad(int i) { return i + ((i >> 5) << 2); }
+
+template <bool FULL>
+__device__ __forceinline__ uint32_t tile_digit(uint32_t rec) {
+    // a partial tile pads with 0xFFFFFFFF records, which sort behind everything else
+    if (!FULL && rec == 0xFFFFFFFFu) return kParts - 1;
+    return digit_of(rec);
+}
+
+template <bool FULL>
+__device__ __forceinline__ void scatter_tile(const SortBatch& b, const int seg, const uint32_t tile, const int nvalid,
+                                             uint8_t* smem) {
+    uint32_t* sorted = reinterpret_cast<uint32_t*>(smem);                 // padded, kPaddedTile words
+    uint32_t* cnt = sorted + kPaddedTile;                                  // padded [kSubBins][kPThreads]
+    uint8_t* stage = reinterpret_cast<uint8_t*>(cnt);                      // byte staging (dead before round A)
+    uint32_t* bin_start = cnt;                                             // [kParts]  (after round B)
+    uint32_t* gofs = cnt + kParts;                                         // [kParts]
+    uint32_t* wsum = sorted + 2 * kPaddedTile;                             // [8] + [8]
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31, warp = tid >> 5;
+    const uint32_t nt = b.ntiles[seg];
+
+    // global offsets of this tile's four digits per thread, and the digit counts (difference to the next entry of
+    // the scanned [digit][tile] matrix); loaded now, used at the end
+    uint32_t g_off[4], g_cnt[4];
 #pragma unroll
-        for (int t = 0; t < kSteps; t++) {
-            const int i = warp * kPerWarp + t * 32 + lane;
-            uint32_t key = 0;
-            if (i < nvalid) {
-                const int a = sh + i;
-                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(stage + (a & ~3));
-                const uint32_t w1 = *reinterpret_cast<const uint32_t*>(stage + (a & ~3) + 4);
-                key = __funnelshift_r(w0, w1, 8 * (a & 3)) & kRecKeyMask;
-            }
-            rec[t] = key | (group_nskip(ltu_bucket(key), lane) << 24);  // nvalid is a multiple of 4
-        }
-        __syncthreads();  // everyone is done reading `stage` before `sorted` is written
-    } else {
-        const uint32_t* src = b.rec_a[seg] + (size_t)tile * kTile;
-#pragma unroll
-        for (int t = 0; t < kSteps; t++) {
-            const int i = warp * kPerWarp + t * 32 + lane;
-            rec[t] = i < nvalid ? __ldg(src + i) : 0u;
-        }
-        __syncthreads();
+    for (int k = 0; k < 4; k++) {
+        const size_t lin = (size_t)(tid * 4 + k) * nt + tile;
+        g_off[k] = __ldg(b.cnt[seg] + lin);
+        g_cnt[k] = (lin + 1 < (size_t)kParts * nt ? __ldg(b.cnt[seg] + lin + 1) : b.npos[seg]) - g_off[k];
     }
 
-    // rank of every record among the records of its warp with the same digit (stream order);
-    // meta = digit | rank << 8
-    uint32_t meta[kSteps];
-#pragma unroll
-    for (int t = 0; t < kSteps; t++) {
-        const int i = warp * kPerWarp + t * 32 + lane;
-        const bool valid = i < nvalid;
-        const uint32_t d = digit_of<PASS>(rec[t]);
-        const unsigned mask = match_bits<8>(d, valid);
-        const uint32_t before = valid ? warp_cnt[warp][d] : 0;
-        meta[t] = d | ((before + __popc(mask & ((1u << lane) - 1u))) << 8);
-        __syncwarp();
-        if (valid && (mask >> lane) == 1u) warp_cnt[warp][d] = (uint16_t)(before + __popc(mask));
-        __syncwarp();
-    }
+    // ---- keys: strided extraction (conflict-free), one word per position into sorted[]
+    const int sh = stage_bytes(b.seg[seg].d_ptr + (size_t)tile * kTile, nvalid + 2, stage);  // key(p) = bytes p..p+2
     __syncthreads();
-
-    // thread d < 256: per-warp bases of digit d, the tile's digit histogram and its exclusive scan
-    uint32_t tot = 0, inc = 0;
-    if (threadIdx.x < kRadix) {
-        const int d = threadIdx.x;
-#pragma unroll
-        for (int w = 0; w < kSortWarps; w++) {
-            const uint32_t c = warp_cnt[w][d];
-            warp_cnt[w][d] = (uint16_t)tot;
-            tot += c;
+#pragma unroll 8
+    for (int k = 0; k < kPPer; k++) {
+        const int i = k * kPThreads + tid;
+        uint32_t key = 0xFFFFFFFFu;
+        if (FULL || i < nvalid) {
+            const int a = sh + i;
+            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(stage + (a & ~3));
+            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(stage + (a & ~3) + 4);
+            key = __funnelshift_r(w0, w1, 8 * (a & 3)) & kRecKeyMask;
         }
-        inc = tot;
+        sorted[pad(i)] = key;
+    }
+    __syncthreads();   // stage is dead from here on
+
+    // ---- records: 32 consecutive positions per thread, nskip inside each group of four
+    uint32_t rec[kPPer];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(sorted + pad(tid * kPPer));
+#pragma unroll
+        for (int q = 0; q < kPPer / 4; q++) {
+            const uint4 v = src[q];
+            const uint32_t k0 = v.x, k1 = v.y, k2 = v.z, k3 = v.w;
+            const uint32_t b0 = ltu_bucket(k0 & kRecKeyMask), b1 = ltu_bucket(k1 & kRecKeyMask), b2 = ltu_bucket(k2 & kRecKeyMask),
+                           b3 = ltu_bucket(k3 & kRecKeyMask);
+            const uint32_t n1 = b1 == b0, n2 = (uint32_t)(b2 == b0) + (b2 == b1), n3 = (uint32_t)(b3 == b0) + (b3 == b1) + (b3 == b2);
+            // nvalid is a multiple of 4: a group is entirely valid or entirely padding (padding keeps 0xFFFFFFFF)
+            const bool padding = !FULL && k0 == 0xFFFFFFFFu;
+            rec[4 * q + 0] = k0;
+            rec[4 * q + 1] = padding ? k1 : k1 | (n1 << 24);
+            rec[4 * q + 2] = padding ? k2 : k2 | (n2 << 24);
+            rec[4 * q + 3] = padding ? k3 : k3 | (n3 << 24);
+        }
+    }
+
+    // ---- two LSD rounds
+#pragma unroll
+    for (int round = 0; round < 2; round++) {
+        const int shift = round * kSubBits;
+        // zero the counters (the padding words too; they are never read)
+        for (int i = tid; i < kPaddedTile / 4; i += kPThreads) reinterpret_cast<uint4*>(cnt)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();   // also: every thread holds its records in registers before sorted[] is overwritten
+#pragma unroll
+        for (int j = 0; j < kPPer; j++) {
+            const uint32_t d = (tile_digit<FULL>(rec[j]) >> shift) & (kSubBins - 1);
+            cnt[pad((int)d * kPThreads + tid)]++;
+        }
+        __syncthreads();
+        // exclusive scan in (bin, thread) order: thread t owns the 32 consecutive counters [32t, 32t+32)
+        {
+            uint4* row = reinterpret_cast<uint4*>(cnt + pad(tid * 32));
+            uint32_t run = 0;   // pass 1: the row total (the row is re-read in pass 2: cheaper than 32 live registers)
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint4 v = row[q];
+                run += v.x + v.y + v.z + v.w;
+            }
+            uint32_t inc = run;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(kFull, inc, o);
+                if ((int)lane >= o) inc += up;
+            }
+            if (lane == 31) wsum[round * 8 + warp] = inc;
+            __syncthreads();
+            uint32_t base = inc - run;
+            for (unsigned w = 0; w < warp; w++) base += wsum[round * 8 + w];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint4 v = row[q];
+                uint4 o;
+                o.x = base, base += v.x;
+                o.y = base, base += v.y;
+                o.z = base, base += v.z;
+                o.w = base, base += v.w;
+                row[q] = o;
+            }
+        }
+        __syncthreads();
+        // the counters are cursors now: stable because a thread walks its records in stream order
+#pragma unroll
+        for (int j = 0; j < kPPer; j++) {
+            const uint32_t d = (tile_digit<FULL>(rec[j]) >> shift) & (kSubBins - 1);
+            uint32_t* c = cnt + pad((int)d * kPThreads + tid);
+            const uint32_t pos = *c;
+            *c = pos + 1;
+            sorted[pad((int)pos)] = rec[j];
+        }
+        __syncthreads();
+        if (round == 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(sorted + pad(tid * kPPer));
+#pragma unroll
+            for (int q = 0; q < kPPer / 4; q++) {
+                const uint4 v = src[q];
+                rec[4 * q + 0] = v.x, rec[4 * q + 1] = v.y, rec[4 * q + 2] = v.z, rec[4 * q + 3] = v.w;
+            }
+        }
+    }
+
+    // ---- where each digit's run starts inside the tile (exclusive scan of the four counts per thread) and globally
+    {
+        const uint32_t sum = g_cnt[0] + g_cnt[1] + g_cnt[2] + g_cnt[3];
+        uint32_t inc = sum;
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t up = __shfl_up_sync(kFull, inc, o);
             if ((int)lane >= o) inc += up;
         }
-        if (lane == 31) wsum[warp] = inc;
-    }
-    __syncthreads();
-    if (threadIdx.x < kRadix) {
-        uint32_t off = inc - tot;
-        for (int w = 0; w < (int)warp; w++) off += wsum[w];
-        bin_start[threadIdx.x] = off;
-        gofs[threadIdx.x] = b.cnt[seg][(size_t)threadIdx.x * b.ntiles[seg] + tile];
-    }
-    __syncthreads();
-
+        if (lane == 31) wsum[16 + warp] = inc;   // cnt[] (aliased by bin_start / gofs) is dead: all cursors were consumed
+        __syncthreads();
+        uint32_t off = inc - sum;
+        for (unsigned w = 0; w < warp; w++) off += wsum[16 + w];
 #pragma unroll
-    for (int t = 0; t < kSteps; t++) {
-        const int i = warp * kPerWarp + t * 32 + lane;
-        if (i < nvalid) {
-            const uint32_t d = meta[t] & 0xFFu;
-            sorted[bin_start[d] + warp_cnt[warp][d] + (meta[t] >> 8)] = rec[t];
+        for (int k = 0; k < 4; k++) {
+            bin_start[tid * 4 + k] = off;
+            gofs[tid * 4 + k] = g_off[k];
+            off += g_cnt[k];
         }
     }
     __syncthreads();
 
-    // write-out: consecutive threads write consecutive records of a digit's run
-    uint32_t* out = PASS == 0 ? b.rec_a[seg] : b.rec_b[seg];
-    for (int i = threadIdx.x; i < nvalid; i += kSortThreads) {
-        const uint32_t r = sorted[i];
-        const uint32_t d = digit_of<PASS>(r);
-        out[gofs[d] + (uint32_t)i - bin_start[d]] = r;
+    // ---- write-out: consecutive threads write consecutive records of a digit's run
+    uint32_t* out = b.rec[seg];
+#pragma unroll 4
+    for (int k = 0; k < kPPer; k++) {
+        const int i = k * kPThreads + tid;
+        if (FULL || i < nvalid) {
+            const uint32_t r = sorted[pad(i)];
+            const uint32_t d = digit_of(r);
+            out[gofs[d] + (uint32_t)i - bin_start[d]] = r;
+        }
     }
 }
 
-// ---- compare every record with its bucket predecessor --------------------------------------------
-// Four consecutive records per thread (one 128-bit load); the predecessor of a record is at most 4
-// records back, i.e. in the thread's own vector or in the previous lane's (shuffle; lane 0 reloads).
-__global__ void __launch_bounds__(256) ltu_compare_kernel(const SortBatch b, unsigned long long* matches) {
+__global__ void __launch_bounds__(kPThreads, 3) ltu_scatter_kernel(const SortBatch b) {
     const int seg = blockIdx.y;
-    const uint32_t n = b.npos[seg];  // a multiple of 4
-    const uint4* rec4 = reinterpret_cast<const uint4*>(b.rec_b[seg]);
-    const uint32_t nvec = n / 4;
-    const unsigned lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.x;
+    if (tile >= b.ntiles[seg]) return;
+    extern __shared__ __align__(16) uint8_t scatter_smem[];
+    const uint32_t left = b.npos[seg] - tile * kTile;
+    if (left >= (uint32_t)kTile) scatter_tile<true>(b, seg, tile, kTile, scatter_smem);
+    else scatter_tile<false>(b, seg, tile, (int)left, scatter_smem);
+}
+
+// ---- plan: partition boundaries -> pieces ------------------------------------------------------------
+// Partition p holds records [part_off[p], part_off[p+1]); it is cut at multiples of L, so it owns the slots
+// part_off[p] / L .. (part_off[p+1] - 1) / L.  piece_base[] numbers the pieces partition after partition.
+__global__ void __launch_bounds__(kParts) ltu_plan_kernel(const SortBatch b) {
+    const int seg = blockIdx.x;
+    const uint32_t p = threadIdx.x;
+    const uint32_t npos = b.npos[seg], nt = b.ntiles[seg], L = b.run_len;
+    const uint32_t o0 = b.cnt[seg][(size_t)p * nt];
+    const uint32_t o1 = p == kParts - 1 ? npos : b.cnt[seg][(size_t)(p + 1) * nt];
+    const uint32_t pieces = o1 > o0 ? (o1 - 1) / L - o0 / L + 1 : 0;
+    __shared__ uint32_t ws[kParts / 32];
+    const unsigned lane = p & 31, warp = p >> 5;
+    uint32_t inc = pieces;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(kFull, inc, o);
+        if ((int)lane >= o) inc += up;
+    }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    uint32_t base = inc - pieces;
+    for (unsigned w = 0; w < warp; w++) base += ws[w];
+    b.part_off[seg][p] = o0;
+    b.piece_base[seg][p] = base;
+    if (p == kParts - 1) b.part_off[seg][kParts] = npos, b.piece_base[seg][kParts] = base + pieces;
+    for (uint32_t k = 0; k < pieces; k++) b.part[seg][base + k] = (uint16_t)p;
+}
+
+// ---- runs: one thread per piece, private class table in shared memory ---------------------------------
+__device__ __forceinline__ uint4 ldg_nc16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// Every piece-thread streams its own piece: tens of thousands of concurrent 128-byte reads at unrelated addresses
+// (DRAM row misses).  Each thread therefore pulls the next kPrefetchRecords of its piece into L2 with ONE bulk
+// prefetch, so DRAM sees kilobyte-sized contiguous reads and the record loads hit L2.
+constexpr uint32_t kPrefetchRecords = 512;   // 2 KiB
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(32, kRunsWarpsPerSm) ltu_runs_kernel(const SortBatch b, unsigned long long* matches) {
+    __shared__ uint32_t table[kClasses * 32];      // [class][lane]
+    const int seg = blockIdx.y;
+    const unsigned lane = threadIdx.x;
+    const uint32_t L = b.run_len;
+    const uint32_t total = b.piece_base[seg][kParts];
+    if (blockIdx.x * 32u >= total) return;
+
+    const uint32_t g = blockIdx.x * 32u + lane;   // piece id
+    uint32_t start = 0, end = 0, part_start = 0, part_end = 0;
+    if (g < total) {
+        const uint32_t p = b.part[seg][g];
+        part_start = b.part_off[seg][p], part_end = b.part_off[seg][p + 1];
+        const uint32_t slot = part_start / L + (g - b.piece_base[seg][p]);
+        start = max(part_start, slot * L);
+        end = min(part_end, (slot + 1) * L);
+    }
+#pragma unroll 8
+    for (int c = 0; c < kClasses; c++) table[c * 32 + lane] = kUnknown;
+
+    const uint32_t* rec = b.rec[seg];
+    uint32_t* dk = b.dkey[seg] + (size_t)g * 4 * kClasses;
     uint32_t count = 0;
-    for (uint32_t vbase = blockIdx.x * 256u + (threadIdx.x & ~31u); vbase < nvec; vbase += gridDim.x * 256u) {
-        const uint32_t v = vbase + lane;
-        const bool in = v < nvec;
-        const uint4 cur = in ? __ldg(rec4 + v) : make_uint4(0, 0, 0, 0);
-        uint4 prev;
-        prev.x = __shfl_up_sync(kFull, cur.x, 1);
-        prev.y = __shfl_up_sync(kFull, cur.y, 1);
-        prev.z = __shfl_up_sync(kFull, cur.z, 1);
-        prev.w = __shfl_up_sync(kFull, cur.w, 1);
-        if (lane == 0 && in && v > 0) prev = __ldg(rec4 + v - 1);
-        const uint32_t w[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
+    // history of the last three records: class and what the record saw (a key, kUnknown or kForeign)
+    uint32_t hc1 = 0xFFFFFFFFu, hc2 = 0xFFFFFFFFu, hc3 = 0xFFFFFFFFu, hs1 = kForeign, hs2 = kForeign, hs3 = kForeign;
+    auto push = [&](uint32_t cls, uint32_t seen) {
+        hc3 = hc2, hs3 = hs2, hc2 = hc1, hs2 = hs1, hc1 = cls, hs1 = seen;
+    };
+    // General (scalar) step: piece edges, where records may belong to the neighbouring piece.
+    auto process = [&](uint32_t r, bool in_range) {
+        const uint32_t key = r & kRecKeyMask, nskip = r >> 24;
+        const uint32_t cls = ltu_bucket(key) >> kPartBits;
+        uint32_t* slot = table + cls * 32 + lane;
+        const uint32_t w = *slot;
+        uint32_t seen;
+        if (nskip) seen = hc1 == cls ? hs1 : hc2 == cls ? hs2 : hs3;   // follower: what its leader saw
+        else seen = in_range ? (w & (kUnknown | kRecKeyMask)) : kForeign;  // leader past `end`: the next piece's
+        if (!(seen & kForeign)) {
+            uint32_t nw = (w & kParkedMask) | key;
+            if (seen & kUnknown) {
+                dk[((w >> 24) & 7u) * kClasses + cls] = key;   // decided by the resolve pass
+                nw += 0x01000000u;
+            } else {
+                count += seen == key;
+            }
+            *slot = nw;
+        }
+        push(cls, seen);
+    };
+    // Interior step, four records at a time, branch-free: no record can be foreign once three records of the piece
+    // have been processed.  The four table entries are loaded together; a record that hits the class of one of the
+    // (up to three) records before it in the batch takes that record's updated word instead of the loaded one.
+    auto process4 = [&](const uint4 v) {
+        const uint32_t r[4] = {v.x, v.y, v.z, v.w};
+        uint32_t key[4], cls[4], w[4], nw[4], seen[4];
+        uint32_t* slot[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t r = w[4 + k];
-            const uint32_t key = r & kRecKeyMask, back = (r >> 24) + 1u;  // 1..4
-            const uint32_t q = (back == 1 ? w[3 + k] : back == 2 ? w[2 + k] : back == 3 ? w[1 + k] : w[k]) & kRecKeyMask;
-            const bool have = (uint64_t)v * 4 + k >= back;  // a predecessor index exists at all
-            uint32_t cmp = 0;                               // an untouched bucket holds 0
-            if (have && ltu_bucket(q) == ltu_bucket(key)) cmp = q;
-            count += in && key == cmp;
+        for (int i = 0; i < 4; i++) {
+            key[i] = r[i] & kRecKeyMask;
+            cls[i] = ltu_bucket(key[i]) >> kPartBits;
+            slot[i] = table + cls[i] * 32 + lane;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = *slot[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            // the three records before record i: in the batch (distance <= i) or in the history
+            const uint32_t c1 = i >= 1 ? cls[i - 1] : hc1, c2 = i >= 2 ? cls[i - 2] : (i == 1 ? hc1 : hc2);
+            const uint32_t c3 = i >= 3 ? cls[0] : (i == 2 ? hc1 : i == 1 ? hc2 : hc3);
+            const uint32_t s1 = i >= 1 ? seen[i - 1] : hs1, s2 = i >= 2 ? seen[i - 2] : (i == 1 ? hs1 : hs2);
+            const uint32_t s3 = i >= 3 ? seen[0] : (i == 2 ? hs1 : i == 1 ? hs2 : hs3);
+            const bool m1 = c1 == cls[i], m2 = c2 == cls[i], m3 = c3 == cls[i];
+            uint32_t W = w[i];
+            if (i >= 3 && m3) W = nw[i - 3];
+            if (i >= 2 && m2) W = nw[i - 2];
+            if (i >= 1 && m1) W = nw[i - 1];
+            const uint32_t follower_seen = m1 ? s1 : m2 ? s2 : s3;
+            seen[i] = (r[i] >> 24) ? follower_seen : (W & (kUnknown | kRecKeyMask));
+            const uint32_t unknown = seen[i] >> 31;
+            count += seen[i] == key[i];                  // an unknown `seen` has bit 31 set: never equal to a key
+            nw[i] = ((W & kParkedMask) | key[i]) + (unknown << 24);
+            if (unknown) dk[((W >> 24) & 7u) * kClasses + cls[i]] = key[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) *slot[i] = nw[i];
+        hc3 = cls[1], hs3 = seen[1], hc2 = cls[2], hs2 = seen[2], hc1 = cls[3], hs1 = seen[3];
+    };
+
+    if (g < total) {
+        // the (up to three) records before the piece are foreign history
+        for (uint32_t j = start >= part_start + 3 ? start - 3 : part_start; j < start; j++) push(class_of(__ldg(rec + j)), kForeign);
+        uint32_t i = start;
+        for (; i < end && ((i & 31u) || i < start + 3); i++) process(__ldg(rec + i), true);
+        if (i + 32 <= end) {
+            // prime the first prefetch window; the loop keeps one window ahead
+            const uint32_t w0 = (i + kPrefetchRecords - 1) / kPrefetchRecords * kPrefetchRecords;   // first window boundary
+            if (w0 + 4 <= end) prefetch_l2_bulk(rec + w0, (min(kPrefetchRecords, end - w0) & ~3u) * 4u);   // multiple of 16 bytes
+            uint4 cur[8], nxt[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) cur[k] = ldg_nc16(rec + i + 4 * k);
+            for (; i + 32 <= end; i += 32) {
+                const bool more = i + 64 <= end;
+                if ((i & (kPrefetchRecords - 1)) == 0) {
+                    const uint32_t ahead = i + kPrefetchRecords;   // the window after the one being read
+                    if (ahead + 4 <= end) prefetch_l2_bulk(rec + ahead, (min(kPrefetchRecords, end - ahead) & ~3u) * 4u);
+                }
+                if (more) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) nxt[k] = ldg_nc16(rec + i + 32 + 4 * k);   // in flight while `cur` is processed
+                }
+                asm volatile("" ::: "memory");   // keep the prefetch ahead of the table traffic below
+#pragma unroll
+                for (int k = 0; k < 8; k++) process4(cur[k]);
+#pragma unroll
+                for (int k = 0; k < 8; k++) cur[k] = nxt[k];
+            }
+        }
+        for (; i < end; i++) process(__ldg(rec + i), true);
+        for (; i < part_end && i < end + 3; i++) process(__ldg(rec + i), false);   // trailing followers of my leaders
+        // publish the final table
+        uint32_t* st = b.state[seg] + (size_t)g * kClasses;
+#pragma unroll 4
+        for (int c = 0; c < kClasses; c += 4) {
+            const uint4 v = make_uint4(table[(c + 0) * 32 + lane], table[(c + 1) * 32 + lane], table[(c + 2) * 32 + lane],
+                                       table[(c + 3) * 32 + lane]);
+            *reinterpret_cast<uint4*>(st + c) = v;
         }
     }
     for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(kFull, count, o);
-    __shared__ uint32_t ws[8];
+    if (lane == 0 && count) atomicAdd(&matches[seg], (unsigned long long)count);
+}
+
+// ---- resolve, level 1: per chunk and class, the last piece of the chunk that touched the class -----------
+constexpr int kResolveThreads = kClasses;   // one thread per class
+
+__global__ void __launch_bounds__(kResolveThreads) ltu_summarize_kernel(const SortBatch b) {
+    const int seg = blockIdx.y;
+    const uint32_t total = b.piece_base[seg][kParts];
+    const uint32_t g0 = blockIdx.x * kChunkPieces;
+    if (g0 >= total) return;
+    const uint32_t g1 = min(total, g0 + kChunkPieces);
+    const uint32_t c = threadIdx.x;
+    const uint32_t* st = b.state[seg];
+    uint32_t last = kUnknown, last_part = 0;
+    for (uint32_t g = g0; g < g1; g += 8) {
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = g + k < g1 ? __ldg(st + (size_t)(g + k) * kClasses + c) : kUnknown;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (!(w[k] & kUnknown)) last = w[k], last_part = b.part[seg][g + k];
+    }
+    b.sum_word[seg][(size_t)blockIdx.x * kClasses + c] = last;
+    b.sum_part[seg][(size_t)blockIdx.x * kClasses + c] = (uint16_t)last_part;
+}
+
+// ---- resolve, level 2: walk the pieces of a chunk in order, decide the parked compares -----------------
+__global__ void __launch_bounds__(kResolveThreads) ltu_resolve_kernel(const SortBatch b, unsigned long long* matches) {
+    const int seg = blockIdx.y;
+    const uint32_t total = b.piece_base[seg][kParts];
+    const uint32_t g0 = blockIdx.x * kChunkPieces;
+    if (g0 >= total) return;
+    const uint32_t g1 = min(total, g0 + kChunkPieces);
+    const uint32_t c = threadIdx.x;
+    const uint32_t* st = b.state[seg];
+    const uint32_t* dk = b.dkey[seg];
+    const uint16_t* part = b.part[seg];
+    __shared__ uint16_t s_part[kChunkPieces + 1];   // s_part[0] = partition of piece g0 - 1
+    if (threadIdx.x <= g1 - g0) {
+        const uint32_t g = g0 + threadIdx.x;
+        s_part[threadIdx.x] = g == 0 ? 0 : part[g - 1];
+    }
+    __syncthreads();
+
+    uint32_t cur = 0, count = 0;
+    bool known = g0 == 0;   // the very first piece starts a partition: every bucket holds 0
+    for (uint32_t gb = g0; gb < g1; gb += 8) {
+        uint32_t w[8], d0[8];   // state word and first parked key of 8 pieces, all loads in flight together
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            w[k] = gb + k < g1 ? __ldg(st + (size_t)(gb + k) * kClasses + c) : kUnknown;
+            d0[k] = gb + k < g1 ? __ldg(dk + (size_t)(gb + k) * 4 * kClasses + c) : 0u;   // garbage unless parked >= 1
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t g = gb + k;
+            if (g >= g1) break;
+            const uint32_t p = s_part[g - g0 + 1];
+            if (g != 0 && s_part[g - g0] != p) cur = 0, known = true;   // first piece of its partition
+            const uint32_t parked = (w[k] >> 24) & 7u;
+            if (parked) {
+                if (!known) {
+                    // lazily fetch the in-state: the last earlier piece of partition p that touched class c
+                    cur = 0;
+                    for (int q = (int)blockIdx.x - 1; q >= 0; q--) {
+                        const uint32_t sw = __ldg(b.sum_word[seg] + (size_t)q * kClasses + c);
+                        if (!(sw & kUnknown)) {
+                            if (b.sum_part[seg][(size_t)q * kClasses + c] == p) cur = sw & kRecKeyMask;
+                            break;
+                        }
+                        if (part[(size_t)(q + 1) * kChunkPieces - 1] != p) break;   // chunk q ends before partition p starts
+                    }
+                    known = true;
+                }
+                count += d0[k] == cur;
+                for (uint32_t i = 1; i < parked; i++) count += __ldg(dk + ((size_t)g * 4 + i) * kClasses + c) == cur;
+            }
+            if (!(w[k] & kUnknown)) cur = w[k] & kRecKeyMask, known = true;
+        }
+    }
+    for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(kFull, count, o);
+    __shared__ uint32_t ws[kResolveThreads / 32];
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = count;
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long t = 0;
-        for (int i = 0; i < 8; i++) t += ws[i];
+        for (int i = 0; i < kResolveThreads / 32; i++) t += ws[i];
         if (t) atomicAdd(&matches[seg], t);
     }
 }
@@ -460,20 +791,48 @@ __global__ void __launch_bounds__(256) ltu_compare_kernel(const SortBatch b, uns
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SegPlan {
-    size_t npos, ntiles, rec_bytes, cnt_bytes, blk_bytes;
+    size_t npos, ntiles, max_pieces, max_chunks;
+    size_t rec_bytes, cnt_bytes, blk_bytes, poff_bytes, pbase_bytes, part_bytes, state_bytes, dkey_bytes, sumw_bytes, sump_bytes;
+    size_t bytes() const {
+        return rec_bytes + cnt_bytes + blk_bytes + poff_bytes + pbase_bytes + part_bytes + state_bytes + dkey_bytes + sumw_bytes +
+               sump_bytes;
+    }
 };
-SegPlan plan_segment(size_t len) {
+SegPlan plan_segment(size_t len, uint32_t run_len) {
     SegPlan p{};
     p.npos = ltu_positions(len);
     p.ntiles = (p.npos + kTile - 1) / kTile;
+    p.max_pieces = p.npos / run_len + 1 + kParts;   // one partial piece at either end of every partition
+    p.max_chunks = (p.max_pieces + kChunkPieces - 1) / kChunkPieces;
     p.rec_bytes = align_up(p.npos * 4, 256);
-    p.cnt_bytes = align_up(p.ntiles * kRadix * 4, 256);
-    p.blk_bytes = align_up((p.ntiles * kRadix + kScanBlockElems - 1) / kScanBlockElems * 4, 256);
+    p.cnt_bytes = align_up(p.ntiles * kParts * 4, 256);
+    p.blk_bytes = align_up((p.ntiles * kParts + kScanBlockElems - 1) / kScanBlockElems * 4, 256);
+    p.poff_bytes = p.pbase_bytes = align_up((kParts + 1) * 4, 256);
+    p.part_bytes = align_up(p.max_pieces * 2, 256);
+    p.state_bytes = align_up(p.max_pieces * kClasses * 4, 256);
+    p.dkey_bytes = align_up(p.max_pieces * 4 * kClasses * 4, 256);
+    p.sumw_bytes = align_up(p.max_chunks * kClasses * 4, 256);
+    p.sump_bytes = align_up(p.max_chunks * kClasses * 2, 256);
     return p;
 }
 
 constexpr size_t kSmallPositions = 4096;   // at or below: the single-launch kernel
 constexpr size_t kResultBytes = 256;       // matches[] at the front of the scratch
+
+// Piece length for a set of segments: one resident wave of piece-threads over the whole batch (a second, nearly
+// empty wave would double the time), never shorter than kMinRunLen (per-piece overhead: table init and publish,
+// up to 4 parked keys per class).
+uint32_t choose_run_len(const LtuSegment* segs, int nseg) {
+    size_t total = 0, large = 0;
+    for (int i = 0; i < nseg; i++) {
+        const size_t npos = ltu_positions(segs[i].len);
+        if (npos > kSmallPositions) total += npos, large++;
+    }
+    const size_t budget = kTargetPieces > large * (kParts + 1) + 4096 ? kTargetPieces - large * (kParts + 1) : 4096;
+    size_t len = (total + budget - 1) / budget;
+    len = (len + 31) / 32 * 32;
+    return (uint32_t)(len < kMinRunLen ? kMinRunLen : len);
+}
 
 }  // namespace
 
@@ -481,9 +840,10 @@ uint64_t estimator_launch_count() { return g_est_launches.load(std::memory_order
 
 size_t ltu_scratch_bytes(const LtuSegment* segs, int nseg) {
     size_t total = kResultBytes;
+    const uint32_t run_len = choose_run_len(segs, nseg);
     for (int i = 0; i < nseg; i++) {
-        const SegPlan p = plan_segment(segs[i].len);
-        if (p.npos > kSmallPositions) total += 2 * p.rec_bytes + p.cnt_bytes + p.blk_bytes;
+        const SegPlan p = plan_segment(segs[i].len, run_len);
+        if (p.npos > kSmallPositions) total += p.bytes();
     }
     return total;
 }
@@ -506,7 +866,7 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
         int ns = 0, nl = 0, i = done;
         for (; i < nseg; i++) {
             const size_t npos = ltu_positions(segs[i].len);
-            if (npos > 0xFFFFFFFFull) return Status::kCudaError;  // record indices are 32-bit
+            if (npos > 0xFFFF0000ull) return Status::kCudaError;  // record indices are 32-bit
             if (npos <= kSmallPositions) {
                 if (ns == kMaxSegsSmall) break;
                 small_idx[ns++] = i;
@@ -534,37 +894,49 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
 
         if (nl) {
             SortBatch b{};
+            b.run_len = choose_run_len(segs, nseg);
             uint8_t* p = scratch + kResultBytes;
-            uint32_t max_tiles = 0, max_scan_blocks = 0, max_cmp_blocks = 0;
+            uint32_t max_tiles = 0, max_scan_blocks = 0, max_piece_warps = 0, max_chunks = 0;
+            auto take = [&p](size_t bytes) {
+                uint8_t* r = p;
+                p += bytes;
+                return r;
+            };
             for (int k = 0; k < nl; k++) {
-                const SegPlan pl = plan_segment(segs[large_idx[k]].len);
+                const SegPlan pl = plan_segment(segs[large_idx[k]].len, b.run_len);
                 b.seg[k] = segs[large_idx[k]];
                 b.npos[k] = (uint32_t)pl.npos;
                 b.ntiles[k] = (uint32_t)pl.ntiles;
-                b.rec_a[k] = reinterpret_cast<uint32_t*>(p), p += pl.rec_bytes;
-                b.rec_b[k] = reinterpret_cast<uint32_t*>(p), p += pl.rec_bytes;
-                b.cnt[k] = reinterpret_cast<uint32_t*>(p), p += pl.cnt_bytes;
-                b.blk[k] = reinterpret_cast<uint32_t*>(p), p += pl.blk_bytes;
-                const uint32_t sblk = (uint32_t)((pl.ntiles * kRadix + kScanBlockElems - 1) / kScanBlockElems);
-                const uint32_t cblk = (uint32_t)std::min<size_t>((pl.npos / 4 + 255) / 256, 148 * 8);  // grid-stride, 4 records per thread
-                max_tiles = pl.ntiles > max_tiles ? (uint32_t)pl.ntiles : max_tiles;
-                max_scan_blocks = sblk > max_scan_blocks ? sblk : max_scan_blocks;
-                max_cmp_blocks = cblk > max_cmp_blocks ? cblk : max_cmp_blocks;
+                b.rec[k] = reinterpret_cast<uint32_t*>(take(pl.rec_bytes));
+                b.cnt[k] = reinterpret_cast<uint32_t*>(take(pl.cnt_bytes));
+                b.blk[k] = reinterpret_cast<uint32_t*>(take(pl.blk_bytes));
+                b.part_off[k] = reinterpret_cast<uint32_t*>(take(pl.poff_bytes));
+                b.piece_base[k] = reinterpret_cast<uint32_t*>(take(pl.pbase_bytes));
+                b.part[k] = reinterpret_cast<uint16_t*>(take(pl.part_bytes));
+                b.state[k] = reinterpret_cast<uint32_t*>(take(pl.state_bytes));
+                b.dkey[k] = reinterpret_cast<uint32_t*>(take(pl.dkey_bytes));
+                b.sum_word[k] = reinterpret_cast<uint32_t*>(take(pl.sumw_bytes));
+                b.sum_part[k] = reinterpret_cast<uint16_t*>(take(pl.sump_bytes));
+                const uint32_t sblk = (uint32_t)((pl.ntiles * kParts + kScanBlockElems - 1) / kScanBlockElems);
+                max_tiles = std::max(max_tiles, (uint32_t)pl.ntiles);
+                max_scan_blocks = std::max(max_scan_blocks, sblk);
+                max_piece_warps = std::max(max_piece_warps, (uint32_t)((pl.max_pieces + 31) / 32));
+                max_chunks = std::max(max_chunks, (uint32_t)pl.max_chunks);
             }
+            static const cudaError_t attr = cudaFuncSetAttribute(ltu_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                 kScatterSmemBytes);
+            if (attr != cudaSuccess) return fail(attr);
             const dim3 tiles(max_tiles, nl), scan_grid(max_scan_blocks, nl);
-            auto scan = [&]() {
-                ltu_scan_sums_kernel<<<scan_grid, 256, 0, stream>>>(b);
-                ltu_scan_blocks_kernel<<<nl, 32, 0, stream>>>(b);
-                ltu_scan_apply_kernel<<<scan_grid, 256, 0, stream>>>(b);
-            };
-            ltu_hist_kernel<0><<<tiles, kSortThreads, 0, stream>>>(b);
-            scan();
-            ltu_scatter_kernel<0><<<tiles, kSortThreads, 0, stream>>>(b);
-            ltu_hist_kernel<1><<<tiles, kSortThreads, 0, stream>>>(b);
-            scan();
-            ltu_scatter_kernel<1><<<tiles, kSortThreads, 0, stream>>>(b);
-            ltu_compare_kernel<<<dim3(max_cmp_blocks, nl), 256, 0, stream>>>(b, d_matches);
-            g_est_launches.fetch_add(11, std::memory_order_relaxed);
+            ltu_hist_kernel<<<tiles, kSortThreads, 0, stream>>>(b);
+            ltu_scan_sums_kernel<<<scan_grid, 256, 0, stream>>>(b);
+            ltu_scan_blocks_kernel<<<nl, 32, 0, stream>>>(b);
+            ltu_scan_apply_kernel<<<scan_grid, 256, 0, stream>>>(b);
+            ltu_scatter_kernel<<<tiles, kPThreads, kScatterSmemBytes, stream>>>(b);
+            ltu_plan_kernel<<<nl, kParts, 0, stream>>>(b);
+            ltu_runs_kernel<<<dim3(max_piece_warps, nl), 32, 0, stream>>>(b, d_matches);
+            ltu_summarize_kernel<<<dim3(max_chunks, nl), kResolveThreads, 0, stream>>>(b);
+            ltu_resolve_kernel<<<dim3(max_chunks, nl), kResolveThreads, 0, stream>>>(b, d_matches);
+            g_est_launches.fetch_add(9, std::memory_order_relaxed);
             if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
             if ((e = cudaMemcpyAsync(host, d_matches, sizeof(uint64_t) * nl, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
                 (e = cudaStreamSynchronize(stream)) != cudaSuccess)

@@ -78,6 +78,39 @@ def test_estimator_device_pointer_any_alignment(dlt, torch):
         assert dlt.ltu_estimate_device(d.data_ptr() + off, data.size - off) == oracle.ltu_estimate(data[off:])
 
 
+def adversarial_streams():
+    """Inputs aimed at the partition + per-piece compare path: everything in one bucket, rare outliers in a flat
+    stream (long look-backs in the resolve pass), same-group bucket collisions across piece boundaries, sizes on
+    both sides of every piece-length threshold."""
+    rng = np.random.default_rng(77)
+    yield "zeros_1M", np.zeros(1 << 20, np.uint8)
+    yield "ff_3M+5", np.full((3 << 20) + 5, 0xFF, np.uint8)
+    flat = np.full(6_000_001, 0x55, np.uint8)
+    flat[::100_003] = 0xAA
+    flat[1_234_567:1_234_600] = rng.integers(0, 256, 33, dtype=np.uint8)
+    yield "flat_with_outliers", flat
+    for period in (2, 3, 4, 5, 7, 8, 12):
+        yield f"period{period}", np.tile(rng.integers(0, 256, period, dtype=np.uint8), 700_001 // period + 1)
+    yield "two_symbols_2M", rng.integers(0, 2, 2_000_003, dtype=np.uint8)
+    yield "three_symbols_9M", rng.integers(0, 3, 9_000_000, dtype=np.uint8)
+    yield "random_20M", rng.integers(0, 256, 20_000_000, dtype=np.uint8)
+    runs = np.repeat(rng.integers(0, 256, 200_000, dtype=np.uint8), rng.integers(1, 60, 200_000))
+    yield "runs_6M", runs
+    for n in (4100, 4104, 5000, 40_000, 131_072 + 7, 1_048_576 + 11):
+        yield f"low_entropy_{n}", rng.integers(0, 5, n, dtype=np.uint8)
+    # a smooth "texture" stream: few distinct neighbouring keys, heavy partitions
+    t = (np.cumsum(rng.integers(-1, 2, 5_000_000)) // 7 % 256).astype(np.uint8)
+    yield "random_walk_5M", t
+
+
+def test_estimator_large_path_adversarial(dlt, torch):
+    for name, data in adversarial_streams():
+        d = torch.from_numpy(data).cuda()
+        assert dlt.ltu_estimate_device(d.data_ptr(), data.size) == oracle.ltu_estimate(data), name
+        if data.size > 100_000:  # an unaligned view of the same stream
+            assert dlt.ltu_estimate_device(d.data_ptr() + 3, data.size - 3) == oracle.ltu_estimate(data[3:]), name
+
+
 @pytest.mark.parametrize("fmt", [1, 2, 3])
 @pytest.mark.parametrize("use_all", [False, True])
 def test_auto_matches_oracle_choice_and_bytes(dlt, torch, fmt, use_all):
