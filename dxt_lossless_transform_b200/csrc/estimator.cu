@@ -164,7 +164,7 @@ constexpr int kPartBits = 10;
 constexpr int kParts = 1 << kPartBits;           // partitions = radix of the scatter pass
 constexpr int kClassBits = kLtuHashBits - kPartBits;
 constexpr int kClasses = 1 << kClassBits;        // buckets per partition
-constexpr int kScanBlockElems = 4096;            // elements per block of the offset scan
+constexpr int kColChunk = 64;                    // tiles per chunk of the column scan
 constexpr int kChunkPieces = 32;                 // pieces per resolve chunk
 constexpr uint32_t kMinRunLen = 128;             // shortest piece (records); always a multiple of 32
 constexpr int kRunsWarpsPerSm = 20;              // resident piece-warps per SM (register cap 102)
@@ -178,8 +178,9 @@ static_assert(kClasses % 4 == 0 && kClasses >= 32, "class table layout");
 struct SortBatch {
     LtuSegment seg[kMaxSegs];
     uint32_t* rec[kMaxSegs];        // records, partitioned by bucket & (kParts - 1) (stable)
-    uint32_t* cnt[kMaxSegs];        // [kParts][ntiles] tile histograms -> exclusive offsets
-    uint32_t* blk[kMaxSegs];        // block sums of the scan
+    uint32_t* cnt[kMaxSegs];        // [ntiles + 1][kParts] tile histograms -> exclusive offsets (digit-major order);
+                                    // row ntiles = where every digit's partition ends
+    uint32_t* blk[kMaxSegs];        // [chunks][kParts] column sums of kColChunk tiles -> offset of the chunk's first tile
     uint32_t* part_off[kMaxSegs];   // [kParts + 1]: first record of every partition
     uint32_t* piece_base[kMaxSegs]; // [kParts + 1]: first piece of every partition; [kParts] = number of pieces
     uint16_t* part[kMaxSegs];       // [piece]: partition of the piece
@@ -255,76 +256,72 @@ __global__ void __launch_bounds__(kSortThreads) ltu_hist_kernel(const SortBatch 
     }
     if (run) atomicAdd(&hist[cur], run);
     __syncthreads();
-    for (int d = threadIdx.x; d < kParts; d += kSortThreads) b.cnt[seg][(size_t)d * b.ntiles[seg] + tile] = hist[d];
+    for (int d = threadIdx.x; d < kParts; d += kSortThreads) b.cnt[seg][(size_t)tile * kParts + d] = hist[d];   // coalesced row
 }
 
-// ---- exclusive scan of cnt[seg][0 .. kParts*ntiles) in three small launches ----------------------
-__global__ void __launch_bounds__(256) ltu_scan_sums_kernel(const SortBatch b) {
+// ---- exclusive scan of the [tile][digit] matrix in digit-major order (all tiles of digit 0, then digit 1, ...) -------
+// Three small launches, every access a coalesced row of kParts counters: column sums per chunk of kColChunk tiles,
+// one CTA per segment that turns them into chunk offsets (+ the digit bases), then the running sums inside each chunk.
+__global__ void __launch_bounds__(kParts) ltu_colsum_kernel(const SortBatch b) {
     const int seg = blockIdx.y;
-    const uint32_t n = kParts * b.ntiles[seg];
-    const uint32_t base = blockIdx.x * kScanBlockElems;
-    if (base >= n) return;
+    const uint32_t nt = b.ntiles[seg];
+    const uint32_t t0 = blockIdx.x * kColChunk;
+    if (t0 >= nt) return;
+    const uint32_t t1 = min(nt, t0 + kColChunk);
+    const uint32_t d = threadIdx.x;
+    const uint32_t* m = b.cnt[seg];
     uint32_t s = 0;
-    for (uint32_t i = base + threadIdx.x; i < base + kScanBlockElems && i < n; i += 256) s += b.cnt[seg][i];
-    __shared__ uint32_t ws[8];
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int i = 0; i < 8; i++) t += ws[i];
-        b.blk[seg][blockIdx.x] = t;
-    }
+#pragma unroll 8
+    for (uint32_t t = t0; t < t1; t++) s += __ldg(m + (size_t)t * kParts + d);
+    b.blk[seg][(size_t)blockIdx.x * kParts + d] = s;
 }
 
-__global__ void __launch_bounds__(32) ltu_scan_blocks_kernel(const SortBatch b) {
+__global__ void __launch_bounds__(kParts) ltu_colbase_kernel(const SortBatch b) {
     const int seg = blockIdx.x;
-    const uint32_t n = kParts * b.ntiles[seg];
-    const uint32_t nblk = (n + kScanBlockElems - 1) / kScanBlockElems;
-    const unsigned lane = threadIdx.x;
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < nblk; base += 32) {
-        const uint32_t i = base + lane;
-        const uint32_t v = i < nblk ? b.blk[seg][i] : 0;
-        uint32_t inc = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t up = __shfl_up_sync(kFull, inc, o);
-            if ((int)lane >= o) inc += up;
-        }
-        if (i < nblk) b.blk[seg][i] = carry + inc - v;
-        carry += __shfl_sync(kFull, inc, 31);
+    const uint32_t nt = b.ntiles[seg];
+    const uint32_t nchunks = (nt + kColChunk - 1) / kColChunk;
+    const uint32_t d = threadIdx.x;
+    uint32_t* blk = b.blk[seg];
+    uint32_t total = 0;
+    for (uint32_t c = 0; c < nchunks; c++) {   // exclusive running sum down the column of chunk sums
+        const uint32_t v = blk[(size_t)c * kParts + d];
+        blk[(size_t)c * kParts + d] = total;
+        total += v;
     }
-}
-
-__global__ void __launch_bounds__(256) ltu_scan_apply_kernel(const SortBatch b) {
-    const int seg = blockIdx.y;
-    const uint32_t n = kParts * b.ntiles[seg];
-    const uint32_t base = blockIdx.x * kScanBlockElems;
-    if (base >= n) return;
-    constexpr int kPer = kScanBlockElems / 256;  // consecutive elements per thread
-    uint32_t v[kPer], sum = 0;
-    const uint32_t first = base + threadIdx.x * kPer;
-#pragma unroll
-    for (int k = 0; k < kPer; k++) {
-        v[k] = first + k < n ? b.cnt[seg][first + k] : 0;
-        sum += v[k];
-    }
-    // block-wide exclusive scan of the per-thread sums
-    __shared__ uint32_t ws[8];
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = sum;
+    // digit bases: exclusive scan of the column totals over the digits
+    __shared__ uint32_t ws[kParts / 32];
+    const unsigned lane = d & 31, warp = d >> 5;
+    uint32_t inc = total;
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t up = __shfl_up_sync(kFull, inc, o);
         if ((int)lane >= o) inc += up;
     }
     if (lane == 31) ws[warp] = inc;
     __syncthreads();
-    uint32_t off = b.blk[seg][blockIdx.x] + inc - sum;
-    for (int w = 0; w < (int)warp; w++) off += ws[w];
+    uint32_t base = inc - total;
+    for (unsigned w = 0; w < warp; w++) base += ws[w];
+    for (uint32_t c = 0; c < nchunks; c++) blk[(size_t)c * kParts + d] += base;
+    b.cnt[seg][(size_t)nt * kParts + d] = base + total;   // the extra row: end of the digit's partition
+}
+
+__global__ void __launch_bounds__(kParts) ltu_colapply_kernel(const SortBatch b) {
+    const int seg = blockIdx.y;
+    const uint32_t nt = b.ntiles[seg];
+    const uint32_t t0 = blockIdx.x * kColChunk;
+    if (t0 >= nt) return;
+    const uint32_t t1 = min(nt, t0 + kColChunk);
+    const uint32_t d = threadIdx.x;
+    uint32_t* m = b.cnt[seg];
+    uint32_t run = b.blk[seg][(size_t)blockIdx.x * kParts + d];
+    for (uint32_t t = t0; t < t1; t += 8) {
+        uint32_t v[8];
 #pragma unroll
-    for (int k = 0; k < kPer; k++) {
-        if (first + k < n) b.cnt[seg][first + k] = off;
-        off += v[k];
+        for (int k = 0; k < 8; k++) v[k] = t + k < t1 ? m[(size_t)(t + k) * kParts + d] : 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (t + k < t1) m[(size_t)(t + k) * kParts + d] = run;
+            run += v[k];
+        }
     }
 }
 
@@ -349,12 +346,11 @@ static_assert(kTile + 48 <= kPaddedTile * 4 && 2 * kParts * 4 <= kPaddedTile * 4
 
 __device__ __forceinline__ int pad(int i) { return i + ((i >> 5) << 2); }
 
-template <bool FULL>
-__device__ __forceinline__ uint32_t tile_digit(uint32_t rec) {
-    // a partial tile pads with 0xFFFFFFFF records, which sort behind everything else
-    if (!FULL && rec == 0xFFFFFFFFu) return kParts - 1;
-    return digit_of(rec);
-}
+// While a record sits in the tile sort its spare bits 26-30 carry the 5-bit digit of the current round, so the ranking
+// loops need one shift per record instead of a hash.  Padding records of a partial tile are 0x7FFFFFFF: digit 31 in
+// both rounds and last in stream order, hence last in the sorted tile.
+constexpr uint32_t kRecMask26 = 0x03FFFFFFu;
+constexpr uint32_t kPadRecord = 0x7FFFFFFFu;
 
 template <bool FULL>
 __device__ __forceinline__ void scatter_tile(const SortBatch& b, const int seg, const uint32_t tile, const int nvalid,
@@ -364,19 +360,18 @@ __device__ __forceinline__ void scatter_tile(const SortBatch& b, const int seg, 
     uint8_t* stage = reinterpret_cast<uint8_t*>(cnt);                      // byte staging (dead before round A)
     uint32_t* bin_start = cnt;                                             // [kParts]  (after round B)
     uint32_t* gofs = cnt + kParts;                                         // [kParts]
-    uint32_t* wsum = sorted + 2 * kPaddedTile;                             // [8] + [8]
+    uint32_t* wsum = sorted + 2 * kPaddedTile;                             // [8] + [8] + [8]
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31, warp = tid >> 5;
-    const uint32_t nt = b.ntiles[seg];
 
-    // global offsets of this tile's four digits per thread, and the digit counts (difference to the next entry of
-    // the scanned [digit][tile] matrix); loaded now, used at the end
+    // global offsets of this tile's four digits per thread and the digit counts (difference to the same digits of the
+    // next tile; the row after the last tile holds the partition ends): two coalesced 128-bit loads, used at the end
     uint32_t g_off[4], g_cnt[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const size_t lin = (size_t)(tid * 4 + k) * nt + tile;
-        g_off[k] = __ldg(b.cnt[seg] + lin);
-        g_cnt[k] = (lin + 1 < (size_t)kParts * nt ? __ldg(b.cnt[seg] + lin + 1) : b.npos[seg]) - g_off[k];
+    {
+        const uint4 o = __ldg(reinterpret_cast<const uint4*>(b.cnt[seg] + (size_t)tile * kParts) + tid);
+        const uint4 n = __ldg(reinterpret_cast<const uint4*>(b.cnt[seg] + (size_t)(tile + 1) * kParts) + tid);
+        g_off[0] = o.x, g_off[1] = o.y, g_off[2] = o.z, g_off[3] = o.w;
+        g_cnt[0] = n.x - o.x, g_cnt[1] = n.y - o.y, g_cnt[2] = n.z - o.z, g_cnt[3] = n.w - o.w;
     }
 
     // ---- keys: strided extraction (conflict-free), one word per position into sorted[]
@@ -385,7 +380,7 @@ __device__ __forceinline__ void scatter_tile(const SortBatch& b, const int seg, 
 #pragma unroll 8
     for (int k = 0; k < kPPer; k++) {
         const int i = k * kPThreads + tid;
-        uint32_t key = 0xFFFFFFFFu;
+        uint32_t key = kPadRecord;
         if (FULL || i < nvalid) {
             const int a = sh + i;
             const uint32_t w0 = *reinterpret_cast<const uint32_t*>(stage + (a & ~3));
@@ -396,7 +391,7 @@ __device__ __forceinline__ void scatter_tile(const SortBatch& b, const int seg, 
     }
     __syncthreads();   // stage is dead from here on
 
-    // ---- records: 32 consecutive positions per thread, nskip inside each group of four
+    // ---- records: 32 consecutive positions per thread, nskip inside each group of four, round-A digit in bits 26-30
     uint32_t rec[kPPer];
     {
         const uint4* src = reinterpret_cast<const uint4*>(sorted + pad(tid * kPPer));
@@ -404,38 +399,52 @@ __device__ __forceinline__ void scatter_tile(const SortBatch& b, const int seg, 
         for (int q = 0; q < kPPer / 4; q++) {
             const uint4 v = src[q];
             const uint32_t k0 = v.x, k1 = v.y, k2 = v.z, k3 = v.w;
-            const uint32_t b0 = ltu_bucket(k0 & kRecKeyMask), b1 = ltu_bucket(k1 & kRecKeyMask), b2 = ltu_bucket(k2 & kRecKeyMask),
-                           b3 = ltu_bucket(k3 & kRecKeyMask);
+            // nvalid is a multiple of 4: a group is entirely valid or entirely padding
+            if (!FULL && k0 == kPadRecord) {
+                rec[4 * q + 0] = rec[4 * q + 1] = rec[4 * q + 2] = rec[4 * q + 3] = kPadRecord;
+                continue;
+            }
+            const uint32_t b0 = ltu_bucket(k0), b1 = ltu_bucket(k1), b2 = ltu_bucket(k2), b3 = ltu_bucket(k3);
             const uint32_t n1 = b1 == b0, n2 = (uint32_t)(b2 == b0) + (b2 == b1), n3 = (uint32_t)(b3 == b0) + (b3 == b1) + (b3 == b2);
-            // nvalid is a multiple of 4: a group is entirely valid or entirely padding (padding keeps 0xFFFFFFFF)
-            const bool padding = !FULL && k0 == 0xFFFFFFFFu;
-            rec[4 * q + 0] = k0;
-            rec[4 * q + 1] = padding ? k1 : k1 | (n1 << 24);
-            rec[4 * q + 2] = padding ? k2 : k2 | (n2 << 24);
-            rec[4 * q + 3] = padding ? k3 : k3 | (n3 << 24);
+            rec[4 * q + 0] = k0 | ((b0 & (kSubBins - 1)) << 26);
+            rec[4 * q + 1] = k1 | (n1 << 24) | ((b1 & (kSubBins - 1)) << 26);
+            rec[4 * q + 2] = k2 | (n2 << 24) | ((b2 & (kSubBins - 1)) << 26);
+            rec[4 * q + 3] = k3 | (n3 << 24) | ((b3 & (kSubBins - 1)) << 26);
         }
     }
 
-    // ---- two LSD rounds
+    // ---- two LSD rounds.  cnt[bin][thread] lives at word bin*288 + row (pad() folded into the constants).
+    const int row = tid + ((tid >> 5) << 2);
 #pragma unroll
     for (int round = 0; round < 2; round++) {
-        const int shift = round * kSubBits;
         // zero the counters (the padding words too; they are never read)
         for (int i = tid; i < kPaddedTile / 4; i += kPThreads) reinterpret_cast<uint4*>(cnt)[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();   // also: every thread holds its records in registers before sorted[] is overwritten
+        // count, four records at a time: the four counters are loaded together (no smem round trip between records);
+        // a record whose digit repeats an earlier one of the batch adds to that record's value, and the stores go out
+        // in order so the last one per counter wins
 #pragma unroll
-        for (int j = 0; j < kPPer; j++) {
-            const uint32_t d = (tile_digit<FULL>(rec[j]) >> shift) & (kSubBins - 1);
-            cnt[pad((int)d * kPThreads + tid)]++;
+        for (int j = 0; j < kPPer; j += 4) {
+            uint32_t d[4], c[4];
+            uint32_t* ptr[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) d[i] = rec[j + i] >> 26, ptr[i] = cnt + d[i] * 288 + row;
+#pragma unroll
+            for (int i = 0; i < 4; i++) c[i] = *ptr[i];
+            c[1] += d[1] == d[0];
+            c[2] += (uint32_t)(d[2] == d[0]) + (d[2] == d[1]);
+            c[3] += (uint32_t)(d[3] == d[0]) + (d[3] == d[1]) + (d[3] == d[2]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) *ptr[i] = c[i] + 1;
         }
         __syncthreads();
         // exclusive scan in (bin, thread) order: thread t owns the 32 consecutive counters [32t, 32t+32)
         {
-            uint4* row = reinterpret_cast<uint4*>(cnt + pad(tid * 32));
+            uint4* rowp = reinterpret_cast<uint4*>(cnt + pad(tid * 32));
             uint32_t run = 0;   // pass 1: the row total (the row is re-read in pass 2: cheaper than 32 live registers)
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                const uint4 v = row[q];
+                const uint4 v = rowp[q];
                 run += v.x + v.y + v.z + v.w;
             }
             uint32_t inc = run;
@@ -449,32 +458,47 @@ __device__ __forceinline__ void scatter_tile(const SortBatch& b, const int seg, 
             for (unsigned w = 0; w < warp; w++) base += wsum[round * 8 + w];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                const uint4 v = row[q];
+                const uint4 v = rowp[q];
                 uint4 o;
                 o.x = base, base += v.x;
                 o.y = base, base += v.y;
                 o.z = base, base += v.z;
                 o.w = base, base += v.w;
-                row[q] = o;
+                rowp[q] = o;
             }
         }
         __syncthreads();
         // the counters are cursors now: stable because a thread walks its records in stream order
 #pragma unroll
-        for (int j = 0; j < kPPer; j++) {
-            const uint32_t d = (tile_digit<FULL>(rec[j]) >> shift) & (kSubBins - 1);
-            uint32_t* c = cnt + pad((int)d * kPThreads + tid);
-            const uint32_t pos = *c;
-            *c = pos + 1;
-            sorted[pad((int)pos)] = rec[j];
+        for (int j = 0; j < kPPer; j += 4) {
+            uint32_t d[4], c[4];
+            uint32_t* ptr[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) d[i] = rec[j + i] >> 26, ptr[i] = cnt + d[i] * 288 + row;
+#pragma unroll
+            for (int i = 0; i < 4; i++) c[i] = *ptr[i];
+            c[1] += d[1] == d[0];
+            c[2] += (uint32_t)(d[2] == d[0]) + (d[2] == d[1]);
+            c[3] += (uint32_t)(d[3] == d[0]) + (d[3] == d[1]) + (d[3] == d[2]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                *ptr[i] = c[i] + 1;
+                sorted[pad((int)c[i])] = rec[j + i];
+            }
         }
         __syncthreads();
         if (round == 0) {
+            // reload in round-A order and switch the spare bits to the round-B digit
             const uint4* src = reinterpret_cast<const uint4*>(sorted + pad(tid * kPPer));
 #pragma unroll
             for (int q = 0; q < kPPer / 4; q++) {
                 const uint4 v = src[q];
-                rec[4 * q + 0] = v.x, rec[4 * q + 1] = v.y, rec[4 * q + 2] = v.z, rec[4 * q + 3] = v.w;
+                const uint32_t r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t hi = (ltu_bucket(r[i] & kRecKeyMask) >> kSubBits) & (kSubBins - 1);
+                    rec[4 * q + i] = (!FULL && r[i] == kPadRecord) ? kPadRecord : (r[i] & kRecMask26) | (hi << 26);
+                }
             }
         }
     }
@@ -506,14 +530,17 @@ __device__ __forceinline__ void scatter_tile(const SortBatch& b, const int seg, 
     for (int k = 0; k < kPPer; k++) {
         const int i = k * kPThreads + tid;
         if (FULL || i < nvalid) {
-            const uint32_t r = sorted[pad(i)];
+            const uint32_t r = sorted[pad(i)] & kRecMask26;
             const uint32_t d = digit_of(r);
             out[gofs[d] + (uint32_t)i - bin_start[d]] = r;
         }
     }
 }
 
-__global__ void __launch_bounds__(kPThreads, 3) ltu_scatter_kernel(const SortBatch b) {
+#ifndef DLT_SCATTER_CTAS
+#define DLT_SCATTER_CTAS 2
+#endif
+__global__ void __launch_bounds__(kPThreads, DLT_SCATTER_CTAS) ltu_scatter_kernel(const SortBatch b) {
     const int seg = blockIdx.y;
     const uint32_t tile = blockIdx.x;
     if (tile >= b.ntiles[seg]) return;
@@ -529,9 +556,9 @@ __global__ void __launch_bounds__(kPThreads, 3) ltu_scatter_kernel(const SortBat
 __global__ void __launch_bounds__(kParts) ltu_plan_kernel(const SortBatch b) {
     const int seg = blockIdx.x;
     const uint32_t p = threadIdx.x;
-    const uint32_t npos = b.npos[seg], nt = b.ntiles[seg], L = b.run_len;
-    const uint32_t o0 = b.cnt[seg][(size_t)p * nt];
-    const uint32_t o1 = p == kParts - 1 ? npos : b.cnt[seg][(size_t)(p + 1) * nt];
+    const uint32_t npos = b.npos[seg], L = b.run_len;
+    const uint32_t o0 = b.cnt[seg][p];   // row 0 of the scanned matrix: first record of every partition
+    const uint32_t o1 = p == kParts - 1 ? npos : b.cnt[seg][p + 1];
     const uint32_t pieces = o1 > o0 ? (o1 - 1) / L - o0 / L + 1 : 0;
     __shared__ uint32_t ws[kParts / 32];
     const unsigned lane = p & 31, warp = p >> 5;
@@ -805,8 +832,8 @@ SegPlan plan_segment(size_t len, uint32_t run_len) {
     p.max_pieces = p.npos / run_len + 1 + kParts;   // one partial piece at either end of every partition
     p.max_chunks = (p.max_pieces + kChunkPieces - 1) / kChunkPieces;
     p.rec_bytes = align_up(p.npos * 4, 256);
-    p.cnt_bytes = align_up(p.ntiles * kParts * 4, 256);
-    p.blk_bytes = align_up((p.ntiles * kParts + kScanBlockElems - 1) / kScanBlockElems * 4, 256);
+    p.cnt_bytes = align_up((p.ntiles + 1) * kParts * 4, 256);
+    p.blk_bytes = align_up((p.ntiles + kColChunk - 1) / kColChunk * kParts * 4, 256);
     p.poff_bytes = p.pbase_bytes = align_up((kParts + 1) * 4, 256);
     p.part_bytes = align_up(p.max_pieces * 2, 256);
     p.state_bytes = align_up(p.max_pieces * kClasses * 4, 256);
@@ -917,7 +944,7 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
                 b.dkey[k] = reinterpret_cast<uint32_t*>(take(pl.dkey_bytes));
                 b.sum_word[k] = reinterpret_cast<uint32_t*>(take(pl.sumw_bytes));
                 b.sum_part[k] = reinterpret_cast<uint16_t*>(take(pl.sump_bytes));
-                const uint32_t sblk = (uint32_t)((pl.ntiles * kParts + kScanBlockElems - 1) / kScanBlockElems);
+                const uint32_t sblk = (uint32_t)((pl.ntiles + kColChunk - 1) / kColChunk);
                 max_tiles = std::max(max_tiles, (uint32_t)pl.ntiles);
                 max_scan_blocks = std::max(max_scan_blocks, sblk);
                 max_piece_warps = std::max(max_piece_warps, (uint32_t)((pl.max_pieces + 31) / 32));
@@ -928,9 +955,9 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
             if (attr != cudaSuccess) return fail(attr);
             const dim3 tiles(max_tiles, nl), scan_grid(max_scan_blocks, nl);
             ltu_hist_kernel<<<tiles, kSortThreads, 0, stream>>>(b);
-            ltu_scan_sums_kernel<<<scan_grid, 256, 0, stream>>>(b);
-            ltu_scan_blocks_kernel<<<nl, 32, 0, stream>>>(b);
-            ltu_scan_apply_kernel<<<scan_grid, 256, 0, stream>>>(b);
+            ltu_colsum_kernel<<<scan_grid, kParts, 0, stream>>>(b);
+            ltu_colbase_kernel<<<nl, kParts, 0, stream>>>(b);
+            ltu_colapply_kernel<<<scan_grid, kParts, 0, stream>>>(b);
             ltu_scatter_kernel<<<tiles, kPThreads, kScatterSmemBytes, stream>>>(b);
             ltu_plan_kernel<<<nl, kParts, 0, stream>>>(b);
             ltu_runs_kernel<<<dim3(max_piece_warps, nl), 32, 0, stream>>>(b, d_matches);
