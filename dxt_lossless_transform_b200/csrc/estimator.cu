@@ -578,12 +578,11 @@ __global__ void __launch_bounds__(kParts) ltu_plan_kernel(const SortBatch b) {
 }
 
 // ---- runs: one thread per piece, private class table in shared memory ---------------------------------
-__device__ __forceinline__ uint4 ldg_nc16(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+
+__device__ __forceinline__ void ldg_nc32(const void* p, uint4& a, uint4& b) {   // one 256-bit load: a whole sector per lane
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                  : "l"(p));
-    return r;
 }
 
 // Every piece-thread streams its own piece: tens of thousands of concurrent 128-byte reads at unrelated addresses
@@ -691,24 +690,27 @@ __global__ void __launch_bounds__(32, kRunsWarpsPerSm) ltu_runs_kernel(const Sor
             // prime the first prefetch window; the loop keeps one window ahead
             const uint32_t w0 = (i + kPrefetchRecords - 1) / kPrefetchRecords * kPrefetchRecords;   // first window boundary
             if (w0 + 4 <= end) prefetch_l2_bulk(rec + w0, (min(kPrefetchRecords, end - w0) & ~3u) * 4u);   // multiple of 16 bytes
-            uint4 cur[8], nxt[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) cur[k] = ldg_nc16(rec + i + 4 * k);
+            // two 16-record buffers (two 256-bit loads each): while one is processed the other one's loads are in flight
+            uint4 bufa[4], bufb[4];
+            ldg_nc32(rec + i, bufa[0], bufa[1]);
+            ldg_nc32(rec + i + 8, bufa[2], bufa[3]);
             for (; i + 32 <= end; i += 32) {
-                const bool more = i + 64 <= end;
                 if ((i & (kPrefetchRecords - 1)) == 0) {
                     const uint32_t ahead = i + kPrefetchRecords;   // the window after the one being read
                     if (ahead + 4 <= end) prefetch_l2_bulk(rec + ahead, (min(kPrefetchRecords, end - ahead) & ~3u) * 4u);
                 }
-                if (more) {
+                ldg_nc32(rec + i + 16, bufb[0], bufb[1]);
+                ldg_nc32(rec + i + 24, bufb[2], bufb[3]);
+                asm volatile("" ::: "memory");   // keep the loads ahead of the table traffic below
 #pragma unroll
-                    for (int k = 0; k < 8; k++) nxt[k] = ldg_nc16(rec + i + 32 + 4 * k);   // in flight while `cur` is processed
+                for (int k = 0; k < 4; k++) process4(bufa[k]);
+                if (i + 64 <= end) {
+                    ldg_nc32(rec + i + 32, bufa[0], bufa[1]);
+                    ldg_nc32(rec + i + 40, bufa[2], bufa[3]);
                 }
-                asm volatile("" ::: "memory");   // keep the prefetch ahead of the table traffic below
+                asm volatile("" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < 8; k++) process4(cur[k]);
-#pragma unroll
-                for (int k = 0; k < 8; k++) cur[k] = nxt[k];
+                for (int k = 0; k < 4; k++) process4(bufb[k]);
             }
         }
         for (; i < end; i++) process(__ldg(rec + i), true);
