@@ -283,10 +283,12 @@ __global__ void __launch_bounds__(kParts) ltu_colbase_kernel(const SortBatch b) 
     const uint32_t d = threadIdx.x;
     uint32_t* blk = b.blk[seg];
     uint32_t total = 0;
-    for (uint32_t c = 0; c < nchunks; c++) {   // exclusive running sum down the column of chunk sums
-        const uint32_t v = blk[(size_t)c * kParts + d];
-        blk[(size_t)c * kParts + d] = total;
-        total += v;
+    for (uint32_t c = 0; c < nchunks; c += 8) {   // column total (8 independent loads in flight)
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = c + k < nchunks ? blk[(size_t)(c + k) * kParts + d] : 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) total += v[k];
     }
     // digit bases: exclusive scan of the column totals over the digits
     __shared__ uint32_t ws[kParts / 32];
@@ -300,7 +302,17 @@ __global__ void __launch_bounds__(kParts) ltu_colbase_kernel(const SortBatch b) 
     __syncthreads();
     uint32_t base = inc - total;
     for (unsigned w = 0; w < warp; w++) base += ws[w];
-    for (uint32_t c = 0; c < nchunks; c++) blk[(size_t)c * kParts + d] += base;
+    uint32_t run = base;   // exclusive running sum down the column of chunk sums, starting at the digit's base
+    for (uint32_t c = 0; c < nchunks; c += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = c + k < nchunks ? blk[(size_t)(c + k) * kParts + d] : 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (c + k < nchunks) blk[(size_t)(c + k) * kParts + d] = run;
+            run += v[k];
+        }
+    }
     b.cnt[seg][(size_t)nt * kParts + d] = base + total;   // the extra row: end of the digit's partition
 }
 

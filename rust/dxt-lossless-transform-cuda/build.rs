@@ -8,7 +8,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let lib = out.join("libdxt_lossless_transform_cuda.so");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
-    let sources = ["bcn_kernels.cu", "host_pipeline.cu", "estimator.cu", "auto_search.cu", "cabi.cu"];
+    let sources = ["bcn_kernels.cu", "host_pipeline.cu", "estimator.cu", "auto_search.cu", "cabi.cu", "file_formats.cu"];
 
     let status = Command::new(&nvcc)
         .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"])

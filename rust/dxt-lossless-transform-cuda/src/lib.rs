@@ -12,6 +12,8 @@
 //! whose reference signature has no return value).
 #![allow(non_camel_case_types)]
 
+pub mod file_formats; // TransformBundle / dispatch / DdsHandler over the dltff_* and dltdds_* symbols
+
 use core::ffi::c_void;
 use dxt_lossless_transform_api_common::estimate::SizeEstimationOperations;
 use dxt_lossless_transform_bc1::Bc1TransformSettings;
