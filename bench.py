@@ -130,6 +130,14 @@ def cpu_roundtrip_gbs(sample_bytes: int, threads: int, steps: int, warmup: int) 
     return traffic / dt / 1e9, dt * 1e3
 
 
+def cpu_isa() -> str:
+    import oracle
+
+    L = oracle.lib()
+    L.orc_cpu_baseline_uses_avx2.restype = C.c_int
+    return "explicit AVX2 BC1 path" if L.orc_cpu_baseline_uses_avx2() else "word-wise scalar BC1 path"
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -145,7 +153,7 @@ def run_reference_arm(args) -> None:
                    "note": "CPU restatement (oracle/) of the reference path; the Rust reference cannot be built here"},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
                          "sample": f"{sample >> 20} MiB BC1, 8 settings x (transform+untransform) per step, "
-                                   f"scalar C port, {cores} threads by block range"},
+                                   f"C port of the reference ({cpu_isa()}), {cores} threads by block range"},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -352,8 +360,8 @@ def run_gpu_arm(args) -> None:
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_all, "unit": "GB/s", "cores": cores, "kind": "port",
                              "single_thread_value": cpu_one,
-                             "sample": f"{sample >> 20} MiB BC1, the same 8-settings round trip, scalar C port of the "
-                                       f"reference (oracle/), {cores} threads by block range"},
+                             "sample": f"{sample >> 20} MiB BC1, the same 8-settings round trip, C port of the "
+                                       f"reference (oracle/, {cpu_isa()}), {cores} threads by block range"},
             "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
         }
         print(json.dumps(out))

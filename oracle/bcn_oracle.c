@@ -219,6 +219,103 @@ static void bc1_range_fast(int inverse, const uint8_t *restrict in, uint8_t *res
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Explicit AVX2 BC1 path for the CPU BASELINE timing: eight blocks per iteration, colours gathered with dword
+ * shuffles, YCoCg-R on sixteen 16-bit lanes, endpoints split with a byte shuffle — the shape of the reference's
+ * AVX2 tier (core/dxt-lossless-transform-bc1/src/transform/standard/transform/avx2.rs and
+ * common/src/intrinsics/color_565/decorrelate/avx2.rs), restated.  Used by orc_bcn_run_mt / orc_bcn_run_range when
+ * the host CPU has AVX2; tests/test_oracle.py checks it against bc1_range for every settings combination.
+ * ---------------------------------------------------------------------------------------- */
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define ORC_AVX2 __attribute__((target("avx2")))
+
+ORC_AVX2 static inline __m256i decorr16(__m256i v, int variant) {
+    const __m256i m5 = _mm256_set1_epi16(31), m1 = _mm256_set1_epi16(1);
+    __m256i r = _mm256_srli_epi16(v, 11), g = _mm256_and_si256(_mm256_srli_epi16(v, 6), m5);
+    __m256i gl = _mm256_and_si256(_mm256_srli_epi16(v, 5), m1), b = _mm256_and_si256(v, m5);
+    __m256i co = _mm256_and_si256(_mm256_sub_epi16(r, b), m5);
+    __m256i t = _mm256_and_si256(_mm256_add_epi16(b, _mm256_srli_epi16(co, 1)), m5);
+    __m256i cg = _mm256_and_si256(_mm256_sub_epi16(g, t), m5);
+    __m256i y = _mm256_and_si256(_mm256_add_epi16(t, _mm256_srli_epi16(cg, 1)), m5);
+    if (variant == ORC_VARIANT_1)
+        return _mm256_or_si256(_mm256_or_si256(_mm256_slli_epi16(y, 11), _mm256_slli_epi16(co, 6)), _mm256_or_si256(_mm256_slli_epi16(gl, 5), cg));
+    if (variant == ORC_VARIANT_2)
+        return _mm256_or_si256(_mm256_or_si256(_mm256_slli_epi16(gl, 15), _mm256_slli_epi16(y, 10)), _mm256_or_si256(_mm256_slli_epi16(co, 5), cg));
+    return _mm256_or_si256(_mm256_or_si256(_mm256_slli_epi16(y, 11), _mm256_slli_epi16(co, 6)), _mm256_or_si256(_mm256_slli_epi16(cg, 1), gl));
+}
+ORC_AVX2 static inline __m256i recorr16(__m256i v, int variant) {
+    const __m256i m5 = _mm256_set1_epi16(31), m1 = _mm256_set1_epi16(1);
+    __m256i y, co, cg, gl;
+    if (variant == ORC_VARIANT_1) {
+        y = _mm256_srli_epi16(v, 11), co = _mm256_and_si256(_mm256_srli_epi16(v, 6), m5);
+        gl = _mm256_and_si256(_mm256_srli_epi16(v, 5), m1), cg = _mm256_and_si256(v, m5);
+    } else if (variant == ORC_VARIANT_2) {
+        gl = _mm256_srli_epi16(v, 15), y = _mm256_and_si256(_mm256_srli_epi16(v, 10), m5);
+        co = _mm256_and_si256(_mm256_srli_epi16(v, 5), m5), cg = _mm256_and_si256(v, m5);
+    } else {
+        y = _mm256_srli_epi16(v, 11), co = _mm256_and_si256(_mm256_srli_epi16(v, 6), m5);
+        cg = _mm256_and_si256(_mm256_srli_epi16(v, 1), m5), gl = _mm256_and_si256(v, m1);
+    }
+    __m256i t = _mm256_and_si256(_mm256_sub_epi16(y, _mm256_srli_epi16(cg, 1)), m5);
+    __m256i g = _mm256_and_si256(_mm256_add_epi16(cg, t), m5);
+    __m256i b = _mm256_and_si256(_mm256_sub_epi16(t, _mm256_srli_epi16(co, 1)), m5);
+    __m256i r = _mm256_and_si256(_mm256_add_epi16(b, co), m5);
+    return _mm256_or_si256(_mm256_or_si256(_mm256_slli_epi16(r, 11), _mm256_slli_epi16(g, 6)), _mm256_or_si256(_mm256_slli_epi16(gl, 5), b));
+}
+
+#define BC1_AVX2_LOOP(VARIANT)                                                                                       \
+    for (; i + 8 <= b1; i += 8) {                                                                                    \
+        if (!inverse) {                                                                                              \
+            const __m256 a = _mm256_castsi256_ps(_mm256_loadu_si256((const __m256i *)(in + 8 * i)));                 \
+            const __m256 b = _mm256_castsi256_ps(_mm256_loadu_si256((const __m256i *)(in + 8 * i + 32)));            \
+            __m256i col = _mm256_permute4x64_epi64(_mm256_castps_si256(_mm256_shuffle_ps(a, b, 0x88)), 0xD8);        \
+            const __m256i idx = _mm256_permute4x64_epi64(_mm256_castps_si256(_mm256_shuffle_ps(a, b, 0xDD)), 0xD8);  \
+            if (VARIANT) col = decorr16(col, VARIANT);                                                               \
+            if (split) {                                                                                             \
+                const __m256i s = _mm256_permute4x64_epi64(_mm256_shuffle_epi8(col, split_mask), 0xD8);              \
+                _mm_storeu_si128((__m128i *)(out + 2 * i), _mm256_castsi256_si128(s));                               \
+                _mm_storeu_si128((__m128i *)(out + len / 4 + 2 * i), _mm256_extracti128_si256(s, 1));                \
+            } else _mm256_storeu_si256((__m256i *)(out + 4 * i), col);                                               \
+            _mm256_storeu_si256((__m256i *)(out + len / 2 + 4 * i), idx);                                            \
+        } else {                                                                                                     \
+            __m256i col;                                                                                             \
+            if (split) {                                                                                             \
+                const __m256i c0 = _mm256_cvtepu16_epi32(_mm_loadu_si128((const __m128i *)(in + 2 * i)));            \
+                const __m256i c1 = _mm256_cvtepu16_epi32(_mm_loadu_si128((const __m128i *)(in + len / 4 + 2 * i)));  \
+                col = _mm256_or_si256(c0, _mm256_slli_epi32(c1, 16));                                                \
+            } else col = _mm256_loadu_si256((const __m256i *)(in + 4 * i));                                          \
+            const __m256i idx = _mm256_loadu_si256((const __m256i *)(in + len / 2 + 4 * i));                         \
+            if (VARIANT) col = recorr16(col, VARIANT);                                                               \
+            const __m256i lo = _mm256_unpacklo_epi32(col, idx), hi = _mm256_unpackhi_epi32(col, idx);                \
+            _mm256_storeu_si256((__m256i *)(out + 8 * i), _mm256_permute2x128_si256(lo, hi, 0x20));                  \
+            _mm256_storeu_si256((__m256i *)(out + 8 * i + 32), _mm256_permute2x128_si256(lo, hi, 0x31));             \
+        }                                                                                                            \
+    }
+
+ORC_AVX2 static void bc1_range_avx2(int inverse, const uint8_t *restrict in, uint8_t *restrict out, size_t n, size_t b0,
+                                    size_t b1, int variant, int split) {
+    const size_t len = n * 8;
+    const __m256i split_mask = _mm256_setr_epi8(0, 1, 4, 5, 8, 9, 12, 13, 2, 3, 6, 7, 10, 11, 14, 15,
+                                                0, 1, 4, 5, 8, 9, 12, 13, 2, 3, 6, 7, 10, 11, 14, 15);
+    size_t i = b0;
+    switch (variant) {
+    case ORC_VARIANT_NONE: BC1_AVX2_LOOP(0) break;
+    case ORC_VARIANT_1: BC1_AVX2_LOOP(1) break;
+    case ORC_VARIANT_2: BC1_AVX2_LOOP(2) break;
+    default: BC1_AVX2_LOOP(3) break;
+    }
+    if (i < b1) bc1_range_fast(inverse, in, out, n, i, b1, variant, split);   /* < 8 blocks left */
+}
+static int have_avx2(void) { return __builtin_cpu_supports("avx2"); }
+#else
+static int have_avx2(void) { return 0; }
+static void bc1_range_avx2(int inverse, const uint8_t *in, uint8_t *out, size_t n, size_t b0, size_t b1, int variant, int split) {
+    bc1_range_fast(inverse, in, out, n, b0, b1, variant, split);
+}
+#endif
+int orc_cpu_baseline_uses_avx2(void) { return have_avx2(); }
+
 void orc_bc1_transform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc1_range(0, in, out, len / 8, 0, len / 8, v, s); }
 void orc_bc1_untransform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc1_range(1, in, out, len / 8, 0, len / 8, v, s); }
 void orc_bc2_transform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc2_range(0, in, out, len / 16, 0, len / 16, v, s); }
@@ -452,7 +549,10 @@ typedef struct {
 static void *mt_worker(void *arg) {
     mt_job *j = (mt_job *)arg;
     switch (j->format) {
-    case 1: bc1_range_fast(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c); break;
+    case 1:
+        if (have_avx2()) bc1_range_avx2(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c);
+        else bc1_range_fast(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c);
+        break;
     case 2: bc2_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c); break;
     default: bc3_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_a, j->split_c); break;
     }

@@ -28,6 +28,9 @@
 
 #ifdef __cplusplus
 extern "C" {
+/* 1 when orc_bcn_run_mt / orc_bcn_run_range take the explicit AVX2 BC1 path on this host. */
+int orc_cpu_baseline_uses_avx2(void);
+
 #endif
 
 /* Internal numbering of common/src/color_565/decorrelate.rs:72-84. */

@@ -347,3 +347,55 @@ def test_split_color_endpoints(dlt, torch):
                 assert np.array_equal(d_out.cpu().numpy()[off:off + data.size], want)
     with pytest.raises(dlt.api.InvalidLength):
         dlt.split_color_endpoints(np.zeros(6, np.uint8), np.zeros(6, np.uint8))
+
+
+def test_concurrent_host_threads(dlt):
+    """SURVEY §8b threading contract: the entry points are synchronous and re-entrant; distinct host threads (each with
+    its own builders) may call them concurrently.  Contexts (streams, slots, scratch) are pooled per device."""
+    import threading
+
+    from dxt_lossless_transform_b200 import file_formats as ff
+    from dxt_lossless_transform_b200 import synth
+    from dds_fixtures import FO, make_dds
+
+    SETTINGS = {fmt: settings_list(dlt, fmt) for fmt in (1, 2, 3)}
+    errors = []
+
+    def worker(k: int):
+        try:
+            rng = np.random.default_rng(k)
+            for it in range(6):
+                fmt = 1 + (k + it) % 3
+                nblocks = int(rng.integers(1, 60_000))
+                data = synth.texture_blocks(fmt, nblocks, seed=100 * k + it)
+                s = list(SETTINGS[fmt])[(k * 7 + it) % len(SETTINGS[fmt])]
+                out, back = np.zeros_like(data), np.zeros_like(data)
+                dlt.transform_with_settings(fmt, data, out, s)
+                assert np.array_equal(out, oracle.transform(fmt, data, *orc_args(s))), (k, it, "transform")
+                dlt.untransform_with_settings(fmt, out, back, s)
+                assert np.array_equal(back, data), (k, it, "roundtrip")
+                if it % 3 == 0:  # a best-settings search (estimator scratch, several launches) in the mix
+                    fa = 1 + k % 2
+                    d2 = synth.texture_blocks(fa, 9_000 + 37 * k, seed=k)
+                    o2 = np.zeros_like(d2)
+                    auto = dlt.transform_bc1_auto if fa == 1 else dlt.transform_bc2_auto
+                    best = auto(d2, o2, dlt.Bc1EstimateSettings(dlt.LosslessTransformUtilsSizeEstimation(), False))
+                    want_out, want = oracle.auto(fa, d2, False)
+                    assert (int(best.decorrelation_mode), False, bool(best.split_colour_endpoints)) == want, (k, it, "auto")
+                    assert np.array_equal(o2, want_out), (k, it, "auto bytes")
+                if it % 3 == 1:  # and a DDS file through the bundle
+                    dds = make_dds(FO.DDS_BC1, 64, 32, 3)
+                    t, b2 = np.zeros_like(dds), np.zeros_like(dds)
+                    h = ff.DdsHandler()
+                    h.transform_bundle(dds, t, ff.TransformBundle.default_all())
+                    h.untransform(t, b2)
+                    assert np.array_equal(b2, dds), (k, it, "dds")
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
