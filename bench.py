@@ -344,6 +344,44 @@ def run_gpu_arm(args) -> None:
         "api": "dltbc1core_transform / dltbc1core_untransform on pinned host buffers",
     }
 
+    # ---- BASELINE configs[3] beside the headline: determine-best-settings (GPU LTU estimator + search) on a 64 MiB
+    # BC1 payload, device resident and through host buffers, with the CPU oracle's search on a bounded sample
+    auto = None
+    if rank == 0 and not args.no_auto:
+        import oracle
+
+        nb = (64 << 20) // BPB
+        a_host = synth.texture_blocks(FMT, nb, seed=synth.BASE_SEED + 4)
+        a_in = torch.from_numpy(a_host).cuda()
+        a_out = torch.empty_like(a_in)
+        pin_in, pin_out = dlt.alloc_pinned(a_host.size), dlt.alloc_pinned(a_host.size)
+        pin_in.array[:] = a_host
+        est = dlt.Bc1EstimateSettings(dlt.LosslessTransformUtilsSizeEstimation(), False)
+        auto = {"workload": "transform_bc1_auto, LTU-semantics estimator, 64 MiB texture-like BC1 payload", "unit": "ms"}
+        for name, use_all in (("fast_k4", False), ("comprehensive_k8", True)):
+            dlt.transform_auto_device(FMT, a_in.data_ptr(), a_out.data_ptr(), a_host.size, use_all)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                best, _sizes = dlt.transform_auto_device(FMT, a_in.data_ptr(), a_out.data_ptr(), a_host.size, use_all)
+            auto[name + "_device_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+            auto[name + "_best"] = f"{best.decorrelation_mode.name}/{'split' if best.split_colour_endpoints else 'nosplit'}"
+        est.use_all_decorrelation_modes = False
+        dlt.transform_bc1_auto(pin_in.array, pin_out.array, est)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dlt.transform_bc1_auto(pin_in.array, pin_out.array, est)
+        auto["fast_k4_host_e2e_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+        small = a_host[: 8 << 20].copy()
+        t0 = time.perf_counter()
+        want_out, want = oracle.auto(FMT, small, False)
+        auto["cpu_oracle_fast_k4_8MiB_sample_ms"] = (time.perf_counter() - t0) * 1e3
+        chk = np.zeros_like(small)
+        got = dlt.transform_bc1_auto(small, chk, est)
+        assert (int(got.decorrelation_mode), False, bool(got.split_colour_endpoints)) == want and np.array_equal(chk, want_out)
+        auto["cpu_oracle_fast_k4_64MiB_extrapolated_ms"] = auto["cpu_oracle_fast_k4_8MiB_sample_ms"] * 8
+        auto["note"] = "GPU choice and bytes checked against the oracle on the 8 MiB sample; CPU figure is single-thread"
+
     if rank == 0:
         cores = os.cpu_count() or 1
         sample = 128 << 20
@@ -364,6 +402,8 @@ def run_gpu_arm(args) -> None:
                                        f"reference (oracle/, {cpu_isa()}), {cores} threads by block range"},
             "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
         }
+        if auto:
+            out["determine_best_settings"] = auto
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -377,6 +417,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gib-per-gpu", type=float, default=1.0)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-auto", action="store_true", help="skip the determine-best-settings side measurement")
     ap.add_argument("--profile-mode", action="store_true",
                     help="kernel-only run for ncu: skips the e2e and cpu_baseline legs (never a bench value)")
     args = ap.parse_args()

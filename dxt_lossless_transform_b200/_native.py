@@ -68,6 +68,11 @@ class DltcudaPayload(C.Structure):
     _fields_ = [("input", C.c_void_p), ("output", C.c_void_p), ("len", C.c_size_t), ("settings", DltcudaSettings)]
 
 
+class DltcudaAutoJob(C.Structure):
+    _fields_ = [("format", C.c_uint8), ("input", C.c_void_p), ("output", C.c_void_p), ("len", C.c_size_t),
+                ("out_settings", DltcudaSettings), ("status", C.c_int32)]
+
+
 class DltffResult(C.Structure):  # dxt_lossless_transform_file_formats.h
     _fields_ = [("error_code", C.c_int32), ("detail_a", C.c_size_t), ("detail_b", C.c_size_t)]
 
@@ -146,6 +151,7 @@ SIGNATURES.update(
             [C.c_int, _P, _P, _SZ, C.c_bool, C.POINTER(DltcudaSettings), C.POINTER(_SZ)],
         ),
         "dltcuda_auto_candidates": (C.c_int, [C.c_int, C.c_bool, C.POINTER(DltcudaSettings)]),
+        "dltcuda_transform_auto_batch": (C.c_int, [C.POINTER(DltcudaAutoJob), _SZ, C.c_bool]),
     }
 )
 

@@ -589,6 +589,32 @@ def transform_auto_device(fmt: int, d_in: int, d_out: int, nbytes: int, use_all:
     return best, [est[i] for i in range(k)]
 
 
+def transform_auto_batch(items, use_all: bool = False) -> list:
+    """transform_bcN_auto (GPU LTU estimator) for a batch of independent host payloads: ``items`` is a list of
+    ``(fmt, input, output)``; returns the winning settings per payload.  One set of estimator launches serves all
+    candidates of all payloads (dltcuda_transform_auto_batch)."""
+    jobs = (N.DltcudaAutoJob * len(items))()
+    keep = []
+    for i, (fmt, inp, out) in enumerate(items):
+        ip, il, ka = _ro(inp)
+        op, ol, kb = _rw(out)
+        if il % block_bytes(fmt):
+            raise InvalidLength(il)
+        if ol < il:
+            raise OutputBufferTooSmall(il, ol)
+        keep += [ka, kb]
+        jobs[i] = N.DltcudaAutoJob(fmt, ip, op, il, N.DltcudaSettings(), 0)
+    _check_device(N.lib().dltcuda_transform_auto_batch(jobs, len(items), bool(use_all)))
+    out = []
+    for j in jobs:
+        s = j.out_settings
+        if j.format == 3:
+            out.append(Bc3TransformSettings(YCoCgVariant(s.decorrelation_mode), bool(s.split_alpha_endpoints), bool(s.split_colour_endpoints)))
+        else:
+            out.append(_SETTINGS[j.format](YCoCgVariant(s.decorrelation_mode), bool(s.split_colour_endpoints)))
+    return out
+
+
 def kernel_launch_count() -> int:
     return N.lib().dltcuda_kernel_launch_count()
 

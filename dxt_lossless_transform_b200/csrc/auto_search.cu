@@ -4,6 +4,8 @@
 #include "bcn_kernels.h"
 #include "estimator.h"
 
+#include <vector>
+
 namespace dlt {
 
 int candidate_order(int format, bool use_all, Settings out[kMaxCandidates]) {
@@ -117,6 +119,108 @@ Status auto_ltu_device(Context* ctx, int format, const uint8_t* d_in, uint8_t* d
     }
     *best = best_s;
     return Status::kOk;
+}
+
+Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_all, cudaStream_t stream) {
+    constexpr size_t kScratchBudget = (size_t)12 << 30;
+    auto cuda_fail = [](cudaError_t e) {
+        note_cuda_error(e);
+        return Status::kCudaError;
+    };
+    struct Cand {
+        int job, index;      // candidate `index` of job `job`
+        uint8_t* image;      // its transformed image in the scratch
+        int first_seg, nseg;
+    };
+    int j0 = 0;
+    while (j0 < njobs) {
+        // ---- the largest group [j0, j1) whose images + estimator scratch fit the budget
+        std::vector<LtuSegment> segs;
+        std::vector<Cand> cands;
+        size_t image_bytes = 0;
+        int j1 = j0;
+        for (; j1 < njobs; j1++) {
+            const AutoJob& job = jobs[j1];
+            if (job.len == 0) continue;
+            Settings order[kMaxCandidates];
+            const int k = candidate_order(job.format, use_all, order);
+            EstimateRange ranges[2];
+            const int nr = estimate_ranges(job.format, job.len, ranges);
+            const size_t img = (job.len + 255) / 256 * 256;
+            const size_t mark_segs = segs.size(), mark_cands = cands.size();
+            for (int c = 0; c < k; c++) {
+                cands.push_back(Cand{j1, c, nullptr, (int)segs.size(), nr});
+                for (int r = 0; r < nr; r++) segs.push_back(LtuSegment{nullptr, ranges[r].len});
+            }
+            const size_t need = image_bytes + (size_t)k * img + ltu_scratch_bytes(segs.data(), (int)segs.size());
+            if (need > kScratchBudget && j1 > j0) {   // this job starts the next group
+                segs.resize(mark_segs), cands.resize(mark_cands);
+                break;
+            }
+            image_bytes += (size_t)k * img;
+        }
+        if (!cands.empty() && image_bytes + ltu_scratch_bytes(segs.data(), (int)segs.size()) > kScratchBudget) {
+            // a single job that is too large for one group: the single-payload path batches its candidates itself
+            AutoJob& job = jobs[j0];
+            const Status st = auto_ltu_device(ctx, job.format, job.d_in, job.d_out, job.len, use_all, &job.best, job.sizes, stream);
+            if (st != Status::kOk) return st;
+            j0 = j0 + 1;
+            continue;
+        }
+        Status st = ensure_scratch(ctx, image_bytes + ltu_scratch_bytes(segs.data(), (int)segs.size()));
+        if (st != Status::kOk) return st;
+
+        // ---- transform every candidate of every job of the group, point the segments at the endpoint streams
+        uint8_t* next_image = ctx->d_scratch;
+        for (Cand& cd : cands) {
+            const AutoJob& job = jobs[cd.job];
+            Settings order[kMaxCandidates];
+            candidate_order(job.format, use_all, order);
+            EstimateRange ranges[2];
+            estimate_ranges(job.format, job.len, ranges);
+            const size_t n = job.len / block_bytes(job.format);
+            cd.image = next_image;
+            next_image += (job.len + 255) / 256 * 256;
+            const cudaError_t e = launch_transform(order[cd.index], job.d_in, reference_layout(cd.image, n, 0, order[cd.index]), n, stream);
+            if (e != cudaSuccess) return cuda_fail(e);
+            for (int r = 0; r < cd.nseg; r++) segs[cd.first_seg + r].d_ptr = cd.image + ranges[r].offset;
+        }
+        std::vector<uint64_t> matches(segs.size(), 0);
+        if (!segs.empty()) {
+            st = ltu_matches_device(segs.data(), (int)segs.size(), matches.data(), stream, ctx->d_scratch + image_bytes,
+                                    ctx->d_scratch_cap - image_bytes);
+            if (st != Status::kOk) return st;
+        }
+
+        // ---- winners (strict '<': the first candidate in test order wins ties) and their final transforms
+        for (int j = j0; j < j1; j++) {
+            // an empty payload: every estimate is 0, the first candidate in test order wins (as in the reference)
+            Settings order[kMaxCandidates];
+            candidate_order(jobs[j].format, use_all, order);
+            jobs[j].best = order[0];
+            for (int c = 0; c < kMaxCandidates; c++) jobs[j].sizes[c] = 0;
+        }
+        std::vector<size_t> best_size((size_t)(j1 - j0), SIZE_MAX);
+        for (const Cand& cd : cands) {
+            AutoJob& job = jobs[cd.job];
+            Settings order[kMaxCandidates];
+            candidate_order(job.format, use_all, order);
+            size_t total = 0;
+            for (int r = 0; r < cd.nseg; r++) total += ltu_estimate_from_matches(segs[cd.first_seg + r].len, matches[cd.first_seg + r]);
+            job.sizes[cd.index] = total;
+            if (total < best_size[cd.job - j0]) best_size[cd.job - j0] = total, job.best = order[cd.index];
+        }
+        for (int j = j0; j < j1; j++) {
+            const AutoJob& job = jobs[j];
+            if (job.len == 0) continue;
+            const size_t n = job.len / block_bytes(job.format);
+            const cudaError_t e = launch_transform(job.best, job.d_in, reference_layout(job.d_out, n, 0, job.best), n, stream);
+            if (e != cudaSuccess) return cuda_fail(e);
+        }
+        j0 = j1;
+    }
+    const cudaError_t e = cudaStreamSynchronize(stream);
+    return e == cudaSuccess ? Status::kOk : cuda_fail(e);
 }
 
 }  // namespace dlt

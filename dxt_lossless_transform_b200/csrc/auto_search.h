@@ -38,4 +38,19 @@ int estimate_ranges(int format, size_t len, EstimateRange out[2]);
 Status auto_ltu_device(Context* ctx, int format, const uint8_t* d_in, uint8_t* d_out, size_t len, bool use_all_modes,
                        Settings* best, size_t* sizes, cudaStream_t stream);
 
+// The same search for MANY independent device-resident payloads at once (a directory of textures): the candidates of
+// all payloads are transformed into scratch images and every endpoint stream of every candidate becomes one segment
+// of a single estimator call, so the launch count does not grow with the number of payloads.  Jobs that do not fit
+// the scratch budget together are processed in consecutive groups; a job too large for a group of its own goes
+// through auto_ltu_device.  d_out of every job holds its winner's transform on return.  Synchronises `stream`.
+struct AutoJob {
+    int format;
+    const uint8_t* d_in;
+    uint8_t* d_out;
+    size_t len;
+    Settings best;                 // out
+    size_t sizes[kMaxCandidates];  // out: per-candidate estimates in test order
+};
+Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_all_modes, cudaStream_t stream);
+
 }  // namespace dlt

@@ -707,6 +707,79 @@ DLT_EXPORT int dltcuda_transform_auto_device(int format, const uint8_t* d_input,
     return dltcuda_status(st);
 }
 
+// transform_bcN_auto with the GPU LTU estimator for a BATCH of independent host payloads (a directory of textures):
+// one upload per payload, ONE set of estimator launches for all candidates of all payloads, one download per payload.
+// jobs[i].status receives that job's DltcudaStatus; the return value is the first failure (or Ok).
+namespace dlt {
+namespace cabi {
+bool is_gpu_ltu_estimator(const DltSizeEstimator& e) { return is_gpu_ltu(e); }
+
+int auto_batch_host(DltcudaAutoJob* jobs, size_t count, bool use_all) {
+    if (count == 0) return kDltcudaOk;
+    if (!jobs) return kDltcudaNullPointer;
+    int first_error = kDltcudaOk;
+    auto note = [&first_error](DltcudaAutoJob& j, int st) {
+        j.status = st;
+        if (st != kDltcudaOk && first_error == kDltcudaOk) first_error = st;
+    };
+    Status st;
+    Context* ctx = acquire_context(-1, &st);
+    if (!ctx) return dltcuda_status(st);
+    struct Releaser {
+        Context* c;
+        ~Releaser() { release_context(c); }
+    } releaser{ctx};
+    cudaStream_t s = ctx->stream[0];
+    constexpr size_t kRoundBytes = (size_t)1 << 30;   // payload bytes uploaded per round
+
+    size_t i0 = 0;
+    while (i0 < count) {
+        // ---- a round: consecutive valid jobs up to kRoundBytes (at least one)
+        std::vector<size_t> idx;
+        std::vector<size_t> offset;
+        size_t total = 0, i1 = i0;
+        for (; i1 < count; i1++) {
+            DltcudaAutoJob& j = jobs[i1];
+            j.status = kDltcudaOk;
+            if (j.format < 1 || j.format > 3) { note(j, kDltcudaInvalidSettings); continue; }
+            if (j.len % (size_t)block_bytes(j.format)) { note(j, kDltcudaInvalidLength); continue; }
+            if (j.len && (!j.input || !j.output)) { note(j, kDltcudaNullPointer); continue; }
+            const size_t padded = (j.len + 255) / 256 * 256;
+            if (!idx.empty() && total + padded > kRoundBytes) break;
+            idx.push_back(i1);
+            offset.push_back(total);
+            total += padded;
+        }
+        if (!idx.empty()) {
+            if ((st = ensure_device_buffers(ctx, total ? total : 256)) != Status::kOk) return dltcuda_status(st);
+            std::vector<AutoJob> aj(idx.size());
+            cudaError_t e = cudaSuccess;
+            for (size_t k = 0; k < idx.size() && e == cudaSuccess; k++) {
+                const DltcudaAutoJob& j = jobs[idx[k]];
+                aj[k] = AutoJob{j.format, ctx->d_in + offset[k], ctx->d_out + offset[k], j.len, Settings{}, {}};
+                if (j.len) e = cudaMemcpyAsync(ctx->d_in + offset[k], j.input, j.len, cudaMemcpyHostToDevice, s);
+            }
+            if (e != cudaSuccess) return dltcuda_status(e);
+            if ((st = auto_ltu_device_batch(ctx, aj.data(), (int)aj.size(), use_all, s)) != Status::kOk) return dltcuda_status(st);
+            for (size_t k = 0; k < idx.size() && e == cudaSuccess; k++) {
+                DltcudaAutoJob& j = jobs[idx[k]];
+                j.out_settings = DltcudaSettings{j.format, (uint8_t)aj[k].best.variant, aj[k].best.split_alpha, aj[k].best.split_colour};
+                if (j.len) e = cudaMemcpyAsync(j.output, ctx->d_out + offset[k], j.len, cudaMemcpyDeviceToHost, s);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) return dltcuda_status(e);
+        }
+        i0 = i1;
+    }
+    return first_error;
+}
+}  // namespace cabi
+}  // namespace dlt
+
+DLT_EXPORT int dltcuda_transform_auto_batch(DltcudaAutoJob* jobs, size_t count, bool use_all_modes) {
+    return dlt::cabi::auto_batch_host(jobs, count, use_all_modes);
+}
+
 // Candidate order of the search, for callers that want to label out_estimates.  Returns the count.
 DLT_EXPORT int dltcuda_auto_candidates(int format, bool use_all_modes, DltcudaSettings* out /* >= 16 entries */) {
     if (format < 1 || format > 3 || !out) return 0;

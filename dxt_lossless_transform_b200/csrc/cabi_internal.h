@@ -58,6 +58,17 @@ struct DltcudaPayload {  // one independent host payload of a batch
 }  // extern "C"
 
 
+extern "C" {
+struct DltcudaAutoJob {  // one payload of dltcuda_transform_auto_batch
+    uint8_t format;
+    const uint8_t* input;
+    uint8_t* output;
+    size_t len;
+    DltcudaSettings out_settings;  // out: the winning settings
+    int32_t status;                // out: DltcudaStatus of this job
+};
+}
+
 namespace dlt {
 namespace cabi {
 
@@ -104,6 +115,11 @@ DltResult api_manual_run(int format, bool inverse, const uint8_t* input, size_t 
 // Like the exported call, but hands the chosen settings back by value instead of allocating a builder.
 DltResult api_auto_settings(int format, const AutoBuilder* b, const uint8_t* data, size_t data_len, uint8_t* output,
                             size_t output_len, Settings* best);
+
+// True when `e` is the estimator handed out by dltltu_new_size_estimator (the search then runs entirely on the GPU).
+bool is_gpu_ltu_estimator(const DltSizeEstimator& e);
+// Body of dltcuda_transform_auto_batch: returns a DltcudaStatus (0 = Ok).
+int auto_batch_host(DltcudaAutoJob* jobs, size_t count, bool use_all);
 
 }  // namespace cabi
 }  // namespace dlt

@@ -71,6 +71,7 @@ __device__ __forceinline__ uint32_t group_nskip(uint32_t bucket, unsigned lane) 
 constexpr int kMaxSegsSmall = 32;
 struct SmallBatch {
     LtuSegment s[kMaxSegsSmall];
+    int slot[kMaxSegsSmall];   // index of the segment's result in matches[]
 };
 
 constexpr int kScanGroups = 64;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(32) ltu_scan_filter_kernel(const SmallBatch ba
         const bool mine = inb && (bucket / kScanBuckets) == g;
         count += consume_step(mine, bucket % kScanBuckets, key, nskip, t_last, t_base);
     }
-    if (lane == 0 && count) atomicAdd(&matches[blockIdx.y], count);
+    if (lane == 0 && count) atomicAdd(&matches[batch.slot[blockIdx.y]], count);
 }
 
 // =================================================================================================
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(32) ltu_scan_filter_kernel(const SmallBatch ba
 // nskip > 0 ("follower") sees what the first same-bucket record of its group ("leader") saw, which the thread keeps
 // in a three-record history.  A follower belongs to the piece that owns its leader, so pieces hand over cleanly: a
 // piece skips leading followers of a foreign leader and processes up to three trailing followers of its own.
-constexpr int kMaxSegs = 16;
+constexpr int kMaxSegs = 64;               // segments per launch set (the batch descriptor is a ~7 KiB kernel parameter)
 constexpr int kTile = 8192;              // records per CTA tile of the partition pass
 constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
@@ -190,6 +191,7 @@ struct SortBatch {
     uint16_t* sum_part[kMaxSegs];   // [chunk][class]: partition of that piece
     uint32_t npos[kMaxSegs];
     uint32_t ntiles[kMaxSegs];
+    uint32_t slot[kMaxSegs];        // index of the segment's result in matches[]
     uint32_t run_len;               // L: records per piece slot (multiple of 32)
 };
 
@@ -737,7 +739,7 @@ __global__ void __launch_bounds__(32, kRunsWarpsPerSm) ltu_runs_kernel(const Sor
         }
     }
     for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(kFull, count, o);
-    if (lane == 0 && count) atomicAdd(&matches[seg], (unsigned long long)count);
+    if (lane == 0 && count) atomicAdd(&matches[b.slot[seg]], (unsigned long long)count);
 }
 
 // ---- resolve, level 1: per chunk and class, the last piece of the chunk that touched the class -----------
@@ -825,7 +827,7 @@ __global__ void __launch_bounds__(kResolveThreads) ltu_resolve_kernel(const Sort
     if (threadIdx.x == 0) {
         unsigned long long t = 0;
         for (int i = 0; i < kResolveThreads / 32; i++) t += ws[i];
-        if (t) atomicAdd(&matches[seg], t);
+        if (t) atomicAdd(&matches[b.slot[seg]], t);
     }
 }
 
@@ -858,7 +860,6 @@ SegPlan plan_segment(size_t len, uint32_t run_len) {
 }
 
 constexpr size_t kSmallPositions = 4096;   // at or below: the single-launch kernel
-constexpr size_t kResultBytes = 256;       // matches[] at the front of the scratch
 
 // Piece length for a set of segments: one resident wave of piece-threads over the whole batch (a second, nearly
 // empty wave would double the time), never shorter than kMinRunLen (per-piece overhead: table init and publish,
@@ -879,8 +880,10 @@ uint32_t choose_run_len(const LtuSegment* segs, int nseg) {
 
 uint64_t estimator_launch_count() { return g_est_launches.load(std::memory_order_relaxed); }
 
+inline size_t result_bytes(int nseg) { return align_up((size_t)(nseg > 0 ? nseg : 1) * sizeof(uint64_t), 256); }
+
 size_t ltu_scratch_bytes(const LtuSegment* segs, int nseg) {
-    size_t total = kResultBytes;
+    size_t total = result_bytes(nseg);
     const uint32_t run_len = choose_run_len(segs, nseg);
     for (int i = 0; i < nseg; i++) {
         const SegPlan p = plan_segment(segs[i].len, run_len);
@@ -889,84 +892,65 @@ size_t ltu_scratch_bytes(const LtuSegment* segs, int nseg) {
     return total;
 }
 
+// All segments are queued on `stream` without intermediate host waits: groups of up to kMaxSegsSmall (single-launch
+// kernel) / kMaxSegs (partition + runs pipeline) segments share one set of launches (grid.y), every segment has its
+// own slice of the scratch and its own result slot, and there is one copy back + one synchronize at the end.  A
+// directory of small textures therefore costs a handful of launches, not a handful per texture.
 Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, cudaStream_t stream, uint8_t* scratch,
                           size_t scratch_bytes) {
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
-    static_assert(kMaxSegs * sizeof(unsigned long long) <= kResultBytes && kMaxSegsSmall * 8 <= kResultBytes, "");
+    if (nseg <= 0) return Status::kOk;
     if (scratch_bytes < ltu_scratch_bytes(segs, nseg)) return Status::kOutOfMemory;
     unsigned long long* d_matches = reinterpret_cast<unsigned long long*>(scratch);
     auto fail = [](cudaError_t e) {
         note_cuda_error(e);
         return Status::kCudaError;
     };
+    for (int i = 0; i < nseg; i++)
+        if (ltu_positions(segs[i].len) > 0xFFFF0000ull) return Status::kCudaError;  // record indices are 32-bit
 
-    // split into the two paths, keeping the caller's order in `matches`
-    int small_idx[kMaxSegsSmall], large_idx[kMaxSegs];
-    int done = 0;
-    while (done < nseg) {
-        int ns = 0, nl = 0, i = done;
-        for (; i < nseg; i++) {
-            const size_t npos = ltu_positions(segs[i].len);
-            if (npos > 0xFFFF0000ull) return Status::kCudaError;  // record indices are 32-bit
-            if (npos <= kSmallPositions) {
-                if (ns == kMaxSegsSmall) break;
-                small_idx[ns++] = i;
-            } else {
-                if (nl == kMaxSegs) break;
-                large_idx[nl++] = i;
-            }
-        }
-        cudaError_t e = cudaMemsetAsync(d_matches, 0, kResultBytes, stream);
-        if (e != cudaSuccess) return fail(e);
-        uint64_t host[kMaxSegsSmall];
+    cudaError_t e = cudaMemsetAsync(d_matches, 0, result_bytes(nseg), stream);
+    if (e != cudaSuccess) return fail(e);
+    static const cudaError_t attr = cudaFuncSetAttribute(ltu_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         kScatterSmemBytes);
+    if (attr != cudaSuccess) return fail(attr);
 
-        if (ns) {
-            SmallBatch sb{};
-            for (int k = 0; k < ns; k++) sb.s[k] = segs[small_idx[k]];
+    const uint32_t run_len = choose_run_len(segs, nseg);
+    uint8_t* p = scratch + result_bytes(nseg);
+    auto take = [&p](size_t bytes) {
+        uint8_t* r = p;
+        p += bytes;
+        return r;
+    };
+
+    // ---- small segments: one launch per group
+    {
+        SmallBatch sb{};
+        int ns = 0;
+        auto flush = [&]() {
+            if (!ns) return cudaSuccess;
             ltu_scan_filter_kernel<<<dim3(kScanGroups, ns), 32, 0, stream>>>(sb, d_matches);
             g_est_launches.fetch_add(1, std::memory_order_relaxed);
-            if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
-            if ((e = cudaMemcpyAsync(host, d_matches, sizeof(uint64_t) * ns, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
-                (e = cudaStreamSynchronize(stream)) != cudaSuccess)
-                return fail(e);
-            for (int k = 0; k < ns; k++) matches[small_idx[k]] = host[k];
-            if (nl && (e = cudaMemsetAsync(d_matches, 0, kResultBytes, stream)) != cudaSuccess) return fail(e);
+            ns = 0;
+            return cudaGetLastError();
+        };
+        for (int i = 0; i < nseg; i++) {
+            if (ltu_positions(segs[i].len) > kSmallPositions) continue;
+            sb.s[ns] = segs[i];
+            sb.slot[ns] = i;
+            if (++ns == kMaxSegsSmall && (e = flush()) != cudaSuccess) return fail(e);
         }
+        if ((e = flush()) != cudaSuccess) return fail(e);
+    }
 
-        if (nl) {
-            SortBatch b{};
-            b.run_len = choose_run_len(segs, nseg);
-            uint8_t* p = scratch + kResultBytes;
-            uint32_t max_tiles = 0, max_scan_blocks = 0, max_piece_warps = 0, max_chunks = 0;
-            auto take = [&p](size_t bytes) {
-                uint8_t* r = p;
-                p += bytes;
-                return r;
-            };
-            for (int k = 0; k < nl; k++) {
-                const SegPlan pl = plan_segment(segs[large_idx[k]].len, b.run_len);
-                b.seg[k] = segs[large_idx[k]];
-                b.npos[k] = (uint32_t)pl.npos;
-                b.ntiles[k] = (uint32_t)pl.ntiles;
-                b.rec[k] = reinterpret_cast<uint32_t*>(take(pl.rec_bytes));
-                b.cnt[k] = reinterpret_cast<uint32_t*>(take(pl.cnt_bytes));
-                b.blk[k] = reinterpret_cast<uint32_t*>(take(pl.blk_bytes));
-                b.part_off[k] = reinterpret_cast<uint32_t*>(take(pl.poff_bytes));
-                b.piece_base[k] = reinterpret_cast<uint32_t*>(take(pl.pbase_bytes));
-                b.part[k] = reinterpret_cast<uint16_t*>(take(pl.part_bytes));
-                b.state[k] = reinterpret_cast<uint32_t*>(take(pl.state_bytes));
-                b.dkey[k] = reinterpret_cast<uint32_t*>(take(pl.dkey_bytes));
-                b.sum_word[k] = reinterpret_cast<uint32_t*>(take(pl.sumw_bytes));
-                b.sum_part[k] = reinterpret_cast<uint16_t*>(take(pl.sump_bytes));
-                const uint32_t sblk = (uint32_t)((pl.ntiles + kColChunk - 1) / kColChunk);
-                max_tiles = std::max(max_tiles, (uint32_t)pl.ntiles);
-                max_scan_blocks = std::max(max_scan_blocks, sblk);
-                max_piece_warps = std::max(max_piece_warps, (uint32_t)((pl.max_pieces + 31) / 32));
-                max_chunks = std::max(max_chunks, (uint32_t)pl.max_chunks);
-            }
-            static const cudaError_t attr = cudaFuncSetAttribute(ltu_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                                 kScatterSmemBytes);
-            if (attr != cudaSuccess) return fail(attr);
+    // ---- large segments: nine launches per group
+    {
+        SortBatch b{};
+        b.run_len = run_len;
+        int nl = 0;
+        uint32_t max_tiles = 0, max_scan_blocks = 0, max_piece_warps = 0, max_chunks = 0;
+        auto flush = [&]() {
+            if (!nl) return cudaSuccess;
             const dim3 tiles(max_tiles, nl), scan_grid(max_scan_blocks, nl);
             ltu_hist_kernel<<<tiles, kSortThreads, 0, stream>>>(b);
             ltu_colsum_kernel<<<scan_grid, kParts, 0, stream>>>(b);
@@ -978,14 +962,40 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
             ltu_summarize_kernel<<<dim3(max_chunks, nl), kResolveThreads, 0, stream>>>(b);
             ltu_resolve_kernel<<<dim3(max_chunks, nl), kResolveThreads, 0, stream>>>(b, d_matches);
             g_est_launches.fetch_add(9, std::memory_order_relaxed);
-            if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
-            if ((e = cudaMemcpyAsync(host, d_matches, sizeof(uint64_t) * nl, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
-                (e = cudaStreamSynchronize(stream)) != cudaSuccess)
-                return fail(e);
-            for (int k = 0; k < nl; k++) matches[large_idx[k]] = host[k];
+            nl = 0, max_tiles = max_scan_blocks = max_piece_warps = max_chunks = 0;
+            return cudaGetLastError();
+        };
+        for (int i = 0; i < nseg; i++) {
+            const SegPlan pl = plan_segment(segs[i].len, run_len);
+            if (pl.npos <= kSmallPositions) continue;
+            const int k = nl++;
+            b.seg[k] = segs[i];
+            b.slot[k] = (uint32_t)i;
+            b.npos[k] = (uint32_t)pl.npos;
+            b.ntiles[k] = (uint32_t)pl.ntiles;
+            b.rec[k] = reinterpret_cast<uint32_t*>(take(pl.rec_bytes));
+            b.cnt[k] = reinterpret_cast<uint32_t*>(take(pl.cnt_bytes));
+            b.blk[k] = reinterpret_cast<uint32_t*>(take(pl.blk_bytes));
+            b.part_off[k] = reinterpret_cast<uint32_t*>(take(pl.poff_bytes));
+            b.piece_base[k] = reinterpret_cast<uint32_t*>(take(pl.pbase_bytes));
+            b.part[k] = reinterpret_cast<uint16_t*>(take(pl.part_bytes));
+            b.state[k] = reinterpret_cast<uint32_t*>(take(pl.state_bytes));
+            b.dkey[k] = reinterpret_cast<uint32_t*>(take(pl.dkey_bytes));
+            b.sum_word[k] = reinterpret_cast<uint32_t*>(take(pl.sumw_bytes));
+            b.sum_part[k] = reinterpret_cast<uint16_t*>(take(pl.sump_bytes));
+            max_tiles = std::max(max_tiles, (uint32_t)pl.ntiles);
+            max_scan_blocks = std::max(max_scan_blocks, (uint32_t)((pl.ntiles + kColChunk - 1) / kColChunk));
+            max_piece_warps = std::max(max_piece_warps, (uint32_t)((pl.max_pieces + 31) / 32));
+            max_chunks = std::max(max_chunks, (uint32_t)pl.max_chunks);
+            if (nl == kMaxSegs && (e = flush()) != cudaSuccess) return fail(e);
         }
-        done = i;
+        if ((e = flush()) != cudaSuccess) return fail(e);
     }
+
+    static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "");
+    if ((e = cudaMemcpyAsync(matches, d_matches, sizeof(uint64_t) * (size_t)nseg, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(stream)) != cudaSuccess)
+        return fail(e);
     return Status::kOk;
 }
 

@@ -605,6 +605,8 @@ DLT_EXPORT int dltdds_transform_bundle_batch(const DltddsFile* files, size_t cou
     std::vector<Settings> used(count);
     std::vector<DltcudaPayload> payloads;
     std::vector<size_t> owner;
+    std::vector<DltcudaAutoJob> auto_fast, auto_all;   // files whose builder is auto + GPU LTU, by search depth
+    std::vector<size_t> owner_fast, owner_all;
     for (size_t i = 0; i < count; i++) {
         const DltddsFile& f = files[i];
         if (f.input_len && (!f.input || !f.output)) {
@@ -622,15 +624,20 @@ DLT_EXPORT int dltdds_transform_bundle_batch(const DltddsFile* files, size_t cou
         const int fmt = p.format == kFmtBc1 ? 1 : 2;
         if (slot.kind == BundleSlot::kNone) {
             results[i] = err(kFfNoBuilderForFormat, p.format);
+        } else if (p.data_length % (size_t)block_bytes(fmt)) {
+            results[i] = err(fmt == 1 ? kFfBc1 : kFfBc2, kApiInvalidLength, p.data_length);
+        } else if (slot.kind == BundleSlot::kAuto && is_gpu_ltu_estimator(slot.automatic.estimator) && !devices) {
+            // GPU LTU estimator: the searches of all such files share ONE batched search (below)
+            (slot.automatic.use_all ? auto_all : auto_fast).push_back(
+                DltcudaAutoJob{(uint8_t)fmt, f.input + p.data_offset, f.output + p.data_offset, p.data_length, {}, 0});
+            (slot.automatic.use_all ? owner_all : owner_fast).push_back(i);
         } else if (slot.kind == BundleSlot::kAuto) {
-            // a best-settings search is a whole-GPU job of its own: run it now
+            // a caller-supplied estimator sees host memory: one search per file, as in the reference
             results[i] = slot_transform(slot, fmt, f.input + p.data_offset, p.data_length, f.output + p.data_offset,
                                         p.data_length, &used[i]);
             if (results[i].error_code == kFfSuccess)
                 dds_finish_transform(f.input, f.input_len, f.output, p,
                                      header_new(p.format, pack_bc12(used[i].variant, used[i].split_colour)));
-        } else if (p.data_length % (size_t)block_bytes(fmt)) {
-            results[i] = err(fmt == 1 ? kFfBc1 : kFfBc2, kApiInvalidLength, p.data_length);
         } else {
             used[i] = Settings{fmt, slot.manual.variant, false, slot.manual.split_colour};
             payloads.push_back(DltcudaPayload{f.input + p.data_offset, f.output + p.data_offset, p.data_length,
@@ -647,6 +654,22 @@ DLT_EXPORT int dltdds_transform_bundle_batch(const DltddsFile* files, size_t cou
         }
         dds_finish_transform(files[i].input, files[i].input_len, files[i].output, plans[i],
                              header_new(plans[i].format, pack_bc12(used[i].variant, used[i].split_colour)));
+    }
+    for (int depth = 0; depth < 2; depth++) {
+        std::vector<DltcudaAutoJob>& jobs = depth ? auto_all : auto_fast;
+        const std::vector<size_t>& own = depth ? owner_all : owner_fast;
+        if (jobs.empty()) continue;
+        const int arc = auto_batch_host(jobs.data(), jobs.size(), depth != 0);
+        for (size_t k = 0; k < own.size(); k++) {
+            const size_t i = own[k];
+            if (arc != 0 || jobs[k].status != 0) {
+                results[i] = err(jobs[k].format == 1 ? kFfBc1 : kFfBc2, kApiAllocationFailed, 0);
+                continue;
+            }
+            dds_finish_transform(files[i].input, files[i].input_len, files[i].output, plans[i],
+                                 header_new(plans[i].format, pack_bc12(jobs[k].out_settings.decorrelation_mode,
+                                                                       jobs[k].out_settings.split_colour_endpoints)));
+        }
     }
     return 0;
 }

@@ -126,6 +126,18 @@ int dltcuda_ltu_estimate_device(const uint8_t *d_data, size_t len, size_t *out_s
 int dltcuda_transform_auto_device(int format, const uint8_t *d_input, uint8_t *d_output, size_t len,
                                   bool use_all_modes, DltcudaSettings *out_settings,
                                   size_t *out_estimates);
+/* The same search for a BATCH of independent host payloads (a directory of textures; BASELINE config "determine-best
+ * over a batch of chunks"): one upload per payload, ONE set of estimator launches for all candidates of all payloads,
+ * one download per payload.  jobs[i].out_settings / .status are written; returns the first failing status (or Ok). */
+typedef struct DltcudaAutoJob {
+  uint8_t format; /* 1 = BC1, 2 = BC2, 3 = BC3 */
+  const uint8_t *input;
+  uint8_t *output;
+  size_t len;
+  DltcudaSettings out_settings;
+  int32_t status; /* DltcudaStatus */
+} DltcudaAutoJob;
+int dltcuda_transform_auto_batch(DltcudaAutoJob *jobs, size_t count, bool use_all_modes);
 /* The candidate order of that search (FAST_/COMPREHENSIVE_TEST_ORDER, bc1 settings.rs:81-98,
  * bc3 settings.rs:91-121).  `out` needs 16 entries; returns the count. */
 int dltcuda_auto_candidates(int format, bool use_all_modes, DltcudaSettings *out);

@@ -214,3 +214,66 @@ def test_auto_empty_input(dlt):
     best = dlt.transform_bc1_auto(np.zeros(0, np.uint8), np.zeros(0, np.uint8),
                                   dlt.Bc1EstimateSettings(dlt.LosslessTransformUtilsSizeEstimation()))
     assert (best.decorrelation_mode, best.split_colour_endpoints) == (dlt.YCoCgVariant.NONE, False)
+
+
+@pytest.mark.parametrize("use_all", [False, True])
+def test_auto_batch_equals_single_calls(dlt, use_all):
+    """dltcuda_transform_auto_batch: a mixed batch (formats, sizes incl. empty and tiny, > 64 estimator segments so the
+    launch sets are split) picks the oracle's settings and writes the oracle's bytes for every payload."""
+    from dxt_lossless_transform_b200 import synth
+
+    rng = np.random.default_rng(11)
+    items, datas = [], []
+    for i in range(40):
+        fmt = 1 + i % 3
+        nb = int(rng.choice([0, 1, 7, 300, 4096, 5463, 20_000]))
+        data = synth.texture_blocks(fmt, nb, seed=i, smooth=float(rng.choice([0.2, 1.0, 5.0]))) if nb else np.zeros(0, np.uint8)
+        datas.append(data)
+        items.append((fmt, data, np.zeros_like(data)))
+    best = dlt.transform_auto_batch(items, use_all)
+    for i, ((fmt, data, out), b) in enumerate(zip(items, best)):
+        want_out, want = oracle.auto(fmt, data, use_all) if data.size else (data, None)
+        got = (int(b.decorrelation_mode), bool(getattr(b, "split_alpha_endpoints", False)), bool(b.split_colour_endpoints))
+        if data.size:
+            assert got == want, (i, fmt, data.size)
+            assert np.array_equal(out, want_out), (i, fmt, data.size)
+        else:  # empty payload: every estimate is 0, the first candidate in test order wins
+            first = dlt.auto_candidates(fmt, use_all)[0]
+            assert b == first, (i, b, first)
+    with pytest.raises(dlt.InvalidLength):
+        dlt.transform_auto_batch([(1, np.zeros(12, np.uint8), np.zeros(12, np.uint8))])
+
+
+def test_dds_batch_with_auto_bundle_shares_one_search(dlt):
+    """DdsHandler.transform_bundle_batch with auto builders + the LTU estimator: per-file results equal the single-file
+    calls (which equal the oracle), through the batched search."""
+    from dxt_lossless_transform_b200 import file_formats as ff
+    from dxt_lossless_transform_b200 import synth
+    from dds_fixtures import FO, make_dds, real_fixture
+
+    est = dlt.LosslessTransformUtilsSizeEstimation()
+    bundle = (ff.TransformBundle.new().with_bc1_auto(dlt.Bc1AutoTransformBuilder(est))
+              .with_bc2_auto(dlt.Bc2AutoTransformBuilder(est).use_all_decorrelation_modes(True)))
+    files = [real_fixture("bc1"), real_fixture("bc2")]
+    for i in range(10):
+        fmt = FO.DDS_BC1 if i % 2 else FO.DDS_BC2
+        n = 1 if fmt == FO.DDS_BC1 else 2
+        w, h, mips = [(64, 64, 1), (256, 128, 8), (20, 12, 2)][i % 3]
+        length = FO.parse_dds_ignore_magic(bytes(make_dds(fmt, w, h, mips)[:128]))[2]
+        files.append(make_dds(fmt, w, h, mips, payload=synth.texture_blocks(n, length // (8 * n), seed=i).tobytes(), leftover=b"xyz" * i))
+    files.insert(4, real_fixture("bc3"))   # FormatNotImplemented stays a per-file result
+    handler = ff.DdsHandler()
+    outs = [np.zeros_like(f) for f in files]
+    res = handler.transform_bundle_batch(list(zip(files, outs)), bundle)
+    for i, (f, o, r) in enumerate(zip(files, outs, res)):
+        single = np.zeros_like(f)
+        try:
+            handler.transform_bundle(f, single, bundle)
+        except ff.TransformError as e:
+            assert type(r) is type(e), i
+            continue
+        assert r is None, (i, r)
+        assert np.array_equal(o, single), i
+        back = np.zeros_like(f)
+        handler.untransform(o, back)
+        assert np.array_equal(back, f), i
