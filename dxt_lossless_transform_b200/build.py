@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
     "--threads", "0",
+    "-diag-suppress", "177",  # unused static members of the layout helper in some instantiations
 ]
 
 

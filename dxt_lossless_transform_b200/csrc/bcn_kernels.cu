@@ -139,24 +139,27 @@ __device__ __forceinline__ uint32_t recorrelate_rt(uint32_t v, int var) {
 // ------------------------------------------------------------------------------------------------
 // Compile-time view of one (format, split_alpha, split_colour) layout.
 // ------------------------------------------------------------------------------------------------
-template <int FMT, bool SA, bool SC>
+template <int FMT, bool SA, bool SC, int HALO = 0>
 struct Lay {
     static constexpr int NS = num_streams(FMT, SA, SC);
     static constexpr int BPB = block_bytes(FMT);
     static constexpr int T = kTileBytes / BPB;    // blocks per tile
+    static constexpr int TS = T + HALO;           // blocks staged in shared memory (tile + halo of the next tile)
     static constexpr int BPV = 16 / BPB;          // blocks per 128-bit vector
     DLT_HD static constexpr int w(int s) { return stream_width(FMT, SA, SC, s); }
-    // Staging region of stream s: w*T payload bytes + kShiftAlign bytes of slack for the alignment shift.
-    DLT_HD static constexpr int region(int s) { return T * stream_prefix(FMT, SA, SC, s) + kShiftAlign * s; }
-    static constexpr int kStageBytes = kTileBytes + kShiftAlign * NS;
-    // 128-bit chunks per stream segment of a full tile (+1 when the segment is shifted).
-    DLT_HD static constexpr int iters(int s) { return (w(s) * T / 16 + kShiftAlign / 16 + kThreads - 1) / kThreads; }
+    // Staging region of stream s: w*TS payload bytes + kShiftAlign bytes of slack for the alignment shift.
+    DLT_HD static constexpr int region(int s) { return TS * stream_prefix(FMT, SA, SC, s) + kShiftAlign * s; }
+    static constexpr int kStageBytes = TS * BPB + kShiftAlign * NS;
+    // 128-bit chunks per stream segment of a full tile (+ the shift, + one sector of halo).
+    DLT_HD static constexpr int iters(int s) {
+        return (w(s) * T / 16 + kShiftAlign / 16 + (HALO ? 2 : 0) + kThreads - 1) / kThreads;
+    }
     // Stream indices of the logical fields.
     static constexpr int sAlpha = 0;                          // BC2 alpha:8 / BC3 a0a1:2 or a0:1
-    static constexpr int sA1 = 1;                             // BC3 split alpha only
+    [[maybe_unused]] static constexpr int sA1 = 1;            // BC3 split alpha only
     static constexpr int sAIdx = SA ? 2 : 1;                  // BC3 only
     static constexpr int sCol = FMT == 1 ? 0 : FMT == 2 ? 1 : sAIdx + 1;  // c0c1:4 or c0:2
-    static constexpr int sC1 = sCol + 1;                      // split colour only
+    [[maybe_unused]] static constexpr int sC1 = sCol + 1;     // split colour only
     static constexpr int sIdx = NS - 1;
 };
 
@@ -172,35 +175,46 @@ __device__ __forceinline__ T lds(const uint8_t* p) {
 // ------------------------------------------------------------------------------------------------
 // Tiled transform kernel
 // ------------------------------------------------------------------------------------------------
-// RAGGED = false is compiled without the head / tail pass: legal when every stream base is 16-byte
-// aligned and every stream's total length is a multiple of 16 (measured: merely carrying that pass
-// costs the 16-byte-block formats up to 20 % even when it stores nothing).
+// RAGGED = false: every stream base is 16-byte aligned and every stream's total length is a multiple of 16; a tile's
+// segments are whole 128-byte lines and nothing else is needed.
+// RAGGED = true (odd block counts: real mip chains): segments start and end inside 32-byte sectors.  Writing such a
+// sector from two tiles costs three PARTIAL L2 writes per stream and tile boundary, and a partial write into the
+// ECC-protected L2 is ~5x a full one (measured: -25 % on BC2/BC3).  Instead a sector belongs to the tile that holds its
+// FIRST byte: the tile also stages kHalo blocks of the next tile (3 % extra reads, L2 hits) and writes the boundary
+// sector whole; only the first and the last sector of the launch's range are written bytewise.
+constexpr int kHalo = 32;   // blocks: covers 31 bytes of the narrowest stream (1 byte per block)
+
 template <int FMT, bool SA, bool SC, int VAR, bool RAGGED>
 __global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
     transform_tiled(const uint8_t* __restrict__ in, const StreamPtrs out, const uint64_t nblocks) {
-    using L = Lay<FMT, SA, SC>;
+    using L = Lay<FMT, SA, SC, RAGGED ? kHalo : 0>;
     __shared__ __align__(16) uint8_t stage[L::kStageBytes];
 
     const int tid = threadIdx.x;
     const uint64_t tile_first = (uint64_t)blockIdx.x * L::T;
     const uint64_t left = nblocks - tile_first;
-    const int nb = left < (uint64_t)L::T ? (int)left : L::T;
+    const int nb = left < (uint64_t)L::T ? (int)left : L::T;        // blocks this tile owns
+    const int nbs = left < (uint64_t)L::TS ? (int)left : L::TS;     // blocks it stages (owned + halo)
 
     // (address & 127) of each stream segment; w*T is a multiple of 128 so it is tile-independent.
     int sh[L::NS];
 #pragma unroll
     for (int s = 0; s < L::NS; s++) sh[s] = (int)(reinterpret_cast<uintptr_t>(out.p[s]) & (kShiftAlign - 1));
 
-    // ---- phase 1: 4 coalesced 128-bit loads in flight per thread
+    // ---- phase 1: 4 coalesced 128-bit loads in flight per thread (+ one halo vector for the first threads)
     const uint8_t* tin = in + tile_first * L::BPB;
-    uint4 v[kUnroll];
+    constexpr int kVec = kUnroll + (RAGGED ? 1 : 0);
+    uint4 v[kVec];
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++) {
+    for (int u = 0; u < kVec; u++) {
         const int j = u * kThreads + tid;
         const int b0 = j * L::BPV;
-        if (b0 + L::BPV <= nb) {
+        const bool halo = u == kUnroll;
+        if (halo && tid >= kHalo / L::BPV) {
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+        } else if (b0 + L::BPV <= nbs) {
             v[u] = ldg_stream16(tin + (size_t)j * 16);
-        } else if (L::BPV == 2 && b0 < nb) {
+        } else if (L::BPV == 2 && b0 < nbs) {
             const uint2 h = ldg_stream8(tin + (size_t)j * 16);
             v[u] = make_uint4(h.x, h.y, 0u, 0u);
         } else {
@@ -210,12 +224,12 @@ __global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
 
     // ---- phase 2: colour arithmetic + scatter into the per-stream staging area
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++) {
+    for (int u = 0; u < kVec; u++) {
         const int j = u * kThreads + tid;
         const int b0 = j * L::BPV;
-        if (b0 >= nb) continue;
+        if (b0 >= nbs || (u == kUnroll && tid >= kHalo / L::BPV)) continue;
         if constexpr (FMT == 1) {
-            const bool two = b0 + 1 < nb;
+            const bool two = b0 + 1 < nbs;
             const uint32_t ca = decorrelate2<VAR>(v[u].x), cb = decorrelate2<VAR>(v[u].z);
             uint8_t* pi = stage + L::region(L::sIdx) + sh[L::sIdx] + 4 * b0;
             sts<uint32_t>(pi, v[u].y);
@@ -262,32 +276,50 @@ __global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
     }
     __syncthreads();
 
-    // ---- phase 3: stream every segment out; the 16-byte aligned interior as 128-bit vectors ...
+    // ---- phase 3: stream every segment out as 128-bit vectors.  Coordinates are relative to `gal`, the 128-byte
+    // aligned address below the segment: the tile owns [lo_valid, hi_valid), has data up to `avail`.
 #pragma unroll
     for (int s = 0; s < L::NS; s++) {
         const int w = L::w(s);
         const int lo_valid = sh[s], hi_valid = sh[s] + w * nb;
-        uint8_t* gal = out.p[s] + (uint64_t)w * tile_first - sh[s];  // 16-byte aligned
+        uint8_t* gal = out.p[s] + (uint64_t)w * tile_first - sh[s];  // 128-byte aligned
         const uint8_t* reg = stage + L::region(s);
-        const int nch = (hi_valid + 15) >> 4;
+        int vec_lo, vec_hi;   // multiples of 16
+        if constexpr (RAGGED) {
+            const int avail = sh[s] + w * nbs;
+            vec_lo = (lo_valid + 31) & ~31;                      // the sector holding lo_valid belongs to the tile before
+            vec_hi = min((hi_valid + 31) & ~31, avail & ~15);    // ... and the one holding hi_valid - 1 to this tile
+        } else {
+            vec_lo = lo_valid, vec_hi = hi_valid;
+        }
 #pragma unroll
         for (int it = 0; it < L::iters(s); it++) {
-            const int k = it * kThreads + tid;
-            const int lo = k << 4;
-            if (k < nch && lo >= lo_valid && lo + 16 <= hi_valid) stg_stream16(gal + lo, lds<uint4>(reg + lo));
+            const int lo = (it * kThreads + tid) << 4;
+            if (lo >= vec_lo && lo + 16 <= vec_hi) stg_stream16(gal + lo, lds<uint4>(reg + lo));
         }
     }
-    // ... and the ragged head / tail (< 16 bytes each; only when a stream base is not 16-byte aligned or
-    // the tile is the last one): warp 0, lanes 0-15 the head bytes, lanes 16-31 the tail bytes.
-    if constexpr (RAGGED) if (tid < 32) {
+    // ... and, in the first / last tile of the launch's range only, the bytes outside whole sectors (< 32 each):
+    // the range may be a shard, so nothing beyond it is touched.  Warp 0, one lane per byte.
+    if constexpr (RAGGED) {
+        const bool first_tile = blockIdx.x == 0, last_tile = left <= (uint64_t)L::TS;
+        if ((first_tile || last_tile) && tid < 32) {
 #pragma unroll
-        for (int s = 0; s < L::NS; s++) {
-            const int lo_valid = sh[s], hi_valid = sh[s] + L::w(s) * nb;
-            const int head_end = min(hi_valid, (lo_valid + 15) & ~15);
-            const int tail_start = max(head_end, hi_valid & ~15);
-            const int i = tid < 16 ? lo_valid + tid : tail_start + tid - 16;
-            if (tid < 16 ? i < head_end : i < hi_valid)
-                (out.p[s] + (uint64_t)L::w(s) * tile_first - sh[s])[i] = stage[L::region(s) + i];
+            for (int s = 0; s < L::NS; s++) {
+                const int w = L::w(s);
+                const int lo_valid = sh[s], hi_valid = sh[s] + w * nb, avail = sh[s] + w * nbs;
+                uint8_t* gal = out.p[s] + (uint64_t)w * tile_first - sh[s];
+                const uint8_t* reg = stage + L::region(s);
+                const int vec_lo = (lo_valid + 31) & ~31, vec_hi = min((hi_valid + 31) & ~31, avail & ~15);
+                if (first_tile) {   // head: [lo_valid, vec_lo), clipped to the data
+                    const int i = lo_valid + tid;
+                    if (i < min(vec_lo, avail)) gal[i] = reg[i];
+                }
+                if (last_tile) {    // tail: what the vector stores could not cover of [.., min(owned sectors, data))
+                    const int end = min((hi_valid + 31) & ~31, avail);
+                    const int i = max(vec_hi, max(vec_lo, lo_valid)) + tid;
+                    if (vec_hi >= vec_lo && i < end) gal[i] = reg[i];
+                }
+            }
         }
     }
 }
