@@ -152,6 +152,7 @@ SIGNATURES.update(
         ),
         "dltcuda_auto_candidates": (C.c_int, [C.c_int, C.c_bool, C.POINTER(DltcudaSettings)]),
         "dltcuda_transform_auto_batch": (C.c_int, [C.POINTER(DltcudaAutoJob), _SZ, C.c_bool]),
+        "dltcuda_transform_auto_batch_multi_gpu": (C.c_int, [C.POINTER(DltcudaAutoJob), _SZ, C.c_bool, C.POINTER(C.c_int), C.c_int]),
     }
 )
 

@@ -589,10 +589,10 @@ def transform_auto_device(fmt: int, d_in: int, d_out: int, nbytes: int, use_all:
     return best, [est[i] for i in range(k)]
 
 
-def transform_auto_batch(items, use_all: bool = False) -> list:
+def transform_auto_batch(items, use_all: bool = False, devices=None) -> list:
     """transform_bcN_auto (GPU LTU estimator) for a batch of independent host payloads: ``items`` is a list of
     ``(fmt, input, output)``; returns the winning settings per payload.  One set of estimator launches serves all
-    candidates of all payloads (dltcuda_transform_auto_batch)."""
+    candidates of all payloads (dltcuda_transform_auto_batch); ``devices`` deals whole payloads out over several GPUs."""
     jobs = (N.DltcudaAutoJob * len(items))()
     keep = []
     for i, (fmt, inp, out) in enumerate(items):
@@ -604,7 +604,11 @@ def transform_auto_batch(items, use_all: bool = False) -> list:
             raise OutputBufferTooSmall(il, ol)
         keep += [ka, kb]
         jobs[i] = N.DltcudaAutoJob(fmt, ip, op, il, N.DltcudaSettings(), 0)
-    _check_device(N.lib().dltcuda_transform_auto_batch(jobs, len(items), bool(use_all)))
+    if devices:
+        dev = (C.c_int * len(devices))(*devices)
+        _check_device(N.lib().dltcuda_transform_auto_batch_multi_gpu(jobs, len(items), bool(use_all), dev, len(devices)))
+    else:
+        _check_device(N.lib().dltcuda_transform_auto_batch(jobs, len(items), bool(use_all)))
     out = []
     for j in jobs:
         s = j.out_settings

@@ -780,6 +780,38 @@ DLT_EXPORT int dltcuda_transform_auto_batch(DltcudaAutoJob* jobs, size_t count, 
     return dlt::cabi::auto_batch_host(jobs, count, use_all_modes);
 }
 
+// The same over several GPUs of one box: whole payloads are dealt out (least-loaded device first), one host thread
+// per device runs its share through dltcuda_transform_auto_batch; nothing is exchanged between devices (an estimate
+// is a property of a whole payload, so payloads - never one payload's streams - are what gets sharded).
+DLT_EXPORT int dltcuda_transform_auto_batch_multi_gpu(DltcudaAutoJob* jobs, size_t count, bool use_all_modes,
+                                                      const int* devices, int num_devices) {
+    if (count == 0) return kDltcudaOk;
+    if (!jobs || !devices || num_devices < 1) return kDltcudaNullPointer;
+    std::vector<std::vector<size_t>> share((size_t)num_devices);
+    std::vector<size_t> load((size_t)num_devices, 0);
+    for (size_t i = 0; i < count; i++) {
+        size_t d = 0;
+        for (size_t k = 1; k < load.size(); k++)
+            if (load[k] < load[d]) d = k;
+        load[d] += jobs[i].len + 1;
+        share[d].push_back(i);
+    }
+    std::vector<int> rc((size_t)num_devices, kDltcudaOk);
+    std::vector<std::thread> threads;
+    for (int d = 0; d < num_devices; d++)
+        threads.emplace_back([&, d] {
+            std::vector<DltcudaAutoJob> mine;
+            for (size_t i : share[d]) mine.push_back(jobs[i]);
+            set_thread_device(devices[d]);
+            rc[d] = dlt::cabi::auto_batch_host(mine.data(), mine.size(), use_all_modes);
+            for (size_t k = 0; k < mine.size(); k++) jobs[share[d][k]] = mine[k];
+        });
+    for (auto& th : threads) th.join();
+    for (int r : rc)
+        if (r != kDltcudaOk) return r;
+    return kDltcudaOk;
+}
+
 // Candidate order of the search, for callers that want to label out_estimates.  Returns the count.
 DLT_EXPORT int dltcuda_auto_candidates(int format, bool use_all_modes, DltcudaSettings* out /* >= 16 entries */) {
     if (format < 1 || format > 3 || !out) return 0;

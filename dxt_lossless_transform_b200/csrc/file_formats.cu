@@ -102,6 +102,8 @@ struct DltddsFile {
 int dltcuda_transform_batch(const DltcudaPayload* payloads, size_t count, bool untransform);
 int dltcuda_transform_batch_multi_gpu(const DltcudaPayload* payloads, size_t count, bool untransform,
                                       const int* devices, int num_devices);
+int dltcuda_transform_auto_batch_multi_gpu(DltcudaAutoJob* jobs, size_t count, bool use_all_modes, const int* devices,
+                                           int num_devices);
 }
 
 namespace {
@@ -626,7 +628,7 @@ DLT_EXPORT int dltdds_transform_bundle_batch(const DltddsFile* files, size_t cou
             results[i] = err(kFfNoBuilderForFormat, p.format);
         } else if (p.data_length % (size_t)block_bytes(fmt)) {
             results[i] = err(fmt == 1 ? kFfBc1 : kFfBc2, kApiInvalidLength, p.data_length);
-        } else if (slot.kind == BundleSlot::kAuto && is_gpu_ltu_estimator(slot.automatic.estimator) && !devices) {
+        } else if (slot.kind == BundleSlot::kAuto && is_gpu_ltu_estimator(slot.automatic.estimator)) {
             // GPU LTU estimator: the searches of all such files share ONE batched search (below)
             (slot.automatic.use_all ? auto_all : auto_fast).push_back(
                 DltcudaAutoJob{(uint8_t)fmt, f.input + p.data_offset, f.output + p.data_offset, p.data_length, {}, 0});
@@ -659,7 +661,9 @@ DLT_EXPORT int dltdds_transform_bundle_batch(const DltddsFile* files, size_t cou
         std::vector<DltcudaAutoJob>& jobs = depth ? auto_all : auto_fast;
         const std::vector<size_t>& own = depth ? owner_all : owner_fast;
         if (jobs.empty()) continue;
-        const int arc = auto_batch_host(jobs.data(), jobs.size(), depth != 0);
+        const int arc = devices && num_devices > 0
+                            ? dltcuda_transform_auto_batch_multi_gpu(jobs.data(), jobs.size(), depth != 0, devices, num_devices)
+                            : auto_batch_host(jobs.data(), jobs.size(), depth != 0);
         for (size_t k = 0; k < own.size(); k++) {
             const size_t i = own[k];
             if (arc != 0 || jobs[k].status != 0) {

@@ -138,6 +138,9 @@ typedef struct DltcudaAutoJob {
   int32_t status; /* DltcudaStatus */
 } DltcudaAutoJob;
 int dltcuda_transform_auto_batch(DltcudaAutoJob *jobs, size_t count, bool use_all_modes);
+/* Same, payloads dealt out whole over several GPUs of one box (one host thread per device, nothing exchanged). */
+int dltcuda_transform_auto_batch_multi_gpu(DltcudaAutoJob *jobs, size_t count, bool use_all_modes,
+                                           const int *devices, int num_devices);
 /* The candidate order of that search (FAST_/COMPREHENSIVE_TEST_ORDER, bc1 settings.rs:81-98,
  * bc3 settings.rs:91-121).  `out` needs 16 entries; returns the count. */
 int dltcuda_auto_candidates(int format, bool use_all_modes, DltcudaSettings *out);

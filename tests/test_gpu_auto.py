@@ -277,3 +277,33 @@ def test_dds_batch_with_auto_bundle_shares_one_search(dlt):
         back = np.zeros_like(f)
         handler.untransform(o, back)
         assert np.array_equal(back, f), i
+
+
+def test_auto_batch_over_every_visible_gpu(dlt, torch):
+    """Payload-granular sharding of the batched search: whole payloads per device, nothing exchanged."""
+    from dxt_lossless_transform_b200 import file_formats as ff
+    from dxt_lossless_transform_b200 import synth
+    from dds_fixtures import real_fixture
+
+    devices = list(range(torch.cuda.device_count()))
+    items = []
+    for i in range(12):
+        fmt = 1 + i % 3
+        data = synth.texture_blocks(fmt, 3000 + 211 * i, seed=50 + i)
+        items.append((fmt, data, np.zeros_like(data)))
+    best = dlt.transform_auto_batch(items, False, devices=devices)
+    for (fmt, data, out), b in zip(items, best):
+        want_out, want = oracle.auto(fmt, data, False)
+        assert (int(b.decorrelation_mode), bool(getattr(b, "split_alpha_endpoints", False)), bool(b.split_colour_endpoints)) == want
+        assert np.array_equal(out, want_out)
+    # and through the DDS batch entry point with an auto bundle
+    est = dlt.LosslessTransformUtilsSizeEstimation()
+    bundle = ff.TransformBundle.new().with_bc1_auto(dlt.Bc1AutoTransformBuilder(est)).with_bc2_auto(dlt.Bc2AutoTransformBuilder(est))
+    files = [real_fixture("bc1"), real_fixture("bc2")] * 3
+    outs = [np.zeros_like(f) for f in files]
+    handler = ff.DdsHandler()
+    assert handler.transform_bundle_batch(list(zip(files, outs)), bundle, devices=devices) == [None] * len(files)
+    for f, o in zip(files, outs):
+        single = np.zeros_like(f)
+        handler.transform_bundle(f, single, bundle)
+        assert np.array_equal(o, single)
