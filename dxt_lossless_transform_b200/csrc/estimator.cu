@@ -911,9 +911,9 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
 
     cudaError_t e = cudaMemsetAsync(d_matches, 0, result_bytes(nseg), stream);
     if (e != cudaSuccess) return fail(e);
-    static const cudaError_t attr = cudaFuncSetAttribute(ltu_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         kScatterSmemBytes);
-    if (attr != cudaSuccess) return fail(attr);
+    // function attributes are per device: set it on every call (microseconds), a process may drive several GPUs
+    if ((e = cudaFuncSetAttribute(ltu_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmemBytes)) != cudaSuccess)
+        return fail(e);
 
     const uint32_t run_len = choose_run_len(segs, nseg);
     uint8_t* p = scratch + result_bytes(nseg);
