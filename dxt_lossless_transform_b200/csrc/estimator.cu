@@ -567,12 +567,9 @@ __global__ void __launch_bounds__(kPThreads, DLT_SCATTER_CTAS) ltu_scatter_kerne
 // ---- plan: partition boundaries -> pieces ------------------------------------------------------------
 // Partition p holds records [part_off[p], part_off[p+1]); it is cut at multiples of L, so it owns the slots
 // part_off[p] / L .. (part_off[p+1] - 1) / L.  piece_base[] numbers the pieces partition after partition.
-__global__ void __launch_bounds__(kParts) ltu_plan_kernel(const SortBatch b) {
-    const int seg = blockIdx.x;
+__device__ __forceinline__ void plan_pieces(const SortBatch& b, const int seg, const uint32_t o0, const uint32_t o1) {
     const uint32_t p = threadIdx.x;
     const uint32_t npos = b.npos[seg], L = b.run_len;
-    const uint32_t o0 = b.cnt[seg][p];   // row 0 of the scanned matrix: first record of every partition
-    const uint32_t o1 = p == kParts - 1 ? npos : b.cnt[seg][p + 1];
     const uint32_t pieces = o1 > o0 ? (o1 - 1) / L - o0 / L + 1 : 0;
     __shared__ uint32_t ws[kParts / 32];
     const unsigned lane = p & 31, warp = p >> 5;
@@ -589,6 +586,59 @@ __global__ void __launch_bounds__(kParts) ltu_plan_kernel(const SortBatch b) {
     b.piece_base[seg][p] = base;
     if (p == kParts - 1) b.part_off[seg][kParts] = npos, b.piece_base[seg][kParts] = base + pieces;
     for (uint32_t k = 0; k < pieces; k++) b.part[seg][base + k] = (uint16_t)p;
+}
+
+__global__ void __launch_bounds__(kParts) ltu_plan_kernel(const SortBatch b) {
+    const int seg = blockIdx.x;
+    const uint32_t p = threadIdx.x;
+    const uint32_t o0 = b.cnt[seg][p];   // row 0 of the scanned matrix: first record of every partition
+    const uint32_t o1 = p == kParts - 1 ? b.npos[seg] : b.cnt[seg][p + 1];
+    plan_pieces(b, seg, o0, o1);
+}
+
+// ---- few tiles (every segment of the launch set has <= kColChunk tiles): the three column-scan launches and the plan
+// in ONE launch, one CTA per segment — what a typical texture (<= 512 KiB per endpoint stream) goes through.
+__global__ void __launch_bounds__(kParts) ltu_colscan_small_kernel(const SortBatch b) {
+    const int seg = blockIdx.x;
+    const uint32_t nt = b.ntiles[seg];
+    const uint32_t d = threadIdx.x;
+    uint32_t* m = b.cnt[seg];
+    uint32_t total = 0;
+    for (uint32_t t = 0; t < nt; t += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = t + k < nt ? m[(size_t)(t + k) * kParts + d] : 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) total += v[k];
+    }
+    __shared__ uint32_t ws[kParts / 32];
+    __shared__ uint32_t s_base[kParts + 1];
+    const unsigned lane = d & 31, warp = d >> 5;
+    uint32_t inc = total;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(kFull, inc, o);
+        if ((int)lane >= o) inc += up;
+    }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    uint32_t base = inc - total;
+    for (unsigned w = 0; w < warp; w++) base += ws[w];
+    s_base[d] = base;
+    if (d == kParts - 1) s_base[kParts] = base + total;
+    uint32_t run = base;
+    for (uint32_t t = 0; t < nt; t += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = t + k < nt ? m[(size_t)(t + k) * kParts + d] : 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (t + k < nt) m[(size_t)(t + k) * kParts + d] = run;
+            run += v[k];
+        }
+    }
+    m[(size_t)nt * kParts + d] = base + total;   // the extra row: end of the digit's partition
+    __syncthreads();   // s_base complete; ws is reused by plan_pieces after its own barrier
+    plan_pieces(b, seg, s_base[d], s_base[d + 1]);
 }
 
 // ---- runs: one thread per piece, private class table in shared memory ---------------------------------
@@ -953,15 +1003,20 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
             if (!nl) return cudaSuccess;
             const dim3 tiles(max_tiles, nl), scan_grid(max_scan_blocks, nl);
             ltu_hist_kernel<<<tiles, kSortThreads, 0, stream>>>(b);
-            ltu_colsum_kernel<<<scan_grid, kParts, 0, stream>>>(b);
-            ltu_colbase_kernel<<<nl, kParts, 0, stream>>>(b);
-            ltu_colapply_kernel<<<scan_grid, kParts, 0, stream>>>(b);
+            const bool few_tiles = max_tiles <= (uint32_t)kColChunk;
+            if (few_tiles) {
+                ltu_colscan_small_kernel<<<nl, kParts, 0, stream>>>(b);   // column scans + plan in one launch
+            } else {
+                ltu_colsum_kernel<<<scan_grid, kParts, 0, stream>>>(b);
+                ltu_colbase_kernel<<<nl, kParts, 0, stream>>>(b);
+                ltu_colapply_kernel<<<scan_grid, kParts, 0, stream>>>(b);
+            }
             ltu_scatter_kernel<<<tiles, kPThreads, kScatterSmemBytes, stream>>>(b);
-            ltu_plan_kernel<<<nl, kParts, 0, stream>>>(b);
+            if (!few_tiles) ltu_plan_kernel<<<nl, kParts, 0, stream>>>(b);
             ltu_runs_kernel<<<dim3(max_piece_warps, nl), 32, 0, stream>>>(b, d_matches);
             ltu_summarize_kernel<<<dim3(max_chunks, nl), kResolveThreads, 0, stream>>>(b);
             ltu_resolve_kernel<<<dim3(max_chunks, nl), kResolveThreads, 0, stream>>>(b, d_matches);
-            g_est_launches.fetch_add(9, std::memory_order_relaxed);
+            g_est_launches.fetch_add(few_tiles ? 6 : 9, std::memory_order_relaxed);
             nl = 0, max_tiles = max_scan_blocks = max_piece_warps = max_chunks = 0;
             return cudaGetLastError();
         };
