@@ -175,6 +175,68 @@ __device__ __forceinline__ T lds(const uint8_t* p) {
 // ------------------------------------------------------------------------------------------------
 // Tiled transform kernel
 // ------------------------------------------------------------------------------------------------
+// One 128-bit vector of blocks (two BC1 blocks or one BC2/BC3 block starting at tile-relative block b0; blocks at or
+// beyond `limit` are not staged): colour arithmetic + scatter of every field into the per-stream staging area.
+template <int FMT, bool SA, bool SC, int VAR, typename L>
+__device__ __forceinline__ void stage_vector(uint8_t* stage, const int* sh, const int b0, const int limit, const uint4 v) {
+    if constexpr (FMT == 1) {
+        const bool two = b0 + 1 < limit;
+        const uint32_t ca = decorrelate2<VAR>(v.x), cb = decorrelate2<VAR>(v.z);
+        uint8_t* pi = stage + L::region(L::sIdx) + sh[L::sIdx] + 4 * b0;
+        sts<uint32_t>(pi, v.y);
+        if (two) sts<uint32_t>(pi + 4, v.w);
+        if constexpr (SC) {
+            uint8_t* p0 = stage + L::region(L::sCol) + sh[L::sCol] + 2 * b0;
+            uint8_t* p1 = stage + L::region(L::sC1) + sh[L::sC1] + 2 * b0;
+            sts<uint16_t>(p0, (uint16_t)ca);
+            sts<uint16_t>(p1, (uint16_t)(ca >> 16));
+            if (two) {
+                sts<uint16_t>(p0 + 2, (uint16_t)cb);
+                sts<uint16_t>(p1 + 2, (uint16_t)(cb >> 16));
+            }
+        } else {
+            uint8_t* pc = stage + L::region(L::sCol) + sh[L::sCol] + 4 * b0;
+            sts<uint32_t>(pc, ca);
+            if (two) sts<uint32_t>(pc + 4, cb);
+        }
+    } else {
+        // BC2 / BC3: one block per vector: [x y] = alpha part, z = colours, w = indices
+        if constexpr (FMT == 2) {
+            sts<uint2>(stage + L::region(L::sAlpha) + sh[L::sAlpha] + 8 * b0, make_uint2(v.x, v.y));
+        } else {
+            if constexpr (SA) {
+                stage[L::region(L::sAlpha) + sh[L::sAlpha] + b0] = (uint8_t)v.x;
+                stage[L::region(L::sA1) + sh[L::sA1] + b0] = (uint8_t)(v.x >> 8);
+            } else {
+                sts<uint16_t>(stage + L::region(L::sAlpha) + sh[L::sAlpha] + 2 * b0, (uint16_t)v.x);
+            }
+            uint8_t* pa = stage + L::region(L::sAIdx) + sh[L::sAIdx] + 6 * b0;
+            sts<uint16_t>(pa, (uint16_t)(v.x >> 16));
+            sts<uint16_t>(pa + 2, (uint16_t)v.y);
+            sts<uint16_t>(pa + 4, (uint16_t)(v.y >> 16));
+        }
+        const uint32_t c = decorrelate2<VAR>(v.z);
+        if constexpr (SC) {
+            sts<uint16_t>(stage + L::region(L::sCol) + sh[L::sCol] + 2 * b0, (uint16_t)c);
+            sts<uint16_t>(stage + L::region(L::sC1) + sh[L::sC1] + 2 * b0, (uint16_t)(c >> 16));
+        } else {
+            sts<uint32_t>(stage + L::region(L::sCol) + sh[L::sCol] + 4 * b0, c);
+        }
+        sts<uint32_t>(stage + L::region(L::sIdx) + sh[L::sIdx] + 4 * b0, v.w);
+    }
+}
+
+template <typename L>
+__device__ __forceinline__ uint4 load_vector(const uint8_t* tin, const int j, const int limit) {
+    const int b0 = j * L::BPV;
+    if (b0 + L::BPV <= limit) return ldg_stream16(tin + (size_t)j * 16);
+    if (L::BPV == 2 && b0 < limit) {
+        const uint2 h = ldg_stream8(tin + (size_t)j * 16);
+        return make_uint4(h.x, h.y, 0u, 0u);
+    }
+    return make_uint4(0u, 0u, 0u, 0u);
+}
+
 // RAGGED = false: every stream base is 16-byte aligned and every stream's total length is a multiple of 16; a tile's
 // segments are whole 128-byte lines and nothing else is needed.
 // RAGGED = true (odd block counts: real mip chains): segments start and end inside 32-byte sectors.  Writing such a
@@ -201,78 +263,27 @@ __global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
 #pragma unroll
     for (int s = 0; s < L::NS; s++) sh[s] = (int)(reinterpret_cast<uintptr_t>(out.p[s]) & (kShiftAlign - 1));
 
-    // ---- phase 1: 4 coalesced 128-bit loads in flight per thread (+ one halo vector for the first threads)
+    // ---- phase 1: 4 coalesced 128-bit loads in flight per thread; warp 0 also fetches the halo (a warp-uniform branch:
+    // predicating a fifth vector through every warp costs +27 % issued instructions on the six-stream BC3 layout)
     const uint8_t* tin = in + tile_first * L::BPB;
-    constexpr int kVec = kUnroll + (RAGGED ? 1 : 0);
-    uint4 v[kVec];
+    uint4 v[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kVec; u++) {
-        const int j = u * kThreads + tid;
-        const int b0 = j * L::BPV;
-        const bool halo = u == kUnroll;
-        if (halo && tid >= kHalo / L::BPV) {
-            v[u] = make_uint4(0u, 0u, 0u, 0u);
-        } else if (b0 + L::BPV <= nbs) {
-            v[u] = ldg_stream16(tin + (size_t)j * 16);
-        } else if (L::BPV == 2 && b0 < nbs) {
-            const uint2 h = ldg_stream8(tin + (size_t)j * 16);
-            v[u] = make_uint4(h.x, h.y, 0u, 0u);
-        } else {
-            v[u] = make_uint4(0u, 0u, 0u, 0u);
-        }
+    for (int u = 0; u < kUnroll; u++) v[u] = load_vector<L>(tin, u * kThreads + tid, nbs);
+    uint4 vh = make_uint4(0u, 0u, 0u, 0u);
+    const bool halo_lane = RAGGED && tid < kHalo / L::BPV;
+    if (RAGGED && tid < 32) {
+        if (halo_lane) vh = load_vector<L>(tin, kUnroll * kThreads + tid, nbs);
     }
 
     // ---- phase 2: colour arithmetic + scatter into the per-stream staging area
 #pragma unroll
-    for (int u = 0; u < kVec; u++) {
-        const int j = u * kThreads + tid;
-        const int b0 = j * L::BPV;
-        if (b0 >= nbs || (u == kUnroll && tid >= kHalo / L::BPV)) continue;
-        if constexpr (FMT == 1) {
-            const bool two = b0 + 1 < nbs;
-            const uint32_t ca = decorrelate2<VAR>(v[u].x), cb = decorrelate2<VAR>(v[u].z);
-            uint8_t* pi = stage + L::region(L::sIdx) + sh[L::sIdx] + 4 * b0;
-            sts<uint32_t>(pi, v[u].y);
-            if (two) sts<uint32_t>(pi + 4, v[u].w);
-            if constexpr (SC) {
-                uint8_t* p0 = stage + L::region(L::sCol) + sh[L::sCol] + 2 * b0;
-                uint8_t* p1 = stage + L::region(L::sC1) + sh[L::sC1] + 2 * b0;
-                sts<uint16_t>(p0, (uint16_t)ca);
-                sts<uint16_t>(p1, (uint16_t)(ca >> 16));
-                if (two) {
-                    sts<uint16_t>(p0 + 2, (uint16_t)cb);
-                    sts<uint16_t>(p1 + 2, (uint16_t)(cb >> 16));
-                }
-            } else {
-                uint8_t* pc = stage + L::region(L::sCol) + sh[L::sCol] + 4 * b0;
-                sts<uint32_t>(pc, ca);
-                if (two) sts<uint32_t>(pc + 4, cb);
-            }
-        } else {
-            // BC2 / BC3: one block per vector: [x y] = alpha part, z = colours, w = indices
-            if constexpr (FMT == 2) {
-                sts<uint2>(stage + L::region(L::sAlpha) + sh[L::sAlpha] + 8 * b0, make_uint2(v[u].x, v[u].y));
-            } else {
-                if constexpr (SA) {
-                    stage[L::region(L::sAlpha) + sh[L::sAlpha] + b0] = (uint8_t)v[u].x;
-                    stage[L::region(L::sA1) + sh[L::sA1] + b0] = (uint8_t)(v[u].x >> 8);
-                } else {
-                    sts<uint16_t>(stage + L::region(L::sAlpha) + sh[L::sAlpha] + 2 * b0, (uint16_t)v[u].x);
-                }
-                uint8_t* pa = stage + L::region(L::sAIdx) + sh[L::sAIdx] + 6 * b0;
-                sts<uint16_t>(pa, (uint16_t)(v[u].x >> 16));
-                sts<uint16_t>(pa + 2, (uint16_t)v[u].y);
-                sts<uint16_t>(pa + 4, (uint16_t)(v[u].y >> 16));
-            }
-            const uint32_t c = decorrelate2<VAR>(v[u].z);
-            if constexpr (SC) {
-                sts<uint16_t>(stage + L::region(L::sCol) + sh[L::sCol] + 2 * b0, (uint16_t)c);
-                sts<uint16_t>(stage + L::region(L::sC1) + sh[L::sC1] + 2 * b0, (uint16_t)(c >> 16));
-            } else {
-                sts<uint32_t>(stage + L::region(L::sCol) + sh[L::sCol] + 4 * b0, c);
-            }
-            sts<uint32_t>(stage + L::region(L::sIdx) + sh[L::sIdx] + 4 * b0, v[u].w);
-        }
+    for (int u = 0; u < kUnroll; u++) {
+        const int b0 = (u * kThreads + tid) * L::BPV;
+        if (b0 < nbs) stage_vector<FMT, SA, SC, VAR, L>(stage, sh, b0, nbs, v[u]);
+    }
+    if (RAGGED && tid < 32) {
+        const int b0 = (kUnroll * kThreads + tid) * L::BPV;
+        if (halo_lane && b0 < nbs) stage_vector<FMT, SA, SC, VAR, L>(stage, sh, b0, nbs, vh);
     }
     __syncthreads();
 
