@@ -17,3 +17,5 @@ from .api import (  # noqa: F401
     LosslessTransformUtilsSizeEstimation,
     YCoCgVariant,
 )
+
+from . import experimental, file_formats  # noqa: E402,F401

@@ -151,6 +151,14 @@ SIGNATURES.update(
             [C.c_int, _P, _P, _SZ, C.c_bool, C.POINTER(DltcudaSettings), C.POINTER(_SZ)],
         ),
         "dltcuda_auto_candidates": (C.c_int, [C.c_int, C.c_bool, C.POINTER(DltcudaSettings)]),
+        "dltcuda_bc1_normalize_blocks": (C.c_int, [_P, _P, _SZ, C.c_int]),
+        "dltcuda_bc1_normalize_blocks_device": (C.c_int, [_P, _P, _SZ, C.c_int, _P]),
+        "dltcuda_bc1_normalize_blocks_all_modes": (C.c_int, [_P, _P, _P, _P, _SZ, C.POINTER(C.c_bool)]),
+        "dltcuda_bc1_normalize_split_blocks_in_place": (C.c_int, [_P, _P, _SZ, C.c_int]),
+        "dltcuda_bc1_transform_with_normalize_blocks": (C.c_int, [_P, _P, _SZ, C.c_int, C.c_uint8, C.c_bool]),
+        "dltcuda_bc1_transform_with_normalize_blocks_device": (C.c_int, [_P, _P, _SZ, C.c_int, C.c_uint8, C.c_bool, _P]),
+        "dltcuda_bc1_transform_auto_with_normalization": (
+            C.c_int, [_P, _P, _SZ, C.c_bool, C.POINTER(C.c_int), C.POINTER(C.c_uint8), C.POINTER(C.c_bool), C.POINTER(_SZ)]),
         "dltcuda_transform_auto_batch": (C.c_int, [C.POINTER(DltcudaAutoJob), _SZ, C.c_bool]),
         "dltcuda_transform_auto_batch_multi_gpu": (C.c_int, [C.POINTER(DltcudaAutoJob), _SZ, C.c_bool, C.POINTER(C.c_int), C.c_int]),
     }

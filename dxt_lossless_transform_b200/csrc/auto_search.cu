@@ -53,55 +53,72 @@ int estimate_ranges(int format, size_t len, EstimateRange out[2]) {
     return 2;
 }
 
+// Transforms `k` candidate settings of one device-resident payload into scratch images and estimates the endpoint
+// streams of each (in batches that fit the scratch budget): totals[i] = estimate of candidate i.
+static Status estimate_candidates(Context* ctx, int format, const uint8_t* d_in, size_t len, const Settings* order, int k,
+                                  size_t* totals, cudaStream_t stream) {
+    const size_t n = len / block_bytes(format);
+    EstimateRange ranges[2];
+    const int nr = estimate_ranges(format, len, ranges);
+    for (int i = 0; i < k; i++) totals[i] = 0;
+    if (len == 0) return Status::kOk;
+    // scratch = [m images][estimator buffers for m*nr segments]; all candidates at once when they fit
+    const size_t img = (len + 255) / 256 * 256;
+    constexpr size_t kScratchBudget = (size_t)12 << 30;
+    std::vector<LtuSegment> segs((size_t)k * nr);
+    auto scratch_for = [&](int m) {
+        for (int c = 0; c < m; c++)
+            for (int r = 0; r < nr; r++) segs[(size_t)c * nr + r] = LtuSegment{nullptr, ranges[r].len};
+        return (size_t)m * img + ltu_scratch_bytes(segs.data(), m * nr);
+    };
+    int m = k;
+    while (m > 1 && scratch_for(m) > kScratchBudget) m--;
+    Status st;
+    while ((st = ensure_scratch(ctx, scratch_for(m))) == Status::kOutOfMemory && m > 1) m = (m + 1) / 2;
+    if (st != Status::kOk) return st;
+    uint8_t* est_scratch = ctx->d_scratch + (size_t)m * img;
+    const size_t est_bytes = ctx->d_scratch_cap - (size_t)m * img;
+
+    for (int c0 = 0; c0 < k; c0 += m) {
+        const int mb = k - c0 < m ? k - c0 : m;
+        for (int c = 0; c < mb; c++) {
+            uint8_t* image = ctx->d_scratch + (size_t)c * img;
+            cudaError_t e = launch_transform(order[c0 + c], d_in, reference_layout(image, n, 0, order[c0 + c]), n, stream);
+            if (e != cudaSuccess) {
+                note_cuda_error(e);
+                return Status::kCudaError;
+            }
+            for (int r = 0; r < nr; r++) segs[(size_t)c * nr + r] = LtuSegment{image + ranges[r].offset, ranges[r].len};
+        }
+        std::vector<uint64_t> matches((size_t)mb * nr, 0);
+        st = ltu_matches_device(segs.data(), mb * nr, matches.data(), stream, est_scratch, est_bytes);
+        if (st != Status::kOk) return st;
+        for (int c = 0; c < mb; c++)
+            for (int r = 0; r < nr; r++)
+                totals[c0 + c] += ltu_estimate_from_matches(ranges[r].len, matches[(size_t)c * nr + r]);
+    }
+    return Status::kOk;
+}
+
+static Status final_transform(const Settings& best, const uint8_t* d_in, uint8_t* d_out, size_t len, cudaStream_t stream) {
+    if (len == 0) return Status::kOk;
+    const size_t n = len / block_bytes(best.format);
+    cudaError_t e = launch_transform(best, d_in, reference_layout(d_out, n, 0, best), n, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        note_cuda_error(e);
+        return Status::kCudaError;
+    }
+    return Status::kOk;
+}
+
 Status auto_ltu_device(Context* ctx, int format, const uint8_t* d_in, uint8_t* d_out, size_t len, bool use_all,
                        Settings* best, size_t* sizes, cudaStream_t stream) {
     Settings order[kMaxCandidates];
     const int k = candidate_order(format, use_all, order);
-    const size_t n = len / block_bytes(format);
-    EstimateRange ranges[2];
-    const int nr = estimate_ranges(format, len, ranges);
-
     size_t totals[kMaxCandidates] = {};
-    if (len != 0) {
-        // Candidates are transformed into scratch images and estimated in batches, so that one set of
-        // estimator launches covers several candidates (small payloads fill the GPU, large ones stay
-        // within the scratch budget).  scratch = [m images][estimator sort buffers for m*nr segments]
-        const size_t img = (len + 255) / 256 * 256;
-        constexpr size_t kScratchBudget = (size_t)12 << 30;
-        LtuSegment segs[kMaxCandidates * 2];
-        auto scratch_for = [&](int m) {
-            for (int c = 0; c < m; c++)
-                for (int r = 0; r < nr; r++) segs[c * nr + r] = LtuSegment{nullptr, ranges[r].len};
-            return (size_t)m * img + ltu_scratch_bytes(segs, m * nr);
-        };
-        int m = k;
-        while (m > 1 && scratch_for(m) > kScratchBudget) m--;
-        Status st;
-        while ((st = ensure_scratch(ctx, scratch_for(m))) == Status::kOutOfMemory && m > 1) m = (m + 1) / 2;
-        if (st != Status::kOk) return st;
-        uint8_t* est_scratch = ctx->d_scratch + (size_t)m * img;
-        const size_t est_bytes = ctx->d_scratch_cap - (size_t)m * img;
-
-        for (int c0 = 0; c0 < k; c0 += m) {
-            const int mb = k - c0 < m ? k - c0 : m;
-            for (int c = 0; c < mb; c++) {
-                uint8_t* image = ctx->d_scratch + (size_t)c * img;
-                cudaError_t e = launch_transform(order[c0 + c], d_in, reference_layout(image, n, 0, order[c0 + c]), n, stream);
-                if (e != cudaSuccess) {
-                    note_cuda_error(e);
-                    return Status::kCudaError;
-                }
-                for (int r = 0; r < nr; r++) segs[c * nr + r] = LtuSegment{image + ranges[r].offset, ranges[r].len};
-            }
-            uint64_t matches[kMaxCandidates * 2] = {};
-            st = ltu_matches_device(segs, mb * nr, matches, stream, est_scratch, est_bytes);
-            if (st != Status::kOk) return st;
-            for (int c = 0; c < mb; c++)
-                for (int r = 0; r < nr; r++)
-                    totals[c0 + c] += ltu_estimate_from_matches(ranges[r].len, matches[c * nr + r]);
-        }
-    }
-
+    const Status st = estimate_candidates(ctx, format, d_in, len, order, k, totals, stream);
+    if (st != Status::kOk) return st;
     // strict '<': the first candidate in test order wins ties (transform_auto.rs:257-260)
     Settings best_s = default_settings(format);
     size_t best_size = SIZE_MAX;
@@ -109,16 +126,50 @@ Status auto_ltu_device(Context* ctx, int format, const uint8_t* d_in, uint8_t* d
         if (sizes) sizes[i] = totals[i];
         if (totals[i] < best_size) best_size = totals[i], best_s = order[i];
     }
-    if (len != 0) {
-        cudaError_t e = launch_transform(best_s, d_in, reference_layout(d_out, n, 0, best_s), n, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        if (e != cudaSuccess) {
-            note_cuda_error(e);
-            return Status::kCudaError;
-        }
-    }
     *best = best_s;
-    return Status::kOk;
+    return final_transform(best_s, d_in, d_out, len, stream);
+}
+
+// experimental::transform_bc1_auto_with_normalization (normalize_blocks/transform.rs:222-340): if no block is
+// normalizable the plain search runs; otherwise every (normalization mode, settings) pair — modes outermost, in
+// ColorNormalizationMode::all_values() order, settings in the usual test order — is estimated over the colour half
+// and the first minimum wins.  Normalization is fused into the candidate transforms: there is no normalized copy.
+Status auto_ltu_norm_device(Context* ctx, const uint8_t* d_in, uint8_t* d_out, size_t len, bool use_all, Settings* best,
+                            size_t* sizes, cudaStream_t stream) {
+    const size_t n = len / 8;
+    Status st = ensure_scratch(ctx, 256);
+    if (st != Status::kOk) return st;
+    unsigned int* d_any = reinterpret_cast<unsigned int*>(ctx->d_scratch);
+    unsigned int any = 0;
+    cudaError_t e = cudaMemsetAsync(d_any, 0, sizeof(unsigned int), stream);
+    if (e == cudaSuccess) e = launch_normalize_blocks(d_in, nullptr, nullptr, nullptr, n, d_any, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&any, d_any, sizeof(any), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        note_cuda_error(e);
+        return Status::kCudaError;
+    }
+    if (!any) return auto_ltu_device(ctx, 1, d_in, d_out, len, use_all, best, sizes, stream);
+
+    Settings base[kMaxCandidates], order[3 * kMaxCandidates];
+    const int k = candidate_order(1, use_all, base);
+    for (int m = 0; m < 3; m++)
+        for (int i = 0; i < k; i++) {
+            order[m * k + i] = base[i];
+            // the `None` candidates are estimated on normalize_blocks_all_modes' None buffer (transparent blocks -> 0xFF)
+            order[m * k + i].normalize = m == kNormNone ? (int)kNormAllModesNone : m;
+        }
+    size_t totals[3 * kMaxCandidates] = {};
+    if ((st = estimate_candidates(ctx, 1, d_in, len, order, 3 * k, totals, stream)) != Status::kOk) return st;
+    Settings best_s = default_settings(1);   // Bc1TransformDetailsWithNormalization::default(): (None, Variant1, split)
+    size_t best_size = SIZE_MAX;
+    for (int i = 0; i < 3 * k; i++) {
+        if (sizes) sizes[i] = totals[i];
+        if (totals[i] < best_size) best_size = totals[i], best_s = order[i];
+    }
+    if (best_s.normalize == kNormAllModesNone) best_s.normalize = kNormNone;   // ... but transformed without normalization
+    *best = best_s;
+    return final_transform(best_s, d_in, d_out, len, stream);
 }
 
 Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_all, cudaStream_t stream) {

@@ -38,6 +38,13 @@ int estimate_ranges(int format, size_t len, EstimateRange out[2]);
 Status auto_ltu_device(Context* ctx, int format, const uint8_t* d_in, uint8_t* d_out, size_t len, bool use_all_modes,
                        Settings* best, size_t* sizes, cudaStream_t stream);
 
+// experimental::transform_bc1_auto_with_normalization (core/dxt-lossless-transform-bc1/src/experimental/
+// normalize_blocks/transform.rs:222-340) with the GPU LTU estimator.  best->normalize receives the winning
+// ColorNormalizationMode; `sizes` (optional, 3 * kMaxCandidates entries) the estimates, normalization mode outermost
+// (only filled when at least one block is normalizable; otherwise the plain search's k entries).
+Status auto_ltu_norm_device(Context* ctx, const uint8_t* d_in, uint8_t* d_out, size_t len, bool use_all_modes,
+                            Settings* best, size_t* sizes, cudaStream_t stream);
+
 // The same search for MANY independent device-resident payloads at once (a directory of textures): the candidates of
 // all payloads are transformed into scratch images and every endpoint stream of every candidate becomes one segment
 // of a single estimator call, so the launch count does not grow with the number of payloads.  Jobs that do not fit

@@ -137,6 +137,55 @@ __device__ __forceinline__ uint32_t recorrelate_rt(uint32_t v, int var) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// experimental::normalize_blocks on one BC1 block held as (c0 | c1 << 16, indices).
+// Restates decode_bc1_block (core/dxt-lossless-transform-bc1/src/util/bc1_decode.rs:7-63), Color565::{red,green,blue}
+// (common/src/color_565/mod.rs:154-191), from_rgb (:108-115) and normalize_blocks_impl / write_normalized_solid_color_block
+// (experimental/normalize_blocks/normalize.rs:104-247).  Returns the BlockCase: 0 cannot normalize (block unchanged),
+// 1 fully transparent (block = 0xFF..), 2 solid round-trippable colour (block rewritten per `mode`).
+// Fast reject: when more than one index VALUE is used and c0 != c1 the pixels cannot all be equal (the expanded
+// endpoints differ by >= 4 in some channel, so every interpolated entry differs from both endpoints and from the
+// other interpolated entry, and the transparent entry differs in alpha) — nearly every real block leaves here.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t expand565(uint32_t c) {   // r | g << 8 | b << 16, 8 bits each
+    const uint32_t r = (c >> 11) & 31u, g = (c >> 5) & 63u, b = c & 31u;
+    return ((r << 3) | (r >> 2)) | (((g << 2) | (g >> 4)) << 8) | (((b << 3) | (b >> 2)) << 16);
+}
+__device__ __forceinline__ uint32_t mix3(uint32_t a, uint32_t b, uint32_t wa, uint32_t wb, uint32_t div) {
+    // per channel (wa * a + wb * b) / div on packed 8-bit channels
+    uint32_t out = 0;
+#pragma unroll
+    for (int sft = 0; sft < 24; sft += 8) {
+        const uint32_t x = wa * ((a >> sft) & 0xFFu) + wb * ((b >> sft) & 0xFFu);
+        out |= (div == 3 ? (x * 0xAAABu) >> 17 : x >> 1) << sft;   // x <= 765: exact
+    }
+    return out;
+}
+__device__ __forceinline__ int normalize_bc1_block(uint32_t& c01, uint32_t& idx, const int mode) {
+    const uint32_t c0 = c01 & 0xFFFFu, c1 = c01 >> 16;
+    const uint32_t lo = idx & 0x55555555u, hi = (idx >> 1) & 0x55555555u;
+    const bool u0 = (~(lo | hi) & 0x55555555u) != 0, u1 = (lo & ~hi) != 0, u2 = (hi & ~lo) != 0, u3 = (lo & hi) != 0;
+    if ((int)u0 + (int)u1 + (int)u2 + (int)u3 > 1 && c0 != c1) return 0;
+    const uint32_t kOpaque = 0xFF000000u;
+    const uint32_t e0 = expand565(c0), e1 = expand565(c1);
+    const uint32_t d0 = e0 | kOpaque, d1 = e1 | kOpaque;
+    const uint32_t d2 = (c0 > c1 ? mix3(e0, e1, 2, 1, 3) : mix3(e0, e1, 1, 1, 2)) | kOpaque;
+    const uint32_t d3 = c0 > c1 ? (mix3(e0, e1, 1, 2, 3) | kOpaque) : 0u;
+    const uint32_t sel = idx & 3u;
+    const uint32_t first = sel == 0 ? d0 : sel == 1 ? d1 : sel == 2 ? d2 : d3;
+    if ((u0 && d0 != first) || (u1 && d1 != first) || (u2 && d2 != first) || (u3 && d3 != first)) return 0;
+    if ((first >> 24) == 0) {   // fully transparent
+        c01 = idx = 0xFFFFFFFFu;
+        return 1;
+    }
+    const uint32_t r = first & 0xFFu, g = (first >> 8) & 0xFFu, b = (first >> 16) & 0xFFu;
+    const uint32_t c565 = ((r & 0xF8u) << 8) | ((g & 0xFCu) << 3) | (b >> 3);
+    if ((expand565(c565) | kOpaque) != first) return 0;
+    if (mode == kNormColor0Only) c01 = c565, idx = 0;
+    else if (mode == kNormReplicateColor) c01 = c565 | (c565 << 16), idx = 0;
+    return 2;   // mode None: the reference writes the source block back
+}
+
+// ------------------------------------------------------------------------------------------------
 // Compile-time view of one (format, split_alpha, split_colour) layout.
 // ------------------------------------------------------------------------------------------------
 template <int FMT, bool SA, bool SC, int HALO = 0>
@@ -177,10 +226,15 @@ __device__ __forceinline__ T lds(const uint8_t* p) {
 // ------------------------------------------------------------------------------------------------
 // One 128-bit vector of blocks (two BC1 blocks or one BC2/BC3 block starting at tile-relative block b0; blocks at or
 // beyond `limit` are not staged): colour arithmetic + scatter of every field into the per-stream staging area.
-template <int FMT, bool SA, bool SC, int VAR, typename L>
-__device__ __forceinline__ void stage_vector(uint8_t* stage, const int* sh, const int b0, const int limit, const uint4 v) {
+template <int FMT, bool SA, bool SC, int VAR, int NORM, typename L>
+__device__ __forceinline__ void stage_vector(uint8_t* stage, const int* sh, const int b0, const int limit, uint4 v) {
     if constexpr (FMT == 1) {
         const bool two = b0 + 1 < limit;
+        if constexpr (NORM != kNormNone) {   // experimental::transform_bc1_with_normalize_blocks: normalize, then transform
+            constexpr int kMode = NORM == kNormAllModesNone ? (int)kNormNone : NORM;   // transparent blocks only
+            normalize_bc1_block(v.x, v.y, kMode);
+            normalize_bc1_block(v.z, v.w, kMode);
+        }
         const uint32_t ca = decorrelate2<VAR>(v.x), cb = decorrelate2<VAR>(v.z);
         uint8_t* pi = stage + L::region(L::sIdx) + sh[L::sIdx] + 4 * b0;
         sts<uint32_t>(pi, v.y);
@@ -246,7 +300,7 @@ __device__ __forceinline__ uint4 load_vector(const uint8_t* tin, const int j, co
 // sector whole; only the first and the last sector of the launch's range are written bytewise.
 constexpr int kHalo = 32;   // blocks: covers 31 bytes of the narrowest stream (1 byte per block)
 
-template <int FMT, bool SA, bool SC, int VAR, bool RAGGED>
+template <int FMT, bool SA, bool SC, int VAR, bool RAGGED, int NORM = kNormNone>
 __global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
     transform_tiled(const uint8_t* __restrict__ in, const StreamPtrs out, const uint64_t nblocks) {
     using L = Lay<FMT, SA, SC, RAGGED ? kHalo : 0>;
@@ -279,11 +333,11 @@ __global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
 #pragma unroll
     for (int u = 0; u < kUnroll; u++) {
         const int b0 = (u * kThreads + tid) * L::BPV;
-        if (b0 < nbs) stage_vector<FMT, SA, SC, VAR, L>(stage, sh, b0, nbs, v[u]);
+        if (b0 < nbs) stage_vector<FMT, SA, SC, VAR, NORM, L>(stage, sh, b0, nbs, v[u]);
     }
     if (RAGGED && tid < 32) {
         const int b0 = (kUnroll * kThreads + tid) * L::BPV;
-        if (halo_lane && b0 < nbs) stage_vector<FMT, SA, SC, VAR, L>(stage, sh, b0, nbs, vh);
+        if (halo_lane && b0 < nbs) stage_vector<FMT, SA, SC, VAR, NORM, L>(stage, sh, b0, nbs, vh);
     }
     __syncthreads();
 
@@ -448,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
 // caller hands in pointers the tiled kernels cannot address (the reference accepts any alignment).
 // ------------------------------------------------------------------------------------------------
 struct RtLayout {
-    int fmt, var, ns;
+    int fmt, var, ns, norm;
     int w[kMaxStreams];
     int s_alpha, s_a1, s_aidx, s_col, s_c1, s_idx;
     bool sa, sc;
@@ -478,6 +532,11 @@ __global__ void __launch_bounds__(kThreads)
         }
         uint32_t c = (uint32_t)blk[coff] | ((uint32_t)blk[coff + 1] << 8) | ((uint32_t)blk[coff + 2] << 16) |
                      ((uint32_t)blk[coff + 3] << 24);
+        if (L.fmt == 1 && L.norm != kNormNone) {   // normalize the block before it is transformed
+            uint32_t x = (uint32_t)blk[4] | ((uint32_t)blk[5] << 8) | ((uint32_t)blk[6] << 16) | ((uint32_t)blk[7] << 24);
+            normalize_bc1_block(c, x, L.norm == kNormAllModesNone ? (int)kNormNone : L.norm);
+            blk[4] = (uint8_t)x, blk[5] = (uint8_t)(x >> 8), blk[6] = (uint8_t)(x >> 16), blk[7] = (uint8_t)(x >> 24);
+        }
         c = decorrelate_rt(c, L.var);
         uint8_t* p0 = L.sc ? streams.p[L.s_col] + i * 2 : streams.p[L.s_col] + i * 4;
         uint8_t* p1 = L.sc ? streams.p[L.s_c1] + i * 2 : p0 + 2;
@@ -536,11 +595,12 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 template <int FMT, bool SA, bool SC>
-RtLayout make_rt_layout(int var) {
+RtLayout make_rt_layout(int var, int norm = kNormNone) {
     using L = Lay<FMT, SA, SC>;
     RtLayout r{};
     r.fmt = FMT;
     r.var = var;
+    r.norm = norm;
     r.ns = L::NS;
     for (int s = 0; s < L::NS; s++) r.w[s] = L::w(s);
     r.s_alpha = L::sAlpha;
@@ -566,8 +626,27 @@ bool tiled_ok(const void* blocks, const StreamPtrs& sp) {
     return true;
 }
 
+template <int FMT, bool SA, bool SC, int VAR, bool RAGGED>
+void launch_tiled_transform(int norm, unsigned tiles, const uint8_t* blocks_in, const StreamPtrs& sp, uint64_t n, cudaStream_t stream) {
+    if constexpr (FMT == 1) {   // experimental normalization exists for BC1 only
+        if (norm == kNormColor0Only) {
+            transform_tiled<FMT, SA, SC, VAR, RAGGED, kNormColor0Only><<<tiles, kThreads, 0, stream>>>(blocks_in, sp, n);
+            return;
+        }
+        if (norm == kNormReplicateColor) {
+            transform_tiled<FMT, SA, SC, VAR, RAGGED, kNormReplicateColor><<<tiles, kThreads, 0, stream>>>(blocks_in, sp, n);
+            return;
+        }
+        if (norm == kNormAllModesNone) {
+            transform_tiled<FMT, SA, SC, VAR, RAGGED, kNormAllModesNone><<<tiles, kThreads, 0, stream>>>(blocks_in, sp, n);
+            return;
+        }
+    }
+    transform_tiled<FMT, SA, SC, VAR, RAGGED><<<tiles, kThreads, 0, stream>>>(blocks_in, sp, n);
+}
+
 template <int FMT, bool SA, bool SC, int VAR>
-cudaError_t run(bool inverse, const uint8_t* blocks_in, uint8_t* blocks_out, const StreamPtrs& sp, uint64_t n,
+cudaError_t run(bool inverse, int norm, const uint8_t* blocks_in, uint8_t* blocks_out, const StreamPtrs& sp, uint64_t n,
                 cudaStream_t stream) {
     using L = Lay<FMT, SA, SC>;
     if (n == 0) return cudaSuccess;
@@ -578,29 +657,27 @@ cudaError_t run(bool inverse, const uint8_t* blocks_in, uint8_t* blocks_out, con
         bool ragged = false;
         for (int s = 0; s < L::NS; s++)
             ragged |= ((reinterpret_cast<uintptr_t>(sp.p[s]) | ((uint64_t)L::w(s) * n)) & 15) != 0;
-        if (!inverse && ragged)
-            transform_tiled<FMT, SA, SC, VAR, true><<<(unsigned)tiles, kThreads, 0, stream>>>(blocks_in, sp, n);
-        else if (!inverse)
-            transform_tiled<FMT, SA, SC, VAR, false><<<(unsigned)tiles, kThreads, 0, stream>>>(blocks_in, sp, n);
+        if (!inverse && ragged) launch_tiled_transform<FMT, SA, SC, VAR, true>(norm, (unsigned)tiles, blocks_in, sp, n, stream);
+        else if (!inverse) launch_tiled_transform<FMT, SA, SC, VAR, false>(norm, (unsigned)tiles, blocks_in, sp, n, stream);
         else untransform_tiled<FMT, SA, SC, VAR><<<(unsigned)tiles, kThreads, 0, stream>>>(sp, blocks_out, n);
     } else {
         const uint64_t ctas = (n + kThreads - 1) / kThreads;
         if (ctas > 0x7fffffffull) return cudaErrorInvalidValue;
-        bytewise_kernel<<<(unsigned)ctas, kThreads, 0, stream>>>(make_rt_layout<FMT, SA, SC>(VAR), inverse, blocks_in,
-                                                                 blocks_out, sp, n);
+        bytewise_kernel<<<(unsigned)ctas, kThreads, 0, stream>>>(make_rt_layout<FMT, SA, SC>(VAR, inverse ? kNormNone : norm),
+                                                                 inverse, blocks_in, blocks_out, sp, n);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 
 template <int FMT, bool SA, bool SC>
-cudaError_t run_var(int var, bool inverse, const uint8_t* bi, uint8_t* bo, const StreamPtrs& sp, uint64_t n,
+cudaError_t run_var(int var, int norm, bool inverse, const uint8_t* bi, uint8_t* bo, const StreamPtrs& sp, uint64_t n,
                     cudaStream_t stream) {
     switch (var) {
-        case kNone: return run<FMT, SA, SC, kNone>(inverse, bi, bo, sp, n, stream);
-        case kVariant1: return run<FMT, SA, SC, kVariant1>(inverse, bi, bo, sp, n, stream);
-        case kVariant2: return run<FMT, SA, SC, kVariant2>(inverse, bi, bo, sp, n, stream);
-        case kVariant3: return run<FMT, SA, SC, kVariant3>(inverse, bi, bo, sp, n, stream);
+        case kNone: return run<FMT, SA, SC, kNone>(inverse, norm, bi, bo, sp, n, stream);
+        case kVariant1: return run<FMT, SA, SC, kVariant1>(inverse, norm, bi, bo, sp, n, stream);
+        case kVariant2: return run<FMT, SA, SC, kVariant2>(inverse, norm, bi, bo, sp, n, stream);
+        case kVariant3: return run<FMT, SA, SC, kVariant3>(inverse, norm, bi, bo, sp, n, stream);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -610,18 +687,18 @@ cudaError_t dispatch(const Settings& st, bool inverse, const uint8_t* bi, uint8_
     const bool sc = st.split_colour, sa = st.split_alpha;
     switch (st.format) {
         case 1:
-            return sc ? run_var<1, false, true>(st.variant, inverse, bi, bo, sp, n, stream)
-                      : run_var<1, false, false>(st.variant, inverse, bi, bo, sp, n, stream);
+            return sc ? run_var<1, false, true>(st.variant, st.normalize, inverse, bi, bo, sp, n, stream)
+                      : run_var<1, false, false>(st.variant, st.normalize, inverse, bi, bo, sp, n, stream);
         case 2:
-            return sc ? run_var<2, false, true>(st.variant, inverse, bi, bo, sp, n, stream)
-                      : run_var<2, false, false>(st.variant, inverse, bi, bo, sp, n, stream);
+            return sc ? run_var<2, false, true>(st.variant, st.normalize, inverse, bi, bo, sp, n, stream)
+                      : run_var<2, false, false>(st.variant, st.normalize, inverse, bi, bo, sp, n, stream);
         case 3:
             if (sa) {
-                return sc ? run_var<3, true, true>(st.variant, inverse, bi, bo, sp, n, stream)
-                          : run_var<3, true, false>(st.variant, inverse, bi, bo, sp, n, stream);
+                return sc ? run_var<3, true, true>(st.variant, st.normalize, inverse, bi, bo, sp, n, stream)
+                          : run_var<3, true, false>(st.variant, st.normalize, inverse, bi, bo, sp, n, stream);
             }
-            return sc ? run_var<3, false, true>(st.variant, inverse, bi, bo, sp, n, stream)
-                      : run_var<3, false, false>(st.variant, inverse, bi, bo, sp, n, stream);
+            return sc ? run_var<3, false, true>(st.variant, st.normalize, inverse, bi, bo, sp, n, stream)
+                      : run_var<3, false, false>(st.variant, st.normalize, inverse, bi, bo, sp, n, stream);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -647,6 +724,95 @@ cudaError_t launch_split_color_endpoints(const uint8_t* in, uint8_t* out, uint64
     const uint64_t ctas = ((npairs + 3) / 4 + kThreads - 1) / kThreads;
     if (ctas > 0x7fffffffull) return cudaErrorInvalidValue;
     split_endpoints_kernel<<<(unsigned)ctas, kThreads, 0, stream>>>(in, out, c1, npairs, vector_ok);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// experimental::normalize_blocks as stand-alone passes (normalize.rs:38-101, 286-386, 417-484)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint2 load_block8(const uint8_t* p, bool aligned) {
+    if (aligned) return *reinterpret_cast<const uint2*>(p);
+    uint2 r;
+    r.x = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    r.y = (uint32_t)p[4] | ((uint32_t)p[5] << 8) | ((uint32_t)p[6] << 16) | ((uint32_t)p[7] << 24);
+    return r;
+}
+__device__ __forceinline__ void store_block8(uint8_t* p, uint2 v, bool aligned) {
+    if (aligned) {
+        *reinterpret_cast<uint2*>(p) = v;
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) p[k] = (uint8_t)(v.x >> (8 * k)), p[4 + k] = (uint8_t)(v.y >> (8 * k));
+}
+
+// One block per thread.  outs[m] (m = mode) may be null; `any` (optional) is set when a block is normalizable.
+struct NormOuts {
+    uint8_t* p[3];
+};
+__global__ void __launch_bounds__(kThreads)
+    normalize_blocks_kernel(const uint8_t* in, const NormOuts outs, const uint64_t nblocks, const bool aligned, unsigned int* any) {
+    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    bool hit = false;
+    if (i < nblocks) {
+        const uint2 src = load_block8(in + 8 * i, aligned);
+        uint2 probe = src;
+        hit = normalize_bc1_block(probe.x, probe.y, kNormColor0Only) != 0;   // the BlockCase does not depend on the mode
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            if (!outs.p[m]) continue;
+            uint2 v = src;
+            if (hit) normalize_bc1_block(v.x, v.y, m);
+            store_block8(outs.p[m] + 8 * i, v, aligned);
+        }
+    }
+    if (any && __syncthreads_or(hit) && threadIdx.x == 0) atomicOr(any, 1u);
+}
+
+// normalize_split_blocks_in_place: colours (c0 c1 pairs) and indices live in separate arrays.
+__global__ void __launch_bounds__(kThreads)
+    normalize_split_kernel(uint8_t* colors, uint8_t* indices, const uint64_t nblocks, const int mode, const bool aligned) {
+    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= nblocks) return;
+    uint32_t c, x;
+    if (aligned) {
+        c = *reinterpret_cast<const uint32_t*>(colors + 4 * i), x = *reinterpret_cast<const uint32_t*>(indices + 4 * i);
+    } else {
+        c = x = 0;
+        for (int k = 0; k < 4; k++) c |= (uint32_t)colors[4 * i + k] << (8 * k), x |= (uint32_t)indices[4 * i + k] << (8 * k);
+    }
+    if (normalize_bc1_block(c, x, mode) == 0) return;   // in place: nothing to write
+    if (aligned) {
+        *reinterpret_cast<uint32_t*>(colors + 4 * i) = c, *reinterpret_cast<uint32_t*>(indices + 4 * i) = x;
+    } else {
+        for (int k = 0; k < 4; k++) colors[4 * i + k] = (uint8_t)(c >> (8 * k)), indices[4 * i + k] = (uint8_t)(x >> (8 * k));
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_normalize_blocks(const uint8_t* in, uint8_t* out_none, uint8_t* out_color0, uint8_t* out_replicate,
+                                    uint64_t nblocks, unsigned int* d_any, cudaStream_t stream) {
+    if (nblocks == 0) return cudaSuccess;
+    const uint64_t ctas = (nblocks + kThreads - 1) / kThreads;
+    if (ctas > 0x7fffffffull) return cudaErrorInvalidValue;
+    const NormOuts outs{{out_none, out_color0, out_replicate}};
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out_none) |
+                           reinterpret_cast<uintptr_t>(out_color0) | reinterpret_cast<uintptr_t>(out_replicate);
+    normalize_blocks_kernel<<<(unsigned)ctas, kThreads, 0, stream>>>(in, outs, nblocks, (bits & 7) == 0, d_any);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_normalize_split_blocks(uint8_t* colors, uint8_t* indices, uint64_t nblocks, int mode, cudaStream_t stream) {
+    if (nblocks == 0 || mode == kNormNone) return cudaSuccess;
+    const uint64_t ctas = (nblocks + kThreads - 1) / kThreads;
+    if (ctas > 0x7fffffffull) return cudaErrorInvalidValue;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(colors) | reinterpret_cast<uintptr_t>(indices)) & 3) == 0;
+    normalize_split_kernel<<<(unsigned)ctas, kThreads, 0, stream>>>(colors, indices, nblocks, mode, aligned);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

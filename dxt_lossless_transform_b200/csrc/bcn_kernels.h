@@ -20,6 +20,16 @@ cudaError_t launch_untransform(const Settings& st, const StreamPtrs& in, uint8_t
 // split_color_endpoints: [c0 c1] x n (len_bytes = 4n) -> c0 x n | c1 x n at out and out + len_bytes/2.
 cudaError_t launch_split_color_endpoints(const uint8_t* in, uint8_t* out, uint64_t len_bytes, cudaStream_t stream);
 
+// experimental::normalize_blocks (BC1; core/dxt-lossless-transform-bc1/src/experimental/normalize_blocks/normalize.rs).
+// One pass over `nblocks` blocks writes the normalized image of every mode whose output pointer is non-null
+// (out_none receives a copy; an output may equal `in`); *d_any (optional, device) is OR-ed with 1 when at least one
+// block is transparent or a round-trippable solid colour (normalize_blocks_all_modes' return value).
+// transform_bc1_with_normalize_blocks needs no pass of its own: set Settings::normalize and call launch_transform.
+cudaError_t launch_normalize_blocks(const uint8_t* in, uint8_t* out_none, uint8_t* out_color0, uint8_t* out_replicate,
+                                    uint64_t nblocks, unsigned int* d_any, cudaStream_t stream);
+// normalize_split_blocks_in_place: colours ([c0 c1] per block) and indices in separate device arrays.
+cudaError_t launch_normalize_split_blocks(uint8_t* colors, uint8_t* indices, uint64_t nblocks, int mode, cudaStream_t stream);
+
 // Number of kernel launches the two functions above have issued in this process (bench evidence).
 uint64_t kernel_launch_count();
 

@@ -27,11 +27,25 @@ constexpr int kMaxStreams = 6;
 // Internal numbering (common/src/color_565/decorrelate.rs:72-84).
 enum Variant : int { kNone = 0, kVariant1 = 1, kVariant2 = 2, kVariant3 = 3 };
 
+// experimental::normalize_blocks (BC1 only) — ColorNormalizationMode::all_values() order
+// (core/dxt-lossless-transform-bc1/src/experimental/normalize_blocks/normalize.rs:487-500).
+enum NormalizeMode : int {
+    kNormNone = 0,
+    kNormColor0Only = 1,
+    kNormReplicateColor = 2,
+    // internal: what normalize_blocks_all_modes writes into its `None` buffer — transparent blocks become 0xFF, solid
+    // blocks stay as they are (normalize.rs:449-466).  transform_bc1_auto_with_normalization ESTIMATES its `None`
+    // candidates on that buffer (transform.rs:250-291) while the final transform with mode None leaves every block
+    // untouched (normalize_split_blocks_in_place returns early, normalize.rs:293).
+    kNormAllModesNone = 3,
+};
+
 struct Settings {
     int format;        // 1, 2, 3
     int variant;       // Variant
     bool split_alpha;  // BC3 only
     bool split_colour;
+    int normalize = kNormNone;  // BC1 transform only: blocks are normalized on their way into the transform
 };
 
 DLT_HD constexpr int block_bytes(int fmt) { return fmt == 1 ? 8 : 16; }

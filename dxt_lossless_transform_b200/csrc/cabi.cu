@@ -812,6 +812,174 @@ DLT_EXPORT int dltcuda_transform_auto_batch_multi_gpu(DltcudaAutoJob* jobs, size
     return kDltcudaOk;
 }
 
+// =================================================================================================
+// experimental::normalize_blocks (BC1) — additive, the reference has no C ABI for its experimental module
+// (core/dxt-lossless-transform-bc1/src/experimental/normalize_blocks/{normalize.rs,transform.rs}).
+// mode: ColorNormalizationMode, None = 0, Color0Only = 1, ReplicateColor = 2.
+// =================================================================================================
+namespace {
+
+// Host buffers through the device for the stand-alone normalization passes (small helper: one upload, one launch,
+// one download per output; these passes exist for completeness — transform_with_normalize_blocks fuses them).
+int normalize_host(const uint8_t* input, uint8_t* const outs[3], size_t len, bool* any_normalized) {
+    if (len % 8) return kDltcudaInvalidLength;
+    if (any_normalized) *any_normalized = false;
+    if (len == 0) return kDltcudaOk;
+    if (!input) return kDltcudaNullPointer;
+    int nout = 0;
+    for (int m = 0; m < 3; m++) nout += outs[m] != nullptr;
+    Status st;
+    Context* ctx = acquire_context(-1, &st);
+    if (!ctx) return dltcuda_status(st);
+    struct Releaser {
+        Context* c;
+        ~Releaser() { release_context(c); }
+    } releaser{ctx};
+    if ((st = ensure_device_buffers(ctx, len)) != Status::kOk) return dltcuda_status(st);
+    if ((st = ensure_scratch(ctx, 3 * ((len + 255) / 256 * 256) + 256)) != Status::kOk) return dltcuda_status(st);
+    cudaStream_t s = ctx->stream[0];
+    const size_t img = (len + 255) / 256 * 256;
+    unsigned int* d_any = reinterpret_cast<unsigned int*>(ctx->d_scratch + 3 * img);
+    uint8_t* d_out[3];
+    for (int m = 0; m < 3; m++) d_out[m] = outs[m] ? ctx->d_scratch + (size_t)m * img : nullptr;
+    unsigned int any = 0;
+    cudaError_t e = cudaMemcpyAsync(ctx->d_in, input, len, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_any, 0, sizeof(unsigned int), s);
+    if (e == cudaSuccess) e = launch_normalize_blocks(ctx->d_in, d_out[0], d_out[1], d_out[2], len / 8, d_any, s);
+    for (int m = 0; m < 3 && e == cudaSuccess; m++)
+        if (outs[m]) e = cudaMemcpyAsync(outs[m], d_out[m], len, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&any, d_any, sizeof(any), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return dltcuda_status(e);
+    if (any_normalized) *any_normalized = any != 0;
+    (void)nout;
+    return kDltcudaOk;
+}
+
+}  // namespace
+
+// normalize_blocks (normalize.rs:38): output may equal input (in place).
+DLT_EXPORT int dltcuda_bc1_normalize_blocks(const uint8_t* input, uint8_t* output, size_t len, int mode) {
+    if (mode < 0 || mode > 2) return kDltcudaInvalidSettings;
+    if (len % 8) return kDltcudaInvalidLength;
+    if (len && (!input || !output)) return kDltcudaNullPointer;
+    if (mode == kNormNone) {   // normalize.rs:56-66: a plain copy (nothing at all when in place)
+        if (len && input != output) std::memmove(output, input, len);
+        return kDltcudaOk;
+    }
+    uint8_t* outs[3] = {nullptr, nullptr, nullptr};
+    outs[mode] = output;
+    return normalize_host(input, outs, len, nullptr);
+}
+// normalize_blocks_all_modes (normalize.rs:417): one pass, three outputs; *any_normalized = its return value.
+DLT_EXPORT int dltcuda_bc1_normalize_blocks_all_modes(const uint8_t* input, uint8_t* out_none, uint8_t* out_color0_only,
+                                                      uint8_t* out_replicate_color, size_t len, bool* any_normalized) {
+    if (len && (!out_none || !out_color0_only || !out_replicate_color)) return kDltcudaNullPointer;
+    uint8_t* outs[3] = {out_none, out_color0_only, out_replicate_color};
+    return normalize_host(input, outs, len, any_normalized);
+}
+// normalize_split_blocks_in_place (normalize.rs:286): colours ([c0 c1] per block) and indices in separate arrays.
+DLT_EXPORT int dltcuda_bc1_normalize_split_blocks_in_place(uint8_t* colors, uint8_t* indices, size_t num_blocks, int mode) {
+    if (mode < 0 || mode > 2) return kDltcudaInvalidSettings;
+    if (num_blocks == 0 || mode == 0) return kDltcudaOk;
+    if (!colors || !indices) return kDltcudaNullPointer;
+    Status st;
+    Context* ctx = acquire_context(-1, &st);
+    if (!ctx) return dltcuda_status(st);
+    struct Releaser {
+        Context* c;
+        ~Releaser() { release_context(c); }
+    } releaser{ctx};
+    const size_t bytes = num_blocks * 4;
+    if ((st = ensure_device_buffers(ctx, bytes)) != Status::kOk) return dltcuda_status(st);
+    cudaStream_t s = ctx->stream[0];
+    cudaError_t e = cudaMemcpyAsync(ctx->d_in, colors, bytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_out, indices, bytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = launch_normalize_split_blocks(ctx->d_in, ctx->d_out, num_blocks, mode, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(colors, ctx->d_in, bytes, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(indices, ctx->d_out, bytes, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    return dltcuda_status(e);
+}
+// Device-resident normalize_blocks (asynchronous on `stream`; d_output may equal d_input).
+DLT_EXPORT int dltcuda_bc1_normalize_blocks_device(const uint8_t* d_input, uint8_t* d_output, size_t len, int mode, void* stream) {
+    if (mode < 0 || mode > 2) return kDltcudaInvalidSettings;
+    if (len % 8) return kDltcudaInvalidLength;
+    if (len == 0) return kDltcudaOk;
+    if (!d_input || !d_output) return kDltcudaNullPointer;
+    if (mode == kNormNone)
+        return d_input == d_output ? kDltcudaOk
+                                   : dltcuda_status(cudaMemcpyAsync(d_output, d_input, len, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    uint8_t* outs[3] = {nullptr, nullptr, nullptr};
+    outs[mode] = d_output;
+    return dltcuda_status(launch_normalize_blocks(d_input, outs[0], outs[1], outs[2], len / 8, nullptr, (cudaStream_t)stream));
+}
+
+// transform_bc1_with_normalize_blocks (transform.rs:65): normalization fused into the transform kernel — one pass.
+// Host pointers (synchronous) and device pointers (asynchronous).  Untransform with dltbc1core_untransform /
+// dltcuda_untransform_device and the same decorrelation mode + split flag (normalization is not undone).
+DLT_EXPORT int dltcuda_bc1_transform_with_normalize_blocks(const uint8_t* input, uint8_t* output, size_t len,
+                                                           int normalization_mode, uint8_t decorrelation_mode,
+                                                           bool split_colour_endpoints) {
+    if (normalization_mode < 0 || normalization_mode > 2 || decorrelation_mode > 3) return kDltcudaInvalidSettings;
+    if (len % 8) return kDltcudaInvalidLength;
+    if (len == 0) return kDltcudaOk;
+    if (!input || !output) return kDltcudaNullPointer;
+    Settings st{1, decorrelation_mode, false, split_colour_endpoints};
+    st.normalize = normalization_mode;
+    return dltcuda_status(run_host(st, false, input, output, len, -1));
+}
+DLT_EXPORT int dltcuda_bc1_transform_with_normalize_blocks_device(const uint8_t* d_input, uint8_t* d_output, size_t len,
+                                                                  int normalization_mode, uint8_t decorrelation_mode,
+                                                                  bool split_colour_endpoints, void* stream) {
+    if (normalization_mode < 0 || normalization_mode > 2 || decorrelation_mode > 3) return kDltcudaInvalidSettings;
+    if (len % 8) return kDltcudaInvalidLength;
+    if (len == 0) return kDltcudaOk;
+    if (!d_input || !d_output) return kDltcudaNullPointer;
+    Settings st{1, decorrelation_mode, false, split_colour_endpoints};
+    st.normalize = normalization_mode;
+    return dltcuda_status(launch_transform(st, d_input, reference_layout(d_output, len / 8, 0, st), len / 8, (cudaStream_t)stream));
+}
+
+// transform_bc1_auto_with_normalization (transform.rs:222) with the GPU LTU estimator, host pointers, synchronous.
+// out_estimates (optional, >= 24 entries): per-candidate estimates, normalization mode outermost (only when a block was
+// normalizable; otherwise the plain search's 4 / 8 entries).
+DLT_EXPORT int dltcuda_bc1_transform_auto_with_normalization(const uint8_t* input, uint8_t* output, size_t len,
+                                                             bool use_all_modes, int* out_normalization_mode,
+                                                             uint8_t* out_decorrelation_mode, bool* out_split_colour_endpoints,
+                                                             size_t* out_estimates) {
+    if (len % 8) return kDltcudaInvalidLength;
+    if (!out_normalization_mode || !out_decorrelation_mode || !out_split_colour_endpoints) return kDltcudaNullPointer;
+    if (len && (!input || !output)) return kDltcudaNullPointer;
+    Settings best{};
+    if (len == 0) {   // no block is normalizable: the plain search on an empty payload picks its first candidate
+        Settings order[kMaxCandidates];
+        candidate_order(1, use_all_modes, order);
+        best = order[0];
+    } else {
+        Status st;
+        Context* ctx = acquire_context(-1, &st);
+        if (!ctx) return dltcuda_status(st);
+        struct Releaser {
+            Context* c;
+            ~Releaser() { release_context(c); }
+        } releaser{ctx};
+        if ((st = ensure_device_buffers(ctx, len)) != Status::kOk) return dltcuda_status(st);
+        cudaStream_t s = ctx->stream[0];
+        cudaError_t e = cudaMemcpyAsync(ctx->d_in, input, len, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return dltcuda_status(e);
+        if ((st = auto_ltu_norm_device(ctx, ctx->d_in, ctx->d_out, len, use_all_modes, &best, out_estimates, s)) != Status::kOk)
+            return dltcuda_status(st);
+        e = cudaMemcpyAsync(output, ctx->d_out, len, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return dltcuda_status(e);
+    }
+    *out_normalization_mode = best.normalize;
+    *out_decorrelation_mode = (uint8_t)best.variant;
+    *out_split_colour_endpoints = best.split_colour;
+    return kDltcudaOk;
+}
+
 // Candidate order of the search, for callers that want to label out_estimates.  Returns the count.
 DLT_EXPORT int dltcuda_auto_candidates(int format, bool use_all_modes, DltcudaSettings* out /* >= 16 entries */) {
     if (format < 1 || format > 3 || !out) return 0;

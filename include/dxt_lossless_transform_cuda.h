@@ -145,6 +145,39 @@ int dltcuda_transform_auto_batch_multi_gpu(DltcudaAutoJob *jobs, size_t count, b
  * bc3 settings.rs:91-121).  `out` needs 16 entries; returns the count. */
 int dltcuda_auto_candidates(int format, bool use_all_modes, DltcudaSettings *out);
 
+/* ---- experimental: BC1 block normalization -------------------------------------------------------- */
+/* core/dxt-lossless-transform-bc1/src/experimental/normalize_blocks/ (Rust-only and experimental in the reference):
+ * solid-colour and fully transparent blocks get one canonical representation before the transform (visually lossless,
+ * NOT bit-lossless).  normalize.rs:38 normalize_blocks, :286 normalize_split_blocks_in_place, :417
+ * normalize_blocks_all_modes; transform.rs:65 transform_bc1_with_normalize_blocks, :222
+ * transform_bc1_auto_with_normalization.  In the fused transform entry points the normalization happens inside the
+ * transform kernel: one pass over the data. */
+typedef enum DltcudaColorNormalizationMode { /* ColorNormalizationMode::all_values() order, normalize.rs:487-500 */
+  DltcudaColorNormalizationMode_None = 0,
+  DltcudaColorNormalizationMode_Color0Only = 1,
+  DltcudaColorNormalizationMode_ReplicateColor = 2,
+} DltcudaColorNormalizationMode;
+int dltcuda_bc1_normalize_blocks(const uint8_t *input, uint8_t *output, size_t len, int mode);
+int dltcuda_bc1_normalize_blocks_device(const uint8_t *d_input, uint8_t *d_output, size_t len, int mode,
+                                        void *stream);
+int dltcuda_bc1_normalize_blocks_all_modes(const uint8_t *input, uint8_t *out_none, uint8_t *out_color0_only,
+                                           uint8_t *out_replicate_color, size_t len, bool *any_normalized);
+int dltcuda_bc1_normalize_split_blocks_in_place(uint8_t *colors, uint8_t *indices, size_t num_blocks,
+                                                int mode);
+int dltcuda_bc1_transform_with_normalize_blocks(const uint8_t *input, uint8_t *output, size_t len,
+                                                int normalization_mode,
+                                                DltCoreYCoCgVariant decorrelation_mode,
+                                                bool split_colour_endpoints);
+int dltcuda_bc1_transform_with_normalize_blocks_device(const uint8_t *d_input, uint8_t *d_output, size_t len,
+                                                       int normalization_mode,
+                                                       DltCoreYCoCgVariant decorrelation_mode,
+                                                       bool split_colour_endpoints, void *stream);
+/* LTU estimator on the GPU; out_estimates optional (>= 24 entries, normalization mode outermost). */
+int dltcuda_bc1_transform_auto_with_normalization(const uint8_t *input, uint8_t *output, size_t len,
+                                                  bool use_all_modes, int *out_normalization_mode,
+                                                  DltCoreYCoCgVariant *out_decorrelation_mode,
+                                                  bool *out_split_colour_endpoints, size_t *out_estimates);
+
 /* Reads back the settings a manual builder holds (Bc1ManualTransformBuilder::get_settings is
  * Rust-only in the reference).  out_mode uses the STABLE numbering.  Works for dltbc1_ and dltbc2_
  * builders.  Returns non-zero on a null builder. */

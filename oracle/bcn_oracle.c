@@ -537,6 +537,182 @@ void orc_generate_bc3_test_data(uint8_t *p, size_t num_blocks) {
 }
 
 /* ------------------------------------------------------------------------------------------
+ * experimental::normalize_blocks (BC1) — core/dxt-lossless-transform-bc1/src/experimental/normalize_blocks/
+ *   decode_bc1_block            core/dxt-lossless-transform-bc1/src/util/bc1_decode.rs:7-63
+ *   Color565::{red,green,blue}  core/dxt-lossless-transform-common/src/color_565/mod.rs:154-191
+ *   Color565::from_rgb          .../color_565/mod.rs:108-115        (to_565_lossy)
+ *   normalize_blocks            normalize.rs:38-101, normalize_blocks_impl :104-176
+ *   write_normalized_solid_color_block   normalize.rs:199-247
+ *   normalize_split_blocks_in_place      normalize.rs:286-386
+ *   normalize_blocks_all_modes           normalize.rs:417-484
+ *   transform_bc1_with_normalize_blocks  transform.rs:65-176
+ *   transform_bc1_auto_with_normalization transform.rs:222-340, test_normalize_variant_with_normalization :344-408
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { uint8_t r, g, b, a; } rgba8;
+static inline int rgba_eq(rgba8 x, rgba8 y) { return x.r == y.r && x.g == y.g && x.b == y.b && x.a == y.a; }
+static inline uint8_t red8(uint16_t v) { unsigned r = (v & 0xF800u) >> 11; return (uint8_t)((r << 3) | (r >> 2)); }
+static inline uint8_t green8(uint16_t v) { unsigned g = (v & 0x07E0u) >> 5; return (uint8_t)((g << 2) | (g >> 4)); }
+static inline uint8_t blue8(uint16_t v) { unsigned b = v & 0x001Fu; return (uint8_t)((b << 3) | (b >> 2)); }
+
+static void decode_bc1_block(const uint8_t *src, rgba8 px[16]) {
+    const uint16_t c0 = rd16(src), c1 = rd16(src + 2);
+    const uint32_t idx = (uint32_t)src[4] | ((uint32_t)src[5] << 8) | ((uint32_t)src[6] << 16) | ((uint32_t)src[7] << 24);
+    const unsigned r0 = red8(c0), g0 = green8(c0), b0 = blue8(c0), r1 = red8(c1), g1 = green8(c1), b1 = blue8(c1);
+    rgba8 dict[4];
+    dict[0] = (rgba8){(uint8_t)r0, (uint8_t)g0, (uint8_t)b0, 255};
+    dict[1] = (rgba8){(uint8_t)r1, (uint8_t)g1, (uint8_t)b1, 255};
+    if (c0 > c1) { /* four-colour block */
+        dict[2] = (rgba8){(uint8_t)((2 * r0 + r1) / 3), (uint8_t)((2 * g0 + g1) / 3), (uint8_t)((2 * b0 + b1) / 3), 255};
+        dict[3] = (rgba8){(uint8_t)((r0 + 2 * r1) / 3), (uint8_t)((g0 + 2 * g1) / 3), (uint8_t)((b0 + 2 * b1) / 3), 255};
+    } else { /* three colours + transparent black */
+        dict[2] = (rgba8){(uint8_t)((r0 + r1) / 2), (uint8_t)((g0 + g1) / 2), (uint8_t)((b0 + b1) / 2), 255};
+        dict[3] = (rgba8){0, 0, 0, 0};
+    }
+    for (int i = 0; i < 16; i++) px[i] = dict[(idx >> (2 * i)) & 3];
+}
+
+/* BlockCase of normalize_blocks_impl: 0 = CannotNormalize, 1 = Transparent, 2 = SolidColorRoundtrippable (+ colour) */
+static int classify_block(const uint8_t *src, uint16_t *color565) {
+    rgba8 px[16];
+    decode_bc1_block(src, px);
+    for (int i = 1; i < 16; i++)
+        if (!rgba_eq(px[i], px[0])) return 0;
+    if (px[0].a == 0) return 1;
+    const uint16_t c = (uint16_t)(((px[0].r & 0xF8u) << 8) | ((px[0].g & 0xFCu) << 3) | (px[0].b >> 3));
+    *color565 = c;
+    const rgba8 back = {red8(c), green8(c), blue8(c), 255};
+    return rgba_eq(back, px[0]) ? 2 : 0;
+}
+
+static void write_normalized_solid(uint8_t *dst, const uint8_t *src, uint16_t c, int mode) {
+    dst[0] = (uint8_t)c, dst[1] = (uint8_t)(c >> 8);
+    if (mode == ORC_NORM_NONE) {
+        memcpy(dst, src, 8);
+    } else if (mode == ORC_NORM_COLOR0_ONLY) {
+        memset(dst + 2, 0, 6);
+    } else {
+        dst[2] = (uint8_t)c, dst[3] = (uint8_t)(c >> 8);
+        memset(dst + 4, 0, 4);
+    }
+}
+
+void orc_bc1_normalize_blocks(const uint8_t *in, uint8_t *out, size_t len, int mode) {
+    if (mode == ORC_NORM_NONE) {
+        if (in != out) memcpy(out, in, len);
+        return;
+    }
+    for (size_t i = 0; i + 8 <= len; i += 8) {
+        uint16_t c = 0;
+        uint8_t blk[8];
+        memcpy(blk, in + i, 8); /* in-place use is allowed */
+        const int kind = classify_block(blk, &c);
+        if (kind == 1) memset(out + i, 0xFF, 8);
+        else if (kind == 2) write_normalized_solid(out + i, blk, c, mode);
+        else memcpy(out + i, blk, 8);
+    }
+}
+
+int orc_bc1_normalize_blocks_all_modes(const uint8_t *in, uint8_t *out_none, uint8_t *out_color0, uint8_t *out_replicate,
+                                       size_t len) {
+    uint8_t *outs[3] = {out_none, out_color0, out_replicate};
+    int any = 0;
+    for (size_t i = 0; i + 8 <= len; i += 8) {
+        uint16_t c = 0;
+        const int kind = classify_block(in + i, &c);
+        if (kind) any = 1;
+        for (int m = 0; m < 3; m++) {
+            if (kind == 1) memset(outs[m] + i, 0xFF, 8);
+            else if (kind == 2) write_normalized_solid(outs[m] + i, in + i, c, m);
+            else memcpy(outs[m] + i, in + i, 8);
+        }
+    }
+    return any;
+}
+
+void orc_bc1_normalize_split_blocks_in_place(uint8_t *colors, uint8_t *indices, size_t num_blocks, int mode) {
+    if (mode == ORC_NORM_NONE) return;
+    for (size_t b = 0; b < num_blocks; b++) {
+        uint8_t blk[8];
+        memcpy(blk, colors + 4 * b, 4);
+        memcpy(blk + 4, indices + 4 * b, 4);
+        uint16_t c = 0;
+        const int kind = classify_block(blk, &c);
+        if (kind == 1) {
+            memset(colors + 4 * b, 0xFF, 4);
+            memset(indices + 4 * b, 0xFF, 4);
+        } else if (kind == 2) {
+            colors[4 * b] = (uint8_t)c, colors[4 * b + 1] = (uint8_t)(c >> 8);
+            if (mode == ORC_NORM_COLOR0_ONLY) colors[4 * b + 2] = colors[4 * b + 3] = 0;
+            else colors[4 * b + 2] = (uint8_t)c, colors[4 * b + 3] = (uint8_t)(c >> 8);
+            memset(indices + 4 * b, 0, 4);
+        }
+    }
+}
+
+static void decorrelate_in_place(uint8_t *colours, size_t count, int variant) {
+    if (variant == ORC_VARIANT_NONE) return;
+    for (size_t i = 0; i < count; i++) wr16(colours + 2 * i, orc_decorrelate(rd16(colours + 2 * i), variant));
+}
+
+/* The four arms of transform_bc1_with_normalize_blocks, step by step as the reference runs them. */
+void orc_bc1_transform_with_normalize_blocks(const uint8_t *in, uint8_t *out, size_t len, int norm, int variant, int split) {
+    const size_t n = len / 8;
+    uint8_t *work = (uint8_t *)malloc(len / 2 + 8);
+    if (split) {
+        for (size_t b = 0; b < n; b++) { /* colours to the work area, indices to their final place */
+            memcpy(work + 4 * b, in + 8 * b, 4);
+            memcpy(out + len / 2 + 4 * b, in + 8 * b + 4, 4);
+        }
+        if (norm != ORC_NORM_NONE) orc_bc1_normalize_split_blocks_in_place(work, out + len / 2, n, norm);
+        orc_split_color_endpoints(work, out, len / 2);
+    } else {
+        for (size_t b = 0; b < n; b++) {
+            memcpy(out + 4 * b, in + 8 * b, 4);
+            memcpy(out + len / 2 + 4 * b, in + 8 * b + 4, 4);
+        }
+        if (norm != ORC_NORM_NONE) orc_bc1_normalize_split_blocks_in_place(out, out + len / 2, n, norm);
+    }
+    decorrelate_in_place(out, len / 4, variant);
+    free(work);
+}
+
+/* transform_bc1_auto_with_normalization.  est == NULL: the LTU restatement.  Returns 0, or 1 when max_compressed_size
+ * style failures would abort (not modelled: the callback has no such entry); a failing estimate SKIPS the variant. */
+int orc_bc1_transform_auto_with_normalization(const uint8_t *in, uint8_t *out, size_t len, int use_all, orc_estimate_fn est,
+                                              void *ctx, int *out_norm, int *out_variant, int *out_split) {
+    if (!est) est = ltu_cb;
+    uint8_t *nb[3], *sb[3];
+    for (int m = 0; m < 3; m++) nb[m] = (uint8_t *)malloc(len + 8), sb[m] = (uint8_t *)malloc(len + 8);
+    uint8_t *work = (uint8_t *)malloc(len / 2 + 8);
+    const int any = orc_bc1_normalize_blocks_all_modes(in, nb[0], nb[1], nb[2], len);
+    int rc = 0;
+    if (any) {
+        int best_norm = ORC_NORM_NONE, best_variant = ORC_VARIANT_1, best_split = 1; /* Default of the details struct */
+        size_t best = (size_t)-1;
+        for (int m = 0; m < 3; m++) orc_bc1_transform(nb[m], sb[m], len, ORC_VARIANT_NONE, 0); /* plain block split */
+        const int k = use_all ? 8 : 4;
+        for (int m = 0; m < 3; m++)
+            for (int i = 0; i < k; i++) {
+                const int variant = use_all ? BC12_ALL[i][0] : BC12_FAST[i][0], split = use_all ? BC12_ALL[i][1] : BC12_FAST[i][1];
+                if (split) orc_split_color_endpoints(sb[m], work, len / 2);
+                else memcpy(work, sb[m], len / 2);
+                decorrelate_in_place(work, len / 4, variant);
+                size_t size = 0;
+                if (est(ctx, work, len / 2, &size) != 0) continue; /* skip this variant */
+                if (size < best) best = size, best_norm = m, best_variant = variant, best_split = split;
+            }
+        orc_bc1_transform_with_normalize_blocks(in, out, len, best_norm, best_variant, best_split);
+        *out_norm = best_norm, *out_variant = best_variant, *out_split = best_split;
+    } else {
+        *out_norm = ORC_NORM_NONE;
+        rc = orc_bc1_transform_auto(in, out, len, use_all, est, ctx, out_variant, out_split);
+    }
+    for (int m = 0; m < 3; m++) free(nb[m]), free(sb[m]);
+    free(work);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Multi-threaded driver (CPU baseline): contiguous block ranges, one per thread.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {

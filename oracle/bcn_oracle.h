@@ -28,9 +28,6 @@
 
 #ifdef __cplusplus
 extern "C" {
-/* 1 when orc_bcn_run_mt / orc_bcn_run_range take the explicit AVX2 BC1 path on this host. */
-int orc_cpu_baseline_uses_avx2(void);
-
 #endif
 
 /* Internal numbering of common/src/color_565/decorrelate.rs:72-84. */
@@ -95,6 +92,22 @@ void orc_bcn_run_mt(int format, int direction, const uint8_t *in, uint8_t *out, 
 /* Block range [b0, b1) only: reads/writes exactly the slices of every stream that range owns. */
 void orc_bcn_run_range(int format, int direction, const uint8_t *in, uint8_t *out, size_t len,
                        int variant, int split_alpha, int split_colour, size_t b0, size_t b1);
+
+/* experimental::normalize_blocks (BC1); ColorNormalizationMode::all_values() order (normalize.rs:487-500). */
+enum { ORC_NORM_NONE = 0, ORC_NORM_COLOR0_ONLY = 1, ORC_NORM_REPLICATE = 2 };
+void orc_bc1_normalize_blocks(const uint8_t *in, uint8_t *out, size_t len, int mode);
+int orc_bc1_normalize_blocks_all_modes(const uint8_t *in, uint8_t *out_none, uint8_t *out_color0,
+                                       uint8_t *out_replicate, size_t len);
+void orc_bc1_normalize_split_blocks_in_place(uint8_t *colors, uint8_t *indices, size_t num_blocks, int mode);
+void orc_bc1_transform_with_normalize_blocks(const uint8_t *in, uint8_t *out, size_t len, int norm, int variant,
+                                             int split);
+int orc_bc1_transform_auto_with_normalization(const uint8_t *in, uint8_t *out, size_t len, int use_all,
+                                              orc_estimate_fn est, void *ctx, int *out_norm, int *out_variant,
+                                              int *out_split);
+
+/* 1 when orc_bcn_run_mt / orc_bcn_run_range take the explicit AVX2 BC1 path on this host. */
+int orc_cpu_baseline_uses_avx2(void);
+
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,14 @@ def lib() -> C.CDLL:
             g = getattr(L, f"orc_generate_{n}_test_data")
             g.restype, g.argtypes = None, [p, sz]
         L.orc_bcn_run_mt.restype, L.orc_bcn_run_mt.argtypes = None, [i, i, p, p, sz, i, i, i, i]
+        L.orc_bc1_normalize_blocks.restype, L.orc_bc1_normalize_blocks.argtypes = None, [p, p, sz, i]
+        L.orc_bc1_normalize_blocks_all_modes.restype, L.orc_bc1_normalize_blocks_all_modes.argtypes = i, [p, p, p, p, sz]
+        L.orc_bc1_normalize_split_blocks_in_place.restype = None
+        L.orc_bc1_normalize_split_blocks_in_place.argtypes = [p, p, sz, i]
+        L.orc_bc1_transform_with_normalize_blocks.restype = None
+        L.orc_bc1_transform_with_normalize_blocks.argtypes = [p, p, sz, i, i, i]
+        L.orc_bc1_transform_auto_with_normalization.restype = i
+        L.orc_bc1_transform_auto_with_normalization.argtypes = [p, p, sz, i, p, p, ip, ip, ip]
         _lib = L
     return _lib
 
@@ -130,3 +138,36 @@ def run_range(fmt: int, inverse: bool, src: np.ndarray, dst: np.ndarray, variant
     f.restype = None
     f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t]
     f(fmt, int(inverse), _ptr(src), _ptr(dst), src.size, variant, int(split_alpha), int(split_colour), b0, b1)
+
+
+# ---- experimental::normalize_blocks (BC1) ---------------------------------------------------------------
+def normalize_blocks(data: np.ndarray, mode: int) -> np.ndarray:
+    out = np.empty_like(data)
+    lib().orc_bc1_normalize_blocks(_ptr(data), _ptr(out), data.size, mode)
+    return out
+
+
+def normalize_blocks_all_modes(data: np.ndarray):
+    outs = [np.empty_like(data) for _ in range(3)]
+    any_ = lib().orc_bc1_normalize_blocks_all_modes(_ptr(data), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), data.size)
+    return outs, bool(any_)
+
+
+def normalize_split_blocks_in_place(colors: np.ndarray, indices: np.ndarray, mode: int) -> None:
+    lib().orc_bc1_normalize_split_blocks_in_place(_ptr(colors), _ptr(indices), colors.size // 4, mode)
+
+
+def transform_with_normalize_blocks(data: np.ndarray, norm: int, variant: int, split: bool) -> np.ndarray:
+    out = np.empty_like(data)
+    lib().orc_bc1_transform_with_normalize_blocks(_ptr(data), _ptr(out), data.size, norm, variant, int(split))
+    return out
+
+
+def auto_with_normalization(data: np.ndarray, use_all: bool):
+    """Returns (transformed bytes, (norm, variant, split_colour)) with the LTU restatement."""
+    out = np.empty_like(data)
+    n, v, s = C.c_int(), C.c_int(), C.c_int()
+    rc = lib().orc_bc1_transform_auto_with_normalization(_ptr(data), _ptr(out), data.size, int(use_all), None, None,
+                                                         C.byref(n), C.byref(v), C.byref(s))
+    assert rc == 0
+    return out, (n.value, v.value, bool(s.value))
