@@ -160,26 +160,41 @@ __device__ __forceinline__ uint32_t mix3(uint32_t a, uint32_t b, uint32_t wa, ui
     }
     return out;
 }
+// Slow part of normalize_bc1_block: every pixel uses interpolated entry `sel` (2 or 3) of a block with c0 != c1.
+// Returns the RGBA8888 pixel (alpha 0 = the transparent entry of the three-colour mode).
+__device__ __noinline__ uint32_t bc1_interpolated_entry(uint32_t c0, uint32_t c1, uint32_t sel) {
+    const uint32_t e0 = expand565(c0), e1 = expand565(c1);
+    if (c0 > c1) return (sel == 2 ? mix3(e0, e1, 2, 1, 3) : mix3(e0, e1, 1, 2, 3)) | 0xFF000000u;
+    return sel == 2 ? (mix3(e0, e1, 1, 1, 2) | 0xFF000000u) : 0u;
+}
 __device__ __forceinline__ int normalize_bc1_block(uint32_t& c01, uint32_t& idx, const int mode) {
     const uint32_t c0 = c01 & 0xFFFFu, c1 = c01 >> 16;
-    const uint32_t lo = idx & 0x55555555u, hi = (idx >> 1) & 0x55555555u;
-    const bool u0 = (~(lo | hi) & 0x55555555u) != 0, u1 = (lo & ~hi) != 0, u2 = (hi & ~lo) != 0, u3 = (lo & hi) != 0;
-    if ((int)u0 + (int)u1 + (int)u2 + (int)u3 > 1 && c0 != c1) return 0;
-    const uint32_t kOpaque = 0xFF000000u;
-    const uint32_t e0 = expand565(c0), e1 = expand565(c1);
-    const uint32_t d0 = e0 | kOpaque, d1 = e1 | kOpaque;
-    const uint32_t d2 = (c0 > c1 ? mix3(e0, e1, 2, 1, 3) : mix3(e0, e1, 1, 1, 2)) | kOpaque;
-    const uint32_t d3 = c0 > c1 ? (mix3(e0, e1, 1, 2, 3) | kOpaque) : 0u;
-    const uint32_t sel = idx & 3u;
-    const uint32_t first = sel == 0 ? d0 : sel == 1 ? d1 : sel == 2 ? d2 : d3;
-    if ((u0 && d0 != first) || (u1 && d1 != first) || (u2 && d2 != first) || (u3 && d3 != first)) return 0;
-    if ((first >> 24) == 0) {   // fully transparent
-        c01 = idx = 0xFFFFFFFFu;
-        return 1;
+    uint32_t c565;
+    if (c0 == c1) {
+        // entries 0, 1 and 2 decode to the colour itself (c0 > c1 is false: entry 2 = (e0 + e0) / 2), entry 3 is transparent
+        const uint32_t threes = idx & (idx >> 1) & 0x55555555u;
+        if (threes != 0) {
+            if (threes != 0x55555555u) return 0;   // opaque and transparent pixels
+            c01 = idx = 0xFFFFFFFFu;
+            return 1;
+        }
+        c565 = c0;   // an expanded RGB565 colour always converts back to itself
+    } else {
+        const uint32_t sel = idx & 3u;
+        if (idx != sel * 0x55555555u) return 0;   // two index values in use: the pixels differ (see above)
+        if (sel < 2) {
+            c565 = sel == 0 ? c0 : c1;
+        } else {
+            const uint32_t px = bc1_interpolated_entry(c0, c1, sel);
+            if ((px >> 24) == 0) {   // fully transparent
+                c01 = idx = 0xFFFFFFFFu;
+                return 1;
+            }
+            const uint32_t r = px & 0xFFu, g = (px >> 8) & 0xFFu, b = (px >> 16) & 0xFFu;
+            c565 = ((r & 0xF8u) << 8) | ((g & 0xFCu) << 3) | (b >> 3);
+            if ((expand565(c565) | 0xFF000000u) != px) return 0;   // not representable as one RGB565 colour
+        }
     }
-    const uint32_t r = first & 0xFFu, g = (first >> 8) & 0xFFu, b = (first >> 16) & 0xFFu;
-    const uint32_t c565 = ((r & 0xF8u) << 8) | ((g & 0xFCu) << 3) | (b >> 3);
-    if ((expand565(c565) | kOpaque) != first) return 0;
     if (mode == kNormColor0Only) c01 = c565, idx = 0;
     else if (mode == kNormReplicateColor) c01 = c565 | (c565 << 16), idx = 0;
     return 2;   // mode None: the reference writes the source block back
@@ -749,24 +764,66 @@ __device__ __forceinline__ void store_block8(uint8_t* p, uint2 v, bool aligned) 
     for (int k = 0; k < 4; k++) p[k] = (uint8_t)(v.x >> (8 * k)), p[4 + k] = (uint8_t)(v.y >> (8 * k));
 }
 
-// One block per thread.  outs[m] (m = mode) may be null; `any` (optional) is set when a block is normalizable.
+// outs[m] (m = mode) may be null; `any` (optional) is set when a block is normalizable.
 struct NormOuts {
     uint8_t* p[3];
 };
+// The three outputs of one block from ONE evaluation: the BlockCase does not depend on the mode.
+__device__ __forceinline__ bool normalize_all_modes(const uint2 src, uint2 (&o)[3]) {
+    uint2 c0only = src;
+    const int bcase = normalize_bc1_block(c0only.x, c0only.y, kNormColor0Only);
+    o[kNormNone] = bcase == 1 ? c0only : src;
+    o[kNormColor0Only] = c0only;
+    o[kNormReplicateColor] = bcase == 2 ? make_uint2(c0only.x | (c0only.x << 16), 0u) : c0only;
+    return bcase != 0;
+}
+// Byte-aligned fallback: one block per thread.
 __global__ void __launch_bounds__(kThreads)
     normalize_blocks_kernel(const uint8_t* in, const NormOuts outs, const uint64_t nblocks, const bool aligned, unsigned int* any) {
     const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
     bool hit = false;
     if (i < nblocks) {
-        const uint2 src = load_block8(in + 8 * i, aligned);
-        uint2 probe = src;
-        hit = normalize_bc1_block(probe.x, probe.y, kNormColor0Only) != 0;   // the BlockCase does not depend on the mode
+        uint2 o[3];
+        hit = normalize_all_modes(load_block8(in + 8 * i, aligned), o);
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+            if (outs.p[m]) store_block8(outs.p[m] + 8 * i, o[m], aligned);
+    }
+    if (any && __syncthreads_or(hit) && threadIdx.x == 0) atomicOr(any, 1u);
+}
+// 16-byte aligned pointers: a CTA owns a 16 KiB tile, every thread keeps four 128-bit loads in flight (plain loads, not
+// .nc: an output may be the input itself) and writes 128-bit vectors — the shape of the transform kernels.
+__global__ void __launch_bounds__(kThreads)
+    normalize_blocks_vec_kernel(const uint8_t* in, const NormOuts outs, const uint64_t nblocks, unsigned int* any) {
+    const uint64_t vec0 = (uint64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    uint4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+        const uint64_t j = vec0 + (uint64_t)u * kThreads;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (2 * j + 1 < nblocks) {
+            asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
+                         : "l"(in + 16 * j)
+                         : "memory");
+        } else if (2 * j < nblocks) {
+            asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v[u].x), "=r"(v[u].y) : "l"(in + 16 * j) : "memory");
+        }
+    }
+    bool hit = false;
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+        const uint64_t j = vec0 + (uint64_t)u * kThreads;
+        if (2 * j >= nblocks) continue;
+        uint2 a[3], b[3];
+        hit |= normalize_all_modes(make_uint2(v[u].x, v[u].y), a);
+        const bool two = 2 * j + 1 < nblocks;
+        if (two) hit |= normalize_all_modes(make_uint2(v[u].z, v[u].w), b);
 #pragma unroll
         for (int m = 0; m < 3; m++) {
             if (!outs.p[m]) continue;
-            uint2 v = src;
-            if (hit) normalize_bc1_block(v.x, v.y, m);
-            store_block8(outs.p[m] + 8 * i, v, aligned);
+            if (two) stg_stream16(outs.p[m] + 16 * j, make_uint4(a[m].x, a[m].y, b[m].x, b[m].y));
+            else stg_stream8(outs.p[m] + 16 * j, a[m]);
         }
     }
     if (any && __syncthreads_or(hit) && threadIdx.x == 0) atomicOr(any, 1u);
@@ -802,7 +859,13 @@ cudaError_t launch_normalize_blocks(const uint8_t* in, uint8_t* out_none, uint8_
     const NormOuts outs{{out_none, out_color0, out_replicate}};
     const uintptr_t bits = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out_none) |
                            reinterpret_cast<uintptr_t>(out_color0) | reinterpret_cast<uintptr_t>(out_replicate);
-    normalize_blocks_kernel<<<(unsigned)ctas, kThreads, 0, stream>>>(in, outs, nblocks, (bits & 7) == 0, d_any);
+    if ((bits & 15) == 0) {
+        const uint64_t per_cta = 2ull * kThreads * kUnroll;
+        const uint64_t vctas = (nblocks + per_cta - 1) / per_cta;
+        normalize_blocks_vec_kernel<<<(unsigned)vctas, kThreads, 0, stream>>>(in, outs, nblocks, d_any);
+    } else {
+        normalize_blocks_kernel<<<(unsigned)ctas, kThreads, 0, stream>>>(in, outs, nblocks, (bits & 7) == 0, d_any);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
