@@ -125,6 +125,9 @@ SIGNATURES.update(
         ),
         "dltltu_new_size_estimator": (C.POINTER(DltSizeEstimator), []),
         "dltltu_free_size_estimator": (None, [C.POINTER(DltSizeEstimator)]),
+        "dltzstd_new_size_estimator": (C.POINTER(DltSizeEstimator), [C.c_int]),
+        "dltzstd_free_size_estimator": (None, [C.POINTER(DltSizeEstimator)]),
+        "dltzstd_version_number": (C.c_uint, []),
         "dltcuda_ManualTransformBuilder_GetSettings": (C.c_int, [_P, C.POINTER(C.c_uint8), C.POINTER(C.c_bool)]),
         "dltcuda_device_count": (C.c_int, []),
         "dltcuda_set_device": (None, [C.c_int]),

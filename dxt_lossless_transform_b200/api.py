@@ -281,6 +281,75 @@ class LosslessTransformUtilsSizeEstimation(SizeEstimator):
             pass
 
 
+class ZStandardError(RuntimeError):
+    """extensions/compressors/dxt-lossless-transform-zstd/src/lib.rs:23-44."""
+
+
+class InvalidLevel(ZStandardError):
+    def __init__(self, level: int):
+        super().__init__(f"Invalid compression level: {level}")
+        self.level = level
+
+
+class ZStandardSizeEstimation(SizeEstimator):
+    """``ZStandardSizeEstimation`` (dxt-lossless-transform-zstd/src/lib.rs:54-140): the estimate is the size real zstd
+    produces (magicless frame, no content size / checksum / dict id).  zstd is bound from the system's libzstd at run
+    time (csrc/zstd_estimator.cu); inside ``transform_bcN_auto`` the candidates are transformed on the GPU and compressed
+    concurrently, one host thread per candidate."""
+
+    def __init__(self, compression_level: int):
+        if not 1 <= compression_level <= 22:   # lib.rs:62-66
+            raise InvalidLevel(compression_level)
+        self.compression_level = compression_level
+        self._e = N.lib().dltzstd_new_size_estimator(compression_level)
+        if not self._e:
+            raise ZStandardError("no libzstd could be loaded (set DLTCUDA_LIBZSTD)")
+
+    @classmethod
+    def new_fast(cls):
+        return cls(1)
+
+    @classmethod
+    def new_default(cls):
+        return cls(3)
+
+    @classmethod
+    def new_best(cls):
+        return cls(22)
+
+    @staticmethod
+    def library_version() -> int:
+        return int(N.lib().dltzstd_version_number())
+
+    def c_estimator(self):
+        return self._e
+
+    def max_compressed_size(self, len_bytes: int) -> int:
+        out = C.c_size_t(0)
+        rc = self._e.contents.max_compressed_size(self._e.contents.context, len_bytes, C.byref(out))
+        if rc:
+            raise SizeEstimationError(f"code {rc}")
+        return out.value
+
+    def estimate_compressed_size(self, data) -> int:
+        p, n, _k = _ro(data)
+        cap = self.max_compressed_size(n)
+        scratch = (C.c_uint8 * max(cap, 1))()
+        out = C.c_size_t(0)
+        rc = self._e.contents.estimate_compressed_size(self._e.contents.context, p, n, scratch, cap, C.byref(out))
+        if rc:
+            raise SizeEstimationError(f"code {rc}")
+        return out.value
+
+    def __del__(self):
+        try:
+            if self._e:
+                N.lib().dltzstd_free_size_estimator(self._e)
+                self._e = None
+        except Exception:
+            pass
+
+
 class CallbackSizeEstimator(SizeEstimator):
     """A caller-supplied estimator: ``estimate(data: np.ndarray) -> int`` sees HOST memory, exactly as a
     Rust ``SizeEstimationOperations`` implementation would.  Raise to signal failure."""

@@ -14,13 +14,14 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libdxt_lossless_transform_cuda.so"
-SOURCES = ["bcn_kernels.cu", "host_pipeline.cu", "estimator.cu", "auto_search.cu", "cabi.cu", "file_formats.cu"]
+SOURCES = ["bcn_kernels.cu", "host_pipeline.cu", "estimator.cu", "auto_search.cu", "cabi.cu", "file_formats.cu", "zstd_estimator.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
     "--threads", "0",
+    "-ldl",
     "-diag-suppress", "177",  # unused static members of the layout helper in some instantiations
 ]
 

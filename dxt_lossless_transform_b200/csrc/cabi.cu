@@ -11,6 +11,7 @@
 // Nothing in here falls back to the CPU: without a usable CUDA device the calls return an error.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +25,7 @@
 #include "bcn_layout.h"
 #include "estimator.h"
 #include "host_pipeline.h"
+#include "zstd_estimator.h"
 
 using namespace dlt;
 using namespace dlt::cabi;
@@ -182,6 +184,70 @@ Outcome auto_host(int format, const uint8_t* in, size_t in_len, uint8_t* out, si
         // Whole search on the device; one D2H of the winner.
         if ((st = auto_ltu_device(ctx, format, ctx->d_in, ctx->d_out, len, use_all, &best_s, nullptr, s)) != Status::kOk)
             return from_status(st);
+    } else if (is_zstd_estimator(est)) {
+        // dltzstd_new_size_estimator (zstd_estimator.cu): the callback is thread-safe and known, so every candidate is
+        // compressed by its own host thread as soon as its endpoint streams have arrived — the reference's loop
+        // (transform_auto.rs:230-262) compresses them one after another.  Same estimates, same strict-'<' selection.
+        const int level = zstd_estimator_level(est);
+        size_t per = 0;
+        for (int r = 0; r < nr; r++) per += ranges[r].len;
+        constexpr size_t kHostBudget = (size_t)4 << 30;   // pinned candidate images + compression buffers in flight
+        const int wave = (int)std::min<size_t>((size_t)k, std::max<size_t>(1, kHostBudget / (per + max_comp + 1)));
+        if ((st = ensure_host_scratch(ctx, (size_t)wave * (per + max_comp))) != Status::kOk) return from_status(st);
+        uint8_t* images = ctx->h_scratch;
+        size_t totals[kMaxCandidates] = {};
+        uint32_t rcs[kMaxCandidates] = {};
+        cudaEvent_t arrived[kMaxCandidates] = {};
+        Outcome failed = Outcome::kOk;
+        for (int c0 = 0; c0 < k && failed == Outcome::kOk; c0 += wave) {
+            const int wb = std::min(wave, k - c0);
+            std::vector<std::thread> workers;
+            workers.reserve(wb);
+            for (int c = 0; c < wb; c++) {
+                const int i = c0 + c;
+                uint8_t* img = images + (size_t)c * (per + max_comp);
+                e = launch_transform(order[i], ctx->d_in, reference_layout(ctx->d_out, n, 0, order[i]), n, s);
+                size_t at = 0;
+                for (int r = 0; r < nr && e == cudaSuccess; r++) {
+                    e = cudaMemcpyAsync(img + at, ctx->d_out + ranges[r].offset, ranges[r].len, cudaMemcpyDeviceToHost, s);
+                    at += ranges[r].len;
+                }
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&arrived[i], cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaEventRecord(arrived[i], s);
+                if (e != cudaSuccess) {
+                    failed = cuda_fail(e);
+                    break;
+                }
+                cudaEvent_t ev = arrived[i];
+                const int dev = ctx->device;
+                workers.emplace_back([=, &totals, &rcs, &ranges] {
+                    if (cudaSetDevice(dev) != cudaSuccess || cudaEventSynchronize(ev) != cudaSuccess) {
+                        rcs[i] = 3;
+                        return;
+                    }
+                    size_t off = 0, total = 0;
+                    for (int r = 0; r < nr; r++) {
+                        size_t sz = 0;
+                        const uint32_t rc = zstd_compressed_size(level, img + off, ranges[r].len, img + per, max_comp, &sz);
+                        if (rc != 0) rcs[i] = rc;
+                        total += sz, off += ranges[r].len;
+                    }
+                    totals[i] = total;
+                });
+            }
+            for (auto& w : workers) w.join();
+            if (cudaStreamSynchronize(s) != cudaSuccess && failed == Outcome::kOk) failed = Outcome::kDevice;
+        }
+        for (int i = 0; i < k; i++)
+            if (arrived[i]) cudaEventDestroy(arrived[i]);
+        if (failed != Outcome::kOk) return failed;
+        size_t best_size = SIZE_MAX;
+        for (int i = 0; i < k; i++) {
+            if (rcs[i] != 0) return Outcome::kEstimator;
+            if (totals[i] < best_size) best_size = totals[i], best_s = order[i];
+        }
+        e = launch_transform(best_s, ctx->d_in, reference_layout(ctx->d_out, n, 0, best_s), n, s);
+        if (e != cudaSuccess) return cuda_fail(e);
     } else {
         // Caller-supplied estimator: it sees host memory, exactly as in the reference — each
         // candidate is transformed on the GPU and only the estimated ranges travel back.
@@ -729,48 +795,93 @@ int auto_batch_host(DltcudaAutoJob* jobs, size_t count, bool use_all) {
         Context* c;
         ~Releaser() { release_context(c); }
     } releaser{ctx};
-    cudaStream_t s = ctx->stream[0];
-    constexpr size_t kRoundBytes = (size_t)1 << 30;   // payload bytes uploaded per round
-
-    size_t i0 = 0;
-    while (i0 < count) {
-        // ---- a round: consecutive valid jobs up to kRoundBytes (at least one)
-        std::vector<size_t> idx;
-        std::vector<size_t> offset;
-        size_t total = 0, i1 = i0;
-        for (; i1 < count; i1++) {
-            DltcudaAutoJob& j = jobs[i1];
-            j.status = kDltcudaOk;
-            if (j.format < 1 || j.format > 3) { note(j, kDltcudaInvalidSettings); continue; }
-            if (j.len % (size_t)block_bytes(j.format)) { note(j, kDltcudaInvalidLength); continue; }
-            if (j.len && (!j.input || !j.output)) { note(j, kDltcudaNullPointer); continue; }
-            const size_t padded = (j.len + 255) / 256 * 256;
-            if (!idx.empty() && total + padded > kRoundBytes) break;
-            idx.push_back(i1);
-            offset.push_back(total);
-            total += padded;
-        }
-        if (!idx.empty()) {
-            if ((st = ensure_device_buffers(ctx, total ? total : 256)) != Status::kOk) return dltcuda_status(st);
-            std::vector<AutoJob> aj(idx.size());
-            cudaError_t e = cudaSuccess;
-            for (size_t k = 0; k < idx.size() && e == cudaSuccess; k++) {
-                const DltcudaAutoJob& j = jobs[idx[k]];
-                aj[k] = AutoJob{j.format, ctx->d_in + offset[k], ctx->d_out + offset[k], j.len, Settings{}, {}};
-                if (j.len) e = cudaMemcpyAsync(ctx->d_in + offset[k], j.input, j.len, cudaMemcpyHostToDevice, s);
-            }
-            if (e != cudaSuccess) return dltcuda_status(e);
-            if ((st = auto_ltu_device_batch(ctx, aj.data(), (int)aj.size(), use_all, s)) != Status::kOk) return dltcuda_status(st);
-            for (size_t k = 0; k < idx.size() && e == cudaSuccess; k++) {
-                DltcudaAutoJob& j = jobs[idx[k]];
-                j.out_settings = DltcudaSettings{j.format, (uint8_t)aj[k].best.variant, aj[k].best.split_alpha, aj[k].best.split_colour};
-                if (j.len) e = cudaMemcpyAsync(j.output, ctx->d_out + offset[k], j.len, cudaMemcpyDeviceToHost, s);
-            }
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-            if (e != cudaSuccess) return dltcuda_status(e);
-        }
-        i0 = i1;
+    // Three queues: uploads, the search (transform candidates + estimator + winners), downloads.  The payloads are cut
+    // into ROUNDS; round r+1 is uploaded and round r-1 downloaded while round r is searched (two device slots).
+    cudaStream_t s_search = ctx->stream[0], s_in = ctx->stream[1], s_out = ctx->stream[2];
+    struct Round {
+        std::vector<size_t> idx, offset;
+        size_t total = 0;
+    };
+    size_t all_bytes = 0;
+    for (size_t i = 0; i < count; i++) all_bytes += jobs[i].len;
+    // enough rounds to overlap the copies with the search, large enough to keep the estimator's launches busy
+    const size_t round_bytes = std::min<size_t>((size_t)256 << 20, std::max<size_t>((size_t)16 << 20, all_bytes / 8));
+    std::vector<Round> rounds;
+    for (size_t i = 0; i < count; i++) {
+        DltcudaAutoJob& j = jobs[i];
+        j.status = kDltcudaOk;
+        if (j.format < 1 || j.format > 3) { note(j, kDltcudaInvalidSettings); continue; }
+        if (j.len % (size_t)block_bytes(j.format)) { note(j, kDltcudaInvalidLength); continue; }
+        if (j.len && (!j.input || !j.output)) { note(j, kDltcudaNullPointer); continue; }
+        const size_t padded = (j.len + 255) / 256 * 256;
+        if (rounds.empty() || (!rounds.back().idx.empty() && rounds.back().total + padded > round_bytes)) rounds.emplace_back();
+        Round& r = rounds.back();
+        r.idx.push_back(i);
+        r.offset.push_back(r.total);
+        r.total += padded;
     }
+    if (rounds.empty()) return first_error;
+    size_t slot_bytes = 256;
+    for (const Round& r : rounds) slot_bytes = std::max(slot_bytes, r.total);
+    const int nslots = rounds.size() > 1 ? 2 : 1;
+    if ((st = ensure_device_buffers(ctx, slot_bytes * nslots)) != Status::kOk) return dltcuda_status(st);
+
+    struct InFlight {   // nothing may touch caller memory after the call returns, whatever the exit path
+        cudaStream_t s[3];
+        cudaEvent_t uploaded[2] = {}, downloaded[2] = {};
+        ~InFlight() {
+            for (cudaStream_t q : s) (void)cudaStreamSynchronize(q);
+            for (int i = 0; i < 2; i++) {
+                if (uploaded[i]) cudaEventDestroy(uploaded[i]);
+                if (downloaded[i]) cudaEventDestroy(downloaded[i]);
+            }
+        }
+    } fl{{s_search, s_in, s_out}};
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < nslots && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&fl.uploaded[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fl.downloaded[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) return dltcuda_status(e);
+
+    auto upload = [&](size_t r) {
+        const int slot = (int)(r % nslots);
+        cudaError_t err = cudaSuccess;
+        for (size_t k = 0; k < rounds[r].idx.size() && err == cudaSuccess; k++) {
+            const DltcudaAutoJob& j = jobs[rounds[r].idx[k]];
+            if (j.len)
+                err = cudaMemcpyAsync(ctx->d_in + slot * slot_bytes + rounds[r].offset[k], j.input, j.len, cudaMemcpyHostToDevice, s_in);
+        }
+        if (err == cudaSuccess) err = cudaEventRecord(fl.uploaded[slot], s_in);
+        return err;
+    };
+    if ((e = upload(0)) != cudaSuccess) return dltcuda_status(e);
+    for (size_t r = 0; r < rounds.size(); r++) {
+        const int slot = (int)(r % nslots);
+        const Round& rd = rounds[r];
+        // the other slot's input was last read by round r-1's search, which has completed (the search ends with a wait)
+        if (r + 1 < rounds.size() && (e = upload(r + 1)) != cudaSuccess) return dltcuda_status(e);
+        e = cudaStreamWaitEvent(s_search, fl.uploaded[slot], 0);
+        // this slot's output may still be on its way to the host (round r-2)
+        if (e == cudaSuccess && r >= 2) e = cudaStreamWaitEvent(s_search, fl.downloaded[slot], 0);
+        if (e != cudaSuccess) return dltcuda_status(e);
+        std::vector<AutoJob> aj(rd.idx.size());
+        for (size_t k = 0; k < rd.idx.size(); k++) {
+            const DltcudaAutoJob& j = jobs[rd.idx[k]];
+            aj[k] = AutoJob{j.format, ctx->d_in + slot * slot_bytes + rd.offset[k], ctx->d_out + slot * slot_bytes + rd.offset[k],
+                            j.len, Settings{}, {}};
+        }
+        if ((st = auto_ltu_device_batch(ctx, aj.data(), (int)aj.size(), use_all, s_search)) != Status::kOk) return dltcuda_status(st);
+        for (size_t k = 0; k < rd.idx.size() && e == cudaSuccess; k++) {
+            DltcudaAutoJob& j = jobs[rd.idx[k]];
+            j.out_settings = DltcudaSettings{j.format, (uint8_t)aj[k].best.variant, aj[k].best.split_alpha, aj[k].best.split_colour};
+            if (j.len) e = cudaMemcpyAsync(j.output, ctx->d_out + slot * slot_bytes + rd.offset[k], j.len, cudaMemcpyDeviceToHost, s_out);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(fl.downloaded[slot], s_out);
+        if (e != cudaSuccess) return dltcuda_status(e);
+    }
+    e = cudaStreamSynchronize(s_out);
+    if (e != cudaSuccess) return dltcuda_status(e);
     return first_error;
 }
 }  // namespace cabi

@@ -213,6 +213,17 @@ Status ensure_scratch(Context* ctx, size_t bytes) {
     return Status::kOk;
 }
 
+Status ensure_host_scratch(Context* ctx, size_t bytes) {
+    if (ctx->h_scratch_cap >= bytes && ctx->h_scratch) return Status::kOk;
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    ctx->h_scratch = nullptr;
+    ctx->h_scratch_cap = 0;
+    const size_t cap = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    DLT_CUDA(cudaMallocHost(&ctx->h_scratch, cap));
+    ctx->h_scratch_cap = cap;
+    return Status::kOk;
+}
+
 Status ensure_staging(Context* ctx) {
     for (int i = 0; i < kStages; i++) {
         if (!ctx->h_in[i]) DLT_CUDA(cudaMallocHost(&ctx->h_in[i], kStagingSlotBytes));

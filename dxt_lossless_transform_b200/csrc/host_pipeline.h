@@ -49,6 +49,8 @@ struct Context {
     uint8_t* h_out[kStages] = {};
     uint8_t* d_scratch = nullptr;  // estimator scratch (see estimator.h)
     size_t d_scratch_cap = 0;
+    uint8_t* h_scratch = nullptr;  // pinned host scratch kept between calls (zstd search: candidate images)
+    size_t h_scratch_cap = 0;
     Context* next_free = nullptr;
 };
 
@@ -60,6 +62,7 @@ void release_context(Context* ctx);
 Status ensure_device_buffers(Context* ctx, size_t len);
 Status ensure_scratch(Context* ctx, size_t bytes);
 Status ensure_staging(Context* ctx);
+Status ensure_host_scratch(Context* ctx, size_t bytes);
 
 // transform (inverse=false) or untransform (inverse=true) `len` bytes of host memory; blocks until
 // `out` holds the result.

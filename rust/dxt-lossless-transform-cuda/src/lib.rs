@@ -12,6 +12,7 @@
 //! whose reference signature has no return value).
 #![allow(non_camel_case_types)]
 
+pub mod extensions; // zstd estimator (host threads) and experimental::normalize_blocks
 pub mod file_formats; // TransformBundle / dispatch / DdsHandler over the dltff_* and dltdds_* symbols
 
 use core::ffi::c_void;
