@@ -6,7 +6,7 @@ Host RAM need not hold 64 GiB: the batch cycles a pinned pool (default 4 GiB in 
 same pool payloads are submitted repeatedly until the requested total has gone through; every pool
 payload is verified against the oracle once (sampled subset) and by a round trip.
 
-    python tools/batch_probe.py [total_GiB=64] [pool_GiB=4] [num_gpus=all]
+    python tests/probes/batch_probe.py [total_GiB=64] [pool_GiB=4] [num_gpus=all]
 """
 import json
 import sys
@@ -15,7 +15,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
