@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <vector>
 
 namespace dlt {
 namespace {
@@ -911,19 +912,38 @@ SegPlan plan_segment(size_t len, uint32_t run_len) {
 
 constexpr size_t kSmallPositions = 4096;   // at or below: the single-launch kernel
 
-// Piece length for a set of segments: one resident wave of piece-threads over the whole batch (a second, nearly
-// empty wave would double the time), never shorter than kMinRunLen (per-piece overhead: table init and publish,
-// up to 4 parked keys per class).
-uint32_t choose_run_len(const LtuSegment* segs, int nseg) {
-    size_t total = 0, large = 0;
-    for (int i = 0; i < nseg; i++) {
-        const size_t npos = ltu_positions(segs[i].len);
-        if (npos > kSmallPositions) total += npos, large++;
-    }
-    const size_t budget = kTargetPieces > large * (kParts + 1) + 4096 ? kTargetPieces - large * (kParts + 1) : 4096;
+// Piece length for ONE launch set (up to kMaxSegs large segments share a set of launches): one resident wave of
+// piece-threads over the set (a second, nearly empty wave would double the time), never shorter than kMinRunLen
+// (per-piece overhead: table init and publish, up to 4 parked keys per class) and never longer than four average
+// partitions: with many small segments the partitions alone fill the wave, and an unbounded piece length would make
+// the heaviest partition of a skewed stream (flat texture regions put most positions into one bucket) ONE thread's
+// sequential job.
+uint32_t choose_run_len(const LtuSegment* segs, const int* idx, int n) {
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += ltu_positions(segs[idx[i]].len);
+    const size_t parts = (size_t)n * (kParts + 1);
+    const size_t budget = kTargetPieces > parts + 4096 ? kTargetPieces - parts : 4096;
     size_t len = (total + budget - 1) / budget;
+    const size_t cap = n ? 4 * (total / ((size_t)n * kParts) + 1) : 0;
+    if (len > cap) len = cap;
     len = (len + 31) / 32 * 32;
     return (uint32_t)(len < kMinRunLen ? kMinRunLen : len);
+}
+
+// The launch sets of a call: large segments in input order, kMaxSegs at a time, each set with its own piece length.
+struct LaunchSet {
+    std::vector<int> idx;
+    uint32_t run_len;
+};
+std::vector<LaunchSet> plan_sets(const LtuSegment* segs, int nseg) {
+    std::vector<LaunchSet> sets;
+    for (int i = 0; i < nseg; i++) {
+        if (ltu_positions(segs[i].len) <= kSmallPositions) continue;
+        if (sets.empty() || (int)sets.back().idx.size() == kMaxSegs) sets.emplace_back();
+        sets.back().idx.push_back(i);
+    }
+    for (LaunchSet& st : sets) st.run_len = choose_run_len(segs, st.idx.data(), (int)st.idx.size());
+    return sets;
 }
 
 }  // namespace
@@ -934,11 +954,8 @@ inline size_t result_bytes(int nseg) { return align_up((size_t)(nseg > 0 ? nseg 
 
 size_t ltu_scratch_bytes(const LtuSegment* segs, int nseg) {
     size_t total = result_bytes(nseg);
-    const uint32_t run_len = choose_run_len(segs, nseg);
-    for (int i = 0; i < nseg; i++) {
-        const SegPlan p = plan_segment(segs[i].len, run_len);
-        if (p.npos > kSmallPositions) total += p.bytes();
-    }
+    for (const LaunchSet& st : plan_sets(segs, nseg))
+        for (int i : st.idx) total += plan_segment(segs[i].len, st.run_len).bytes();
     return total;
 }
 
@@ -965,7 +982,6 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
     if ((e = cudaFuncSetAttribute(ltu_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmemBytes)) != cudaSuccess)
         return fail(e);
 
-    const uint32_t run_len = choose_run_len(segs, nseg);
     uint8_t* p = scratch + result_bytes(nseg);
     auto take = [&p](size_t bytes) {
         uint8_t* r = p;
@@ -996,7 +1012,6 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
     // ---- large segments: nine launches per group
     {
         SortBatch b{};
-        b.run_len = run_len;
         int nl = 0;
         uint32_t max_tiles = 0, max_scan_blocks = 0, max_piece_warps = 0, max_chunks = 0;
         auto flush = [&]() {
@@ -1020,31 +1035,32 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
             nl = 0, max_tiles = max_scan_blocks = max_piece_warps = max_chunks = 0;
             return cudaGetLastError();
         };
-        for (int i = 0; i < nseg; i++) {
-            const SegPlan pl = plan_segment(segs[i].len, run_len);
-            if (pl.npos <= kSmallPositions) continue;
-            const int k = nl++;
-            b.seg[k] = segs[i];
-            b.slot[k] = (uint32_t)i;
-            b.npos[k] = (uint32_t)pl.npos;
-            b.ntiles[k] = (uint32_t)pl.ntiles;
-            b.rec[k] = reinterpret_cast<uint32_t*>(take(pl.rec_bytes));
-            b.cnt[k] = reinterpret_cast<uint32_t*>(take(pl.cnt_bytes));
-            b.blk[k] = reinterpret_cast<uint32_t*>(take(pl.blk_bytes));
-            b.part_off[k] = reinterpret_cast<uint32_t*>(take(pl.poff_bytes));
-            b.piece_base[k] = reinterpret_cast<uint32_t*>(take(pl.pbase_bytes));
-            b.part[k] = reinterpret_cast<uint16_t*>(take(pl.part_bytes));
-            b.state[k] = reinterpret_cast<uint32_t*>(take(pl.state_bytes));
-            b.dkey[k] = reinterpret_cast<uint32_t*>(take(pl.dkey_bytes));
-            b.sum_word[k] = reinterpret_cast<uint32_t*>(take(pl.sumw_bytes));
-            b.sum_part[k] = reinterpret_cast<uint16_t*>(take(pl.sump_bytes));
-            max_tiles = std::max(max_tiles, (uint32_t)pl.ntiles);
-            max_scan_blocks = std::max(max_scan_blocks, (uint32_t)((pl.ntiles + kColChunk - 1) / kColChunk));
-            max_piece_warps = std::max(max_piece_warps, (uint32_t)((pl.max_pieces + 31) / 32));
-            max_chunks = std::max(max_chunks, (uint32_t)pl.max_chunks);
-            if (nl == kMaxSegs && (e = flush()) != cudaSuccess) return fail(e);
+        for (const LaunchSet& st : plan_sets(segs, nseg)) {
+            b.run_len = st.run_len;
+            for (int i : st.idx) {
+                const SegPlan pl = plan_segment(segs[i].len, st.run_len);
+                const int k = nl++;
+                b.seg[k] = segs[i];
+                b.slot[k] = (uint32_t)i;
+                b.npos[k] = (uint32_t)pl.npos;
+                b.ntiles[k] = (uint32_t)pl.ntiles;
+                b.rec[k] = reinterpret_cast<uint32_t*>(take(pl.rec_bytes));
+                b.cnt[k] = reinterpret_cast<uint32_t*>(take(pl.cnt_bytes));
+                b.blk[k] = reinterpret_cast<uint32_t*>(take(pl.blk_bytes));
+                b.part_off[k] = reinterpret_cast<uint32_t*>(take(pl.poff_bytes));
+                b.piece_base[k] = reinterpret_cast<uint32_t*>(take(pl.pbase_bytes));
+                b.part[k] = reinterpret_cast<uint16_t*>(take(pl.part_bytes));
+                b.state[k] = reinterpret_cast<uint32_t*>(take(pl.state_bytes));
+                b.dkey[k] = reinterpret_cast<uint32_t*>(take(pl.dkey_bytes));
+                b.sum_word[k] = reinterpret_cast<uint32_t*>(take(pl.sumw_bytes));
+                b.sum_part[k] = reinterpret_cast<uint16_t*>(take(pl.sump_bytes));
+                max_tiles = std::max(max_tiles, (uint32_t)pl.ntiles);
+                max_scan_blocks = std::max(max_scan_blocks, (uint32_t)((pl.ntiles + kColChunk - 1) / kColChunk));
+                max_piece_warps = std::max(max_piece_warps, (uint32_t)((pl.max_pieces + 31) / 32));
+                max_chunks = std::max(max_chunks, (uint32_t)pl.max_chunks);
+            }
+            if ((e = flush()) != cudaSuccess) return fail(e);
         }
-        if ((e = flush()) != cudaSuccess) return fail(e);
     }
 
     static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "");
