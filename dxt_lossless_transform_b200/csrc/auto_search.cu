@@ -4,6 +4,7 @@
 #include "bcn_kernels.h"
 #include "estimator.h"
 
+#include <algorithm>
 #include <vector>
 
 namespace dlt {
@@ -172,8 +173,62 @@ Status auto_ltu_norm_device(Context* ctx, const uint8_t* d_in, uint8_t* d_out, s
     return final_transform(best_s, d_in, d_out, len, stream);
 }
 
+// Queues the transforms of many (payload, settings) pairs with ONE launch per distinct settings combination
+// (launch_transform_batch); the item descriptors go through `d_desc` (device, room for `n` items).  Pairs the tiled
+// kernels cannot take (misaligned pointers) are launched one by one.
+struct BatchedTransform {
+    Settings st;
+    const uint8_t* in;
+    uint8_t* image;   // reference layout for `len` bytes
+    size_t len;
+};
+static cudaError_t queue_transforms(const BatchedTransform* work, int n, TransformBatchItem* d_desc, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    struct Group {
+        Settings st;
+        std::vector<TransformBatchItem> items;
+        uint64_t max_blocks = 0;
+        bool ragged = false;
+    };
+    std::vector<Group> groups;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < n && e == cudaSuccess; i++) {
+        const BatchedTransform& w = work[i];
+        const size_t nb = w.len / block_bytes(w.st.format);
+        if (nb == 0) continue;
+        TransformBatchItem item{w.in, reference_layout(w.image, nb, 0, w.st), nb};
+        bool ragged = false;
+        if (!transform_batch_item_ok(w.st, item, &ragged)) {
+            e = launch_transform(w.st, w.in, item.out, nb, stream);
+            continue;
+        }
+        Group* g = nullptr;
+        for (Group& c : groups)
+            if (c.st.format == w.st.format && c.st.variant == w.st.variant && c.st.split_alpha == w.st.split_alpha &&
+                c.st.split_colour == w.st.split_colour && c.items.size() < 65535)
+                g = &c;
+        if (!g) groups.emplace_back(), g = &groups.back(), g->st = w.st;
+        g->items.push_back(item);
+        g->max_blocks = std::max<uint64_t>(g->max_blocks, nb);
+        g->ragged |= ragged;
+    }
+    if (e != cudaSuccess) return e;
+    std::vector<TransformBatchItem> all;
+    for (const Group& g : groups) all.insert(all.end(), g.items.begin(), g.items.end());
+    if (all.empty()) return cudaSuccess;
+    e = cudaMemcpyAsync(d_desc, all.data(), all.size() * sizeof(TransformBatchItem), cudaMemcpyHostToDevice, stream);
+    size_t at = 0;
+    for (const Group& g : groups) {
+        if (e != cudaSuccess) break;
+        e = launch_transform_batch(g.st, d_desc + at, (int)g.items.size(), g.max_blocks, g.ragged, stream);
+        at += g.items.size();
+    }
+    return e;
+}
+
 Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_all, cudaStream_t stream) {
     constexpr size_t kScratchBudget = (size_t)12 << 30;
+    auto desc_bytes = [](size_t ncands) { return (ncands * sizeof(TransformBatchItem) + 255) / 256 * 256; };
     auto cuda_fail = [](cudaError_t e) {
         note_cuda_error(e);
         return Status::kCudaError;
@@ -188,6 +243,7 @@ Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_al
         // ---- the largest group [j0, j1) whose images + estimator scratch fit the budget
         std::vector<LtuSegment> segs;
         std::vector<Cand> cands;
+        LtuScratchMeter meter;
         size_t image_bytes = 0;
         int j1 = j0;
         for (; j1 < njobs; j1++) {
@@ -198,19 +254,19 @@ Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_al
             EstimateRange ranges[2];
             const int nr = estimate_ranges(job.format, job.len, ranges);
             const size_t img = (job.len + 255) / 256 * 256;
-            const size_t mark_segs = segs.size(), mark_cands = cands.size();
+            LtuScratchMeter with_job = meter;
+            for (int c = 0; c < k; c++)
+                for (int r = 0; r < nr; r++) with_job.add(ranges[r].len);
+            const size_t need = image_bytes + (size_t)k * img + desc_bytes(cands.size() + k) + with_job.bytes();
+            if (need > kScratchBudget && j1 > j0) break;   // this job starts the next group
+            meter = with_job;
             for (int c = 0; c < k; c++) {
                 cands.push_back(Cand{j1, c, nullptr, (int)segs.size(), nr});
                 for (int r = 0; r < nr; r++) segs.push_back(LtuSegment{nullptr, ranges[r].len});
             }
-            const size_t need = image_bytes + (size_t)k * img + ltu_scratch_bytes(segs.data(), (int)segs.size());
-            if (need > kScratchBudget && j1 > j0) {   // this job starts the next group
-                segs.resize(mark_segs), cands.resize(mark_cands);
-                break;
-            }
             image_bytes += (size_t)k * img;
         }
-        if (!cands.empty() && image_bytes + ltu_scratch_bytes(segs.data(), (int)segs.size()) > kScratchBudget) {
+        if (!cands.empty() && image_bytes + desc_bytes(cands.size()) + meter.bytes() > kScratchBudget) {
             // a single job that is too large for one group: the single-payload path batches its candidates itself
             AutoJob& job = jobs[j0];
             const Status st = auto_ltu_device(ctx, job.format, job.d_in, job.d_out, job.len, use_all, &job.best, job.sizes, stream);
@@ -218,28 +274,32 @@ Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_al
             j0 = j0 + 1;
             continue;
         }
-        Status st = ensure_scratch(ctx, image_bytes + ltu_scratch_bytes(segs.data(), (int)segs.size()));
+        const size_t est_offset = image_bytes + desc_bytes(cands.size());
+        Status st = ensure_scratch(ctx, est_offset + meter.bytes());
         if (st != Status::kOk) return st;
+        TransformBatchItem* d_desc = reinterpret_cast<TransformBatchItem*>(ctx->d_scratch + image_bytes);
 
         // ---- transform every candidate of every job of the group, point the segments at the endpoint streams
         uint8_t* next_image = ctx->d_scratch;
+        std::vector<BatchedTransform> work;
+        work.reserve(cands.size());
         for (Cand& cd : cands) {
             const AutoJob& job = jobs[cd.job];
             Settings order[kMaxCandidates];
             candidate_order(job.format, use_all, order);
             EstimateRange ranges[2];
             estimate_ranges(job.format, job.len, ranges);
-            const size_t n = job.len / block_bytes(job.format);
             cd.image = next_image;
             next_image += (job.len + 255) / 256 * 256;
-            const cudaError_t e = launch_transform(order[cd.index], job.d_in, reference_layout(cd.image, n, 0, order[cd.index]), n, stream);
-            if (e != cudaSuccess) return cuda_fail(e);
+            work.push_back(BatchedTransform{order[cd.index], job.d_in, cd.image, job.len});
             for (int r = 0; r < cd.nseg; r++) segs[cd.first_seg + r].d_ptr = cd.image + ranges[r].offset;
         }
+        cudaError_t qe = queue_transforms(work.data(), (int)work.size(), d_desc, stream);
+        if (qe != cudaSuccess) return cuda_fail(qe);
         std::vector<uint64_t> matches(segs.size(), 0);
         if (!segs.empty()) {
-            st = ltu_matches_device(segs.data(), (int)segs.size(), matches.data(), stream, ctx->d_scratch + image_bytes,
-                                    ctx->d_scratch_cap - image_bytes);
+            st = ltu_matches_device(segs.data(), (int)segs.size(), matches.data(), stream, ctx->d_scratch + est_offset,
+                                    ctx->d_scratch_cap - est_offset);
             if (st != Status::kOk) return st;
         }
 
@@ -261,13 +321,12 @@ Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_al
             job.sizes[cd.index] = total;
             if (total < best_size[cd.job - j0]) best_size[cd.job - j0] = total, job.best = order[cd.index];
         }
-        for (int j = j0; j < j1; j++) {
-            const AutoJob& job = jobs[j];
-            if (job.len == 0) continue;
-            const size_t n = job.len / block_bytes(job.format);
-            const cudaError_t e = launch_transform(job.best, job.d_in, reference_layout(job.d_out, n, 0, job.best), n, stream);
-            if (e != cudaSuccess) return cuda_fail(e);
-        }
+        work.clear();
+        for (int j = j0; j < j1; j++)
+            if (jobs[j].len) work.push_back(BatchedTransform{jobs[j].best, jobs[j].d_in, jobs[j].d_out, jobs[j].len});
+        // (the descriptor area holds at least one entry per candidate, hence per job; stream order protects its reuse)
+        qe = queue_transforms(work.data(), (int)work.size(), d_desc, stream);
+        if (qe != cudaSuccess) return cuda_fail(qe);
         j0 = j1;
     }
     const cudaError_t e = cudaStreamSynchronize(stream);

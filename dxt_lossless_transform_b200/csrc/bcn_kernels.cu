@@ -315,9 +315,8 @@ __device__ __forceinline__ uint4 load_vector(const uint8_t* tin, const int j, co
 // sector whole; only the first and the last sector of the launch's range are written bytewise.
 constexpr int kHalo = 32;   // blocks: covers 31 bytes of the narrowest stream (1 byte per block)
 
-template <int FMT, bool SA, bool SC, int VAR, bool RAGGED, int NORM = kNormNone>
-__global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
-    transform_tiled(const uint8_t* __restrict__ in, const StreamPtrs out, const uint64_t nblocks) {
+template <int FMT, bool SA, bool SC, int VAR, bool RAGGED, int NORM>
+__device__ __forceinline__ void transform_tile(const uint8_t* __restrict__ in, const StreamPtrs& out, const uint64_t nblocks) {
     using L = Lay<FMT, SA, SC, RAGGED ? kHalo : 0>;
     __shared__ __align__(16) uint8_t stage[L::kStageBytes];
 
@@ -402,6 +401,22 @@ __global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
             }
         }
     }
+}
+
+template <int FMT, bool SA, bool SC, int VAR, bool RAGGED, int NORM = kNormNone>
+__global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
+    transform_tiled(const uint8_t* __restrict__ in, const StreamPtrs out, const uint64_t nblocks) {
+    transform_tile<FMT, SA, SC, VAR, RAGGED, NORM>(in, out, nblocks);
+}
+
+// Many independent payloads with the same settings in ONE launch (the candidates of a batched best-settings search:
+// a directory of small textures is launch-bound otherwise): blockIdx.y picks the payload, blockIdx.x its tile.
+template <int FMT, bool SA, bool SC, int VAR, bool RAGGED>
+__global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS) transform_tiled_batch(const TransformBatchItem* __restrict__ items) {
+    const TransformBatchItem it = items[blockIdx.y];
+    using L = Lay<FMT, SA, SC>;
+    if ((uint64_t)blockIdx.x * L::T >= it.nblocks) return;
+    transform_tile<FMT, SA, SC, VAR, RAGGED, kNormNone>(it.in, it.out, it.nblocks);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -718,7 +733,62 @@ cudaError_t dispatch(const Settings& st, bool inverse, const uint8_t* bi, uint8_
     }
 }
 
+template <int FMT, bool SA, bool SC, int VAR>
+cudaError_t run_batch(const TransformBatchItem* d_items, int nitems, uint64_t max_blocks, bool ragged, cudaStream_t stream) {
+    using L = Lay<FMT, SA, SC>;
+    const uint64_t tiles = (max_blocks + L::T - 1) / L::T;
+    if (tiles > 0x7fffffffull || nitems > 65535) return cudaErrorInvalidValue;
+    const dim3 grid((unsigned)tiles, (unsigned)nitems);
+    if (ragged) transform_tiled_batch<FMT, SA, SC, VAR, true><<<grid, kThreads, 0, stream>>>(d_items);
+    else transform_tiled_batch<FMT, SA, SC, VAR, false><<<grid, kThreads, 0, stream>>>(d_items);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+template <int FMT, bool SA, bool SC>
+cudaError_t run_batch_var(int var, const TransformBatchItem* d, int n, uint64_t mb, bool ragged, cudaStream_t s) {
+    switch (var) {
+        case kNone: return run_batch<FMT, SA, SC, kNone>(d, n, mb, ragged, s);
+        case kVariant1: return run_batch<FMT, SA, SC, kVariant1>(d, n, mb, ragged, s);
+        case kVariant2: return run_batch<FMT, SA, SC, kVariant2>(d, n, mb, ragged, s);
+        case kVariant3: return run_batch<FMT, SA, SC, kVariant3>(d, n, mb, ragged, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 }  // namespace
+
+bool transform_batch_item_ok(const Settings& st, const TransformBatchItem& it, bool* ragged) {
+    const int ns = num_streams(st.format, st.split_alpha, st.split_colour);
+    if (reinterpret_cast<uintptr_t>(it.in) & 15) return false;
+    for (int s = 0; s < ns; s++) {
+        const int w = stream_width(st.format, st.split_alpha, st.split_colour, s);
+        if (reinterpret_cast<uintptr_t>(it.out.p[s]) & (uintptr_t)(stream_align(w) - 1)) return false;
+        *ragged |= ((reinterpret_cast<uintptr_t>(it.out.p[s]) | ((uint64_t)w * it.nblocks)) & 15) != 0;
+    }
+    return true;
+}
+
+cudaError_t launch_transform_batch(const Settings& st, const TransformBatchItem* d_items, int nitems, uint64_t max_blocks,
+                                   bool ragged, cudaStream_t stream) {
+    if (nitems <= 0 || max_blocks == 0) return cudaSuccess;
+    if (st.normalize != kNormNone) return cudaErrorInvalidValue;
+    const bool sc = st.split_colour, sa = st.split_alpha;
+    switch (st.format) {
+        case 1:
+            return sc ? run_batch_var<1, false, true>(st.variant, d_items, nitems, max_blocks, ragged, stream)
+                      : run_batch_var<1, false, false>(st.variant, d_items, nitems, max_blocks, ragged, stream);
+        case 2:
+            return sc ? run_batch_var<2, false, true>(st.variant, d_items, nitems, max_blocks, ragged, stream)
+                      : run_batch_var<2, false, false>(st.variant, d_items, nitems, max_blocks, ragged, stream);
+        case 3:
+            if (sa)
+                return sc ? run_batch_var<3, true, true>(st.variant, d_items, nitems, max_blocks, ragged, stream)
+                          : run_batch_var<3, true, false>(st.variant, d_items, nitems, max_blocks, ragged, stream);
+            return sc ? run_batch_var<3, false, true>(st.variant, d_items, nitems, max_blocks, ragged, stream)
+                      : run_batch_var<3, false, false>(st.variant, d_items, nitems, max_blocks, ragged, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
 
 cudaError_t launch_transform(const Settings& st, const uint8_t* in, const StreamPtrs& out, uint64_t nblocks,
                              cudaStream_t stream) {

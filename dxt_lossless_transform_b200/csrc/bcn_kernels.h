@@ -13,6 +13,18 @@ namespace dlt {
 cudaError_t launch_transform(const Settings& st, const uint8_t* in, const StreamPtrs& out, uint64_t nblocks,
                              cudaStream_t stream);
 
+// The same for MANY payloads that share one settings combination, in one launch (grid.y = payload).  `d_items` is a
+// DEVICE array; `max_blocks` the largest nblocks among them.  Every item must pass transform_batch_item_ok (16-byte
+// aligned blocks, naturally aligned streams — what the tiled kernels need); `ragged` is the OR it accumulates.
+struct TransformBatchItem {
+    const uint8_t* in;
+    StreamPtrs out;
+    uint64_t nblocks;
+};
+bool transform_batch_item_ok(const Settings& st, const TransformBatchItem& item, bool* ragged);
+cudaError_t launch_transform_batch(const Settings& st, const TransformBatchItem* d_items, int nitems, uint64_t max_blocks,
+                                   bool ragged, cudaStream_t stream);
+
 // Exact inverse: gathers the streams back into `nblocks` blocks at `out`.
 cudaError_t launch_untransform(const Settings& st, const StreamPtrs& in, uint8_t* out, uint64_t nblocks,
                                cudaStream_t stream);

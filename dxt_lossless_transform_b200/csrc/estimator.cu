@@ -918,9 +918,9 @@ constexpr size_t kSmallPositions = 4096;   // at or below: the single-launch ker
 // partitions: with many small segments the partitions alone fill the wave, and an unbounded piece length would make
 // the heaviest partition of a skewed stream (flat texture regions put most positions into one bucket) ONE thread's
 // sequential job.
-uint32_t choose_run_len(const LtuSegment* segs, const int* idx, int n) {
+uint32_t choose_run_len(const size_t* lens, int n) {
     size_t total = 0;
-    for (int i = 0; i < n; i++) total += ltu_positions(segs[idx[i]].len);
+    for (int i = 0; i < n; i++) total += ltu_positions(lens[i]);
     const size_t parts = (size_t)n * (kParts + 1);
     const size_t budget = kTargetPieces > parts + 4096 ? kTargetPieces - parts : 4096;
     size_t len = (total + budget - 1) / budget;
@@ -928,6 +928,12 @@ uint32_t choose_run_len(const LtuSegment* segs, const int* idx, int n) {
     if (len > cap) len = cap;
     len = (len + 31) / 32 * 32;
     return (uint32_t)(len < kMinRunLen ? kMinRunLen : len);
+}
+size_t set_bytes(const size_t* lens, int n) {
+    const uint32_t run_len = choose_run_len(lens, n);
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += plan_segment(lens[i], run_len).bytes();
+    return total;
 }
 
 // The launch sets of a call: large segments in input order, kMaxSegs at a time, each set with its own piece length.
@@ -942,13 +948,28 @@ std::vector<LaunchSet> plan_sets(const LtuSegment* segs, int nseg) {
         if (sets.empty() || (int)sets.back().idx.size() == kMaxSegs) sets.emplace_back();
         sets.back().idx.push_back(i);
     }
-    for (LaunchSet& st : sets) st.run_len = choose_run_len(segs, st.idx.data(), (int)st.idx.size());
+    for (LaunchSet& st : sets) {
+        size_t lens[kMaxSegs];
+        for (size_t i = 0; i < st.idx.size(); i++) lens[i] = segs[st.idx[i]].len;
+        st.run_len = choose_run_len(lens, (int)st.idx.size());
+    }
     return sets;
 }
 
 }  // namespace
 
 uint64_t estimator_launch_count() { return g_est_launches.load(std::memory_order_relaxed); }
+
+void LtuScratchMeter::add(size_t len) {
+    static_assert(kSet == kMaxSegs, "LtuScratchMeter mirrors the launch-set size");
+    nseg_++;
+    if (ltu_positions(len) <= kSmallPositions) return;
+    open_len_[open_++] = len;
+    if (open_ == kSet) closed_bytes_ += set_bytes(open_len_, open_), open_ = 0;
+}
+size_t LtuScratchMeter::bytes() const {
+    return align_up((nseg_ > 0 ? nseg_ : 1) * sizeof(uint64_t), 256) + closed_bytes_ + (open_ ? set_bytes(open_len_, open_) : 0);
+}
 
 inline size_t result_bytes(int nseg) { return align_up((size_t)(nseg > 0 ? nseg : 1) * sizeof(uint64_t), 256); }
 

@@ -30,6 +30,20 @@ struct LtuSegment {
 // Device scratch the call below needs for these segments (sort buffers: ~8.2 bytes per position).
 size_t ltu_scratch_bytes(const LtuSegment* segs, int nseg);
 
+// The same figure kept incrementally while a caller appends segments (launch sets are formed in input order, so
+// appending a segment only changes the last, still open set): O(1) per segment instead of re-planning all of them.
+// bytes() == ltu_scratch_bytes() of the segments added so far.  Cheap to copy (try a job, keep or drop the copy).
+class LtuScratchMeter {
+public:
+    void add(size_t len);
+    size_t bytes() const;
+
+private:
+    static constexpr int kSet = 64;   // == kMaxSegs of estimator.cu (static_assert there)
+    size_t nseg_ = 0, closed_bytes_ = 0, open_len_[kSet] = {};
+    int open_ = 0;
+};
+
 // Number of LZ matches of each device-resident segment, written to host `matches[0..nseg)`.
 // `scratch` is device memory of at least ltu_scratch_bytes().  Synchronises `stream` before returning.
 Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, cudaStream_t stream, uint8_t* scratch,
