@@ -675,8 +675,12 @@ __global__ void __launch_bounds__(32, kRunsWarpsPerSm) ltu_runs_kernel(const Sor
         start = max(part_start, slot * L);
         end = min(part_end, (slot + 1) * L);
     }
+    // A piece that starts its partition knows its in-state: every bucket still holds 0 (the reference's table is
+    // zero-initialised), so nothing is parked for the resolve pass.  With many small segments (a directory of
+    // textures) every piece is such a piece.
+    const uint32_t initial = (g < total && start == part_start) ? 0u : kUnknown;
 #pragma unroll 8
-    for (int c = 0; c < kClasses; c++) table[c * 32 + lane] = kUnknown;
+    for (int c = 0; c < kClasses; c++) table[c * 32 + lane] = initial;
 
     const uint32_t* rec = b.rec[seg];
     uint32_t* dk = b.dkey[seg] + (size_t)g * 4 * kClasses;
