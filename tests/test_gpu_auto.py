@@ -244,6 +244,25 @@ def test_auto_batch_equals_single_calls(dlt, use_all):
         dlt.transform_auto_batch([(1, np.zeros(12, np.uint8), np.zeros(12, np.uint8))])
 
 
+def test_auto_batch_rounds_overlap_without_mixing_payloads(dlt):
+    """A batch large enough for several upload / search / download rounds (two device slots reused round after
+    round): every payload still gets the oracle's choice and bytes."""
+    from dxt_lossless_transform_b200 import synth
+
+    items = []
+    for i in range(11):
+        fmt = 1 if i % 2 == 0 else 3
+        nb = (4 << 20) // (8 if fmt == 1 else 16) + (3 if i % 3 == 0 else 0)   # some odd block counts
+        data = synth.texture_blocks(fmt, nb, seed=100 + i, smooth=[0.2, 1.0, 5.0][i % 3])
+        items.append((fmt, data, np.zeros_like(data)))
+    best = dlt.transform_auto_batch(items, False)
+    for i, ((fmt, data, out), b) in enumerate(zip(items, best)):
+        want_out, want = oracle.auto(fmt, data, False)
+        got = (int(b.decorrelation_mode), bool(getattr(b, "split_alpha_endpoints", False)), bool(b.split_colour_endpoints))
+        assert got == want, (i, fmt)
+        assert np.array_equal(out, want_out), (i, fmt)
+
+
 def test_dds_batch_with_auto_bundle_shares_one_search(dlt):
     """DdsHandler.transform_bundle_batch with auto builders + the LTU estimator: per-file results equal the single-file
     calls (which equal the oracle), through the batched search."""

@@ -116,7 +116,7 @@ def test_misaligned_host_buffers(dlt, fmt):
 
 @pytest.mark.parametrize("fmt", [1, 2, 3])
 def test_multi_chunk_host_pipeline_pageable_and_pinned(dlt, fmt):
-    """> 3 chunks of 8 MiB so the staging ring wraps; ragged last chunk; pinned and pageable buffers."""
+    """Several chunks for pageable buffers (16 MiB staging slots), ragged last chunk; pinned and pageable buffers."""
     nb = (28 << 20) // bpb(fmt) + 12345
     data = rand_blocks(fmt, nb, 11)
     s = settings_list(dlt, fmt)[0]
@@ -134,6 +134,46 @@ def test_multi_chunk_host_pipeline_pageable_and_pinned(dlt, fmt):
     dlt.untransform_with_settings(fmt, out, back, s)
     assert np.array_equal(back, data)
     pin_in.free(), pin_out.free()
+
+
+_SMALL_CHUNK_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import dxt_lossless_transform_b200 as dlt
+import oracle
+for fmt, S in ((1, dlt.Bc1TransformSettings), (2, dlt.Bc2TransformSettings), (3, dlt.Bc3TransformSettings)):
+    bpb = 8 if fmt == 1 else 16
+    nb = (13 << 20) // bpb + 4321          # 13 MiB and a bit: 13+ chunks of 1 MiB, odd block count
+    rng = np.random.default_rng(fmt)
+    data = rng.integers(0, 256, nb * bpb, dtype=np.uint8)
+    s = S()
+    args = (int(s.decorrelation_mode), bool(getattr(s, "split_alpha_endpoints", False)), bool(s.split_colour_endpoints))
+    expect = oracle.transform(fmt, data, *args, threads=8)
+    pin_in, pin_out = dlt.alloc_pinned(data.size), dlt.alloc_pinned(data.size)
+    for src, dst in ((data, np.zeros_like(data)), (pin_in.array, pin_out.array)):
+        src[:] = data
+        dlt.transform_with_settings(fmt, src, dst, s)
+        assert np.array_equal(dst, expect), (fmt, "transform")
+        src[:] = 0
+        dlt.untransform_with_settings(fmt, dst, src, s)
+        assert np.array_equal(src, data), (fmt, "untransform")
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("ramp", ["0", "1"])
+def test_host_pipeline_with_many_small_chunks(ramp):
+    """The copy pipeline's chunk schedule (ring of slots wrapping many times, short-chunk ramp at both ends, ragged
+    last chunk) — forced by 1 MiB chunks in a child process, because the host-path configuration is read once."""
+    import os
+    import subprocess
+    import sys
+
+    root = str(Path(__file__).resolve().parent.parent)
+    env = dict(os.environ, DLTCUDA_CHUNK_MIB="1", DLTCUDA_RAMP=ramp)
+    r = subprocess.run([sys.executable, "-c", _SMALL_CHUNK_SCRIPT, root], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
 
 
 def test_stable_builders_roundtrip(dlt):
