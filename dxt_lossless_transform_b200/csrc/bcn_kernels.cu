@@ -200,6 +200,84 @@ __device__ __forceinline__ int normalize_bc1_block(uint32_t& c01, uint32_t& idx,
     return 2;   // mode None: the reference writes the source block back
 }
 
+// ---- the same decision for EIGHT blocks per lane, warp-cooperative -----------------------------------------------
+// A block painted entirely with an interpolated palette entry (c0 != c1, all indices 2 or 3) needs ~90 instructions of
+// arithmetic; encoders that store flat areas through their single-colour tables (stb_dxt and friends) produce exactly
+// that, so it is a common block in textures with flat regions.  Taken lane by lane under a branch, every one of a lane's
+// eight blocks that needs it stalls the other 31 lanes (ncu on adversarial data: 10.3 of 32 lanes active per
+// instruction).  Here the fast cases are decided inline and the (colours, entry) pairs of the slow blocks of the whole
+// warp are compacted into a shared-memory queue (ballot + popc ranks); then ALL lanes work the queue 32 entries at a
+// time and the results go back by the same ranks.  Used by the stand-alone normalization pass (3.6 instead of 2.35 TB/s
+// on adversarial data, and faster on ordinary data too).  The fused transform keeps the per-block branch: with the
+// queue it lost 7 % on ordinary data (6.1 instead of 6.6 TB/s) for +22 % on randomly scattered slow blocks, and real flat
+// regions are spatially coherent, so whole warps take the branch together.
+// Result word: BlockCase in bits 0-1 (0 unchanged, 1 transparent, 2 solid colour), the RGB565 colour in bits 16-31.
+constexpr uint32_t kNeedsEntry = 3u;
+__device__ __forceinline__ uint32_t classify_bc1_block(uint32_t c01, uint32_t idx) {
+    const uint32_t c0 = c01 & 0xFFFFu, c1 = c01 >> 16;
+    if (c0 == c1) {
+        const uint32_t threes = idx & (idx >> 1) & 0x55555555u;
+        if (threes != 0) return threes == 0x55555555u ? 1u : 0u;
+        return 2u | (c0 << 16);
+    }
+    const uint32_t sel = idx & 3u;
+    if (idx != sel * 0x55555555u) return 0u;
+    if (sel < 2) return 2u | ((sel ? c1 : c0) << 16);
+    return kNeedsEntry;
+}
+__device__ __forceinline__ uint32_t classify_interpolated(uint32_t c01, uint32_t sel) {
+    const uint32_t c0 = c01 & 0xFFFFu, c1 = c01 >> 16;
+    const uint32_t e0 = expand565(c0), e1 = expand565(c1);
+    uint32_t px;
+    if (c0 > c1) px = (sel == 2 ? mix3(e0, e1, 2, 1, 3) : mix3(e0, e1, 1, 2, 3)) | 0xFF000000u;
+    else px = sel == 2 ? (mix3(e0, e1, 1, 1, 2) | 0xFF000000u) : 0u;
+    if ((px >> 24) == 0) return 1u;
+    const uint32_t r = px & 0xFFu, g = (px >> 8) & 0xFFu, b = (px >> 16) & 0xFFu;
+    const uint32_t c565 = ((r & 0xF8u) << 8) | ((g & 0xFCu) << 3) | (b >> 3);
+    return (expand565(c565) | 0xFF000000u) != px ? 0u : (2u | (c565 << 16));
+}
+__device__ __forceinline__ void apply_normalization(uint32_t& c01, uint32_t& idx, const uint32_t res, const int mode) {
+    const uint32_t bcase = res & 3u, c565 = res >> 16;
+    if (bcase == 1) c01 = idx = 0xFFFFFFFFu;
+    else if (bcase == 2 && mode == kNormColor0Only) c01 = c565, idx = 0;
+    else if (bcase == 2 && mode == kNormReplicateColor) c01 = c565 | (c565 << 16), idx = 0;
+}
+constexpr int kNormQueueEntries = 8 * 32;   // per warp: eight blocks per lane
+// ALL 32 lanes of the warp must call this.  `queue` = this warp's kNormQueueEntries entries of shared memory.
+__device__ __forceinline__ void classify8_warp(const uint4 (&v)[kUnroll], uint32_t (&res)[2 * kUnroll], uint2* queue) {
+    static_assert(kUnroll == 4, "eight BC1 blocks per lane");
+    bool any_slow = false;
+#pragma unroll
+    for (int s = 0; s < 2 * kUnroll; s++) {
+        res[s] = classify_bc1_block((s & 1) ? v[s >> 1].z : v[s >> 1].x, (s & 1) ? v[s >> 1].w : v[s >> 1].y);
+        any_slow |= res[s] == kNeedsEntry;
+    }
+    if (!__any_sync(0xFFFFFFFFu, any_slow)) return;   // the common case costs one vote
+    const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    unsigned queued = 0;
+#pragma unroll
+    for (int s = 0; s < 2 * kUnroll; s++) {
+        const bool slow = res[s] == kNeedsEntry;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, slow);
+        if (slow) queue[queued + __popc(m & below)] = make_uint2((s & 1) ? v[s >> 1].z : v[s >> 1].x, ((s & 1) ? v[s >> 1].w : v[s >> 1].y) & 3u);
+        queued += __popc(m);
+    }
+    __syncwarp();
+    for (unsigned i = lane; i < queued; i += 32) {
+        const uint2 q = queue[i];
+        queue[i].x = classify_interpolated(q.x, q.y);
+    }
+    __syncwarp();
+    queued = 0;
+#pragma unroll
+    for (int s = 0; s < 2 * kUnroll; s++) {
+        const bool slow = res[s] == kNeedsEntry;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, slow);
+        if (slow) res[s] = queue[queued + __popc(m & below)].x;
+        queued += __popc(m);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Compile-time view of one (format, split_alpha, split_colour) layout.
 // ------------------------------------------------------------------------------------------------
@@ -880,20 +958,24 @@ __global__ void __launch_bounds__(kThreads)
             asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v[u].x), "=r"(v[u].y) : "l"(in + 16 * j) : "memory");
         }
     }
+    __shared__ uint2 queue[kNormQueueEntries * (kThreads / 32)];
+    uint32_t res[2 * kUnroll];
+    classify8_warp(v, res, queue + (threadIdx.x >> 5) * kNormQueueEntries);   // blocks past the end are zeros: a fast case
     bool hit = false;
 #pragma unroll
     for (int u = 0; u < kUnroll; u++) {
         const uint64_t j = vec0 + (uint64_t)u * kThreads;
         if (2 * j >= nblocks) continue;
-        uint2 a[3], b[3];
-        hit |= normalize_all_modes(make_uint2(v[u].x, v[u].y), a);
         const bool two = 2 * j + 1 < nblocks;
-        if (two) hit |= normalize_all_modes(make_uint2(v[u].z, v[u].w), b);
+        hit |= (res[2 * u] & 3u) != 0 || (two && (res[2 * u + 1] & 3u) != 0);
 #pragma unroll
         for (int m = 0; m < 3; m++) {
             if (!outs.p[m]) continue;
-            if (two) stg_stream16(outs.p[m] + 16 * j, make_uint4(a[m].x, a[m].y, b[m].x, b[m].y));
-            else stg_stream8(outs.p[m] + 16 * j, a[m]);
+            uint4 o = v[u];
+            apply_normalization(o.x, o.y, res[2 * u], m);
+            apply_normalization(o.z, o.w, res[2 * u + 1], m);
+            if (two) stg_stream16(outs.p[m] + 16 * j, o);
+            else stg_stream8(outs.p[m] + 16 * j, make_uint2(o.x, o.y));
         }
     }
     if (any && __syncthreads_or(hit) && threadIdx.x == 0) atomicOr(any, 1u);
