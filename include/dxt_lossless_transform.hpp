@@ -8,6 +8,8 @@
 //   Bc{1,2}ManualTransformBuilder / Bc{1,2}AutoTransformBuilder
 //       api/dxt-lossless-transform-bc1-api/src/transform/{manual,auto}_transform_builder.rs
 //   LosslessTransformUtilsSizeEstimation      extensions/estimators/dxt-lossless-transform-ltu/src/lib.rs:49
+//   ZStandardSizeEstimation                   extensions/compressors/dxt-lossless-transform-zstd/src/lib.rs:54
+//   experimental::normalize_blocks            core/dxt-lossless-transform-bc1/src/experimental/normalize_blocks/
 // Link with -ldxt_lossless_transform_cuda.
 #pragma once
 #include <cstddef>
@@ -23,6 +25,7 @@
 #include "dxt_lossless_transform_bc3_core.h"
 #include "dxt_lossless_transform_cuda.h"
 #include "dxt_lossless_transform_ltu.h"
+#include "dxt_lossless_transform_zstd.h"
 
 namespace dxt_lossless_transform {
 
@@ -122,6 +125,37 @@ private:
     DltSizeEstimator* e_;
 };
 
+// ZStandardSizeEstimation (dxt-lossless-transform-zstd/src/lib.rs:54-140): real zstd sizes with the reference's
+// parameters; inside transform_bcN_auto the candidates are transformed on the GPU and compressed concurrently.
+struct InvalidLevel : std::invalid_argument {
+    explicit InvalidLevel(int level) : std::invalid_argument("Invalid compression level: " + std::to_string(level)) {}
+};
+class ZStandardSizeEstimation {
+public:
+    explicit ZStandardSizeEstimation(int compression_level) : e_(nullptr) {
+        if (compression_level < 1 || compression_level > 22) throw InvalidLevel(compression_level);   // lib.rs:62-66
+        e_ = dltzstd_new_size_estimator(compression_level);
+        if (!e_) throw std::runtime_error("no libzstd could be loaded (set DLTCUDA_LIBZSTD)");
+    }
+    static ZStandardSizeEstimation new_fast() { return ZStandardSizeEstimation(1); }
+    static ZStandardSizeEstimation new_default() { return ZStandardSizeEstimation(3); }
+    static ZStandardSizeEstimation new_best() { return ZStandardSizeEstimation(22); }
+    ~ZStandardSizeEstimation() { dltzstd_free_size_estimator(e_); }
+    ZStandardSizeEstimation(ZStandardSizeEstimation&& o) noexcept : e_(std::exchange(o.e_, nullptr)) {}
+    ZStandardSizeEstimation(const ZStandardSizeEstimation&) = delete;
+    ZStandardSizeEstimation& operator=(const ZStandardSizeEstimation&) = delete;
+    const DltSizeEstimator* c_estimator() const { return e_; }
+    size_t max_compressed_size(size_t len) const {
+        size_t out = 0;
+        if (e_->max_compressed_size(e_->context, len, &out) != 0) throw SizeEstimationError();
+        return out;
+    }
+    static unsigned library_version() { return dltzstd_version_number(); }
+
+private:
+    DltSizeEstimator* e_;
+};
+
 // ---- transform_bcN_auto ------------------------------------------------------------------------------
 inline Bc1TransformSettings transform_bc1_auto(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len,
                                                const DltSizeEstimator* estimator, bool use_all_decorrelation_modes = false) {
@@ -144,6 +178,45 @@ inline Bc3TransformSettings transform_bc3_auto(const uint8_t* in, size_t in_len,
                        in_len, out_len);
     return {static_cast<YCoCgVariant>(d.decorrelation_mode), d.split_alpha_endpoints, d.split_colour_endpoints};
 }
+
+// ---- experimental::normalize_blocks (BC1) ----------------------------------------------------------------
+namespace experimental {
+enum class ColorNormalizationMode : int { None = 0, Color0Only = 1, ReplicateColor = 2 };   // normalize.rs:487-500
+struct Bc1TransformDetailsWithNormalization {   // normalize_blocks/mod.rs:98-111
+    ColorNormalizationMode color_normalization_mode = ColorNormalizationMode::None;
+    YCoCgVariant decorrelation_mode = YCoCgVariant::Variant1;
+    bool split_colour_endpoints = true;
+};
+inline void check_len(size_t in_len, size_t out_len) {
+    if (in_len % 8) throw InvalidLength(in_len);
+    if (out_len < in_len) throw OutputBufferTooSmall(in_len, out_len);
+}
+// normalize_blocks (normalize.rs:38); `out` may be `in`.
+inline void normalize_blocks(const uint8_t* in, uint8_t* out, size_t len, ColorNormalizationMode mode) {
+    check_len(len, len);
+    if (const int rc = dltcuda_bc1_normalize_blocks(in, out, len, static_cast<int>(mode))) throw DeviceError(rc);
+}
+// transform_bc1_with_normalize_blocks (transform.rs:65): one fused pass on the GPU.
+inline void transform_bc1_with_normalize_blocks(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len,
+                                                Bc1TransformDetailsWithNormalization d = {}) {
+    check_len(in_len, out_len);
+    if (const int rc = dltcuda_bc1_transform_with_normalize_blocks(in, out, in_len, static_cast<int>(d.color_normalization_mode),
+                                                                   static_cast<DltCoreYCoCgVariant>(d.decorrelation_mode),
+                                                                   d.split_colour_endpoints))
+        throw DeviceError(rc);
+}
+// transform_bc1_auto_with_normalization (transform.rs:222) with the LTU-semantics estimator on the GPU.
+inline Bc1TransformDetailsWithNormalization transform_bc1_auto_with_normalization(const uint8_t* in, size_t in_len, uint8_t* out,
+                                                                                  size_t out_len, bool use_all_decorrelation_modes = false) {
+    check_len(in_len, out_len);
+    int norm = 0;
+    DltCoreYCoCgVariant var{};
+    bool split = false;
+    if (const int rc = dltcuda_bc1_transform_auto_with_normalization(in, out, in_len, use_all_decorrelation_modes, &norm, &var, &split, nullptr))
+        throw DeviceError(rc);
+    return {static_cast<ColorNormalizationMode>(norm), static_cast<YCoCgVariant>(var), split};
+}
+}  // namespace experimental
 
 // ---- page-locked buffers (full host-link speed for the host-pointer entry points) -----------------
 class PinnedBuffer {

@@ -264,8 +264,13 @@ int main() {
     ok += d.decorrelation_mode == dlt::YCoCgVariant::Variant1 && d.split_alpha_endpoints && d.split_colour_endpoints;
     dlt::LosslessTransformUtilsSizeEstimation ltu;
     ok += ltu.estimate_compressed_size(nullptr, 0) == 0;
+    try { dlt::ZStandardSizeEstimation z(23); } catch (const dlt::InvalidLevel&) { ok += 1; }
+    try { dlt::experimental::transform_bc1_with_normalize_blocks(in.data(), 12, out.data(), 64); } catch (const dlt::InvalidLength& e) { ok += e.length == 12; }
+    try { dlt::experimental::transform_bc1_auto_with_normalization(in.data(), 64, out.data(), 8); } catch (const dlt::OutputBufferTooSmall& e) { ok += e.needed == 64; }
+    dlt::experimental::Bc1TransformDetailsWithNormalization nd;
+    ok += nd.color_normalization_mode == dlt::experimental::ColorNormalizationMode::None && nd.split_colour_endpoints;
     std::printf("%d\n", ok);
-    return ok == 5 ? 0 : 1;
+    return ok == 9 ? 0 : 1;
 }
 ''')
     exe = tmp_path / "host"
