@@ -69,6 +69,21 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
+// -DDLT_BULK_STORE=1: the RAGGED transform writes every stream segment with one TMA bulk copy (cp.async.bulk
+// shared -> global, UBLKCP) instead of a 128-bit store loop.  Bit-exact (parity + property tests) and 8 % fewer
+// instructions, but no consistent gain at 1 GiB - 3 blocks: BC1 6.69-6.84 -> 6.71-6.78 TB/s, BC2 6.34-6.73 -> 6.66-6.70,
+// BC3 5.11-6.08 -> 5.34-6.66 (one setting +15 %, one -3 %); ncu shows the ragged kernel waiting on its loads (long
+// scoreboard 14 vs 10.7 per issue in the aligned kernel at identical DRAM bytes), not on the store loop.  Off by default.
+#ifndef DLT_BULK_STORE
+#define DLT_BULK_STORE 0
+#endif
+__device__ __forceinline__ void bulk_store(void* gmem, const void* smem, uint32_t bytes) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() {
+    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void stg_stream8(void* p, const uint2& v) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
@@ -431,6 +446,9 @@ __device__ __forceinline__ void transform_tile(const uint8_t* __restrict__ in, c
         const int b0 = (kUnroll * kThreads + tid) * L::BPV;
         if (halo_lane && b0 < nbs) stage_vector<FMT, SA, SC, VAR, NORM, L>(stage, sh, b0, nbs, vh);
     }
+#if DLT_BULK_STORE
+    if (RAGGED) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy reads
+#endif
     __syncthreads();
 
     // ---- phase 3: stream every segment out as 128-bit vectors.  Coordinates are relative to `gal`, the 128-byte
@@ -449,12 +467,22 @@ __device__ __forceinline__ void transform_tile(const uint8_t* __restrict__ in, c
         } else {
             vec_lo = lo_valid, vec_hi = hi_valid;
         }
+#if DLT_BULK_STORE
+        // One bulk copy (TMA engine, shared -> global) per stream segment instead of a 128-bit store loop through every
+        // thread: thread s issues segment s.  Source and destination are 16-byte aligned (the staging shift keeps them
+        // congruent mod 128), the size is a multiple of 16.
+        if (RAGGED && tid == s && vec_hi > vec_lo) bulk_store(gal + vec_lo, reg + vec_lo, (uint32_t)(vec_hi - vec_lo));
+        if (RAGGED) continue;
+#endif
 #pragma unroll
         for (int it = 0; it < L::iters(s); it++) {
             const int lo = (it * kThreads + tid) << 4;
             if (lo >= vec_lo && lo + 16 <= vec_hi) stg_stream16(gal + lo, lds<uint4>(reg + lo));
         }
     }
+#if DLT_BULK_STORE
+    if (RAGGED && tid < L::NS) bulk_store_wait();   // the staging area must outlive the engine's reads
+#endif
     // ... and, in the first / last tile of the launch's range only, the bytes outside whole sectors (< 32 each):
     // the range may be a shard, so nothing beyond it is touched.  Warp 0, one lane per byte.
     if constexpr (RAGGED) {
