@@ -653,7 +653,10 @@ __device__ __forceinline__ void ldg_nc32(const void* p, uint4& a, uint4& b) {   
 // Every piece-thread streams its own piece: tens of thousands of concurrent 128-byte reads at unrelated addresses
 // (DRAM row misses).  Each thread therefore pulls the next kPrefetchRecords of its piece into L2 with ONE bulk
 // prefetch, so DRAM sees kilobyte-sized contiguous reads and the record loads hit L2.
-constexpr uint32_t kPrefetchRecords = 512;   // 2 KiB
+#ifndef DLT_PREFETCH_RECORDS
+#define DLT_PREFETCH_RECORDS 512
+#endif
+constexpr uint32_t kPrefetchRecords = DLT_PREFETCH_RECORDS;   // 512 records = 2 KiB
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
