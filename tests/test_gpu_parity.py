@@ -439,3 +439,35 @@ def test_concurrent_host_threads(dlt):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_repeated_calls_do_not_leak(dlt, torch):
+    """Contexts, staging buffers and scratch are pooled: thousands of calls through every kind of entry point must leave
+    device memory and host RSS where they were after the first few hundred."""
+    import psutil
+
+    from dxt_lossless_transform_b200 import synth
+
+    data1, data3 = synth.texture_blocks(1, 9001, seed=1), synth.texture_blocks(3, 4097, seed=3)
+    out1, out3 = np.zeros_like(data1), np.zeros_like(data3)
+    est = dlt.Bc1EstimateSettings(dlt.LosslessTransformUtilsSizeEstimation(), False)
+    cb = dlt.Bc1EstimateSettings(dlt.CallbackSizeEstimator(lambda a: int(a[::7].sum())), False)
+
+    def burst(n):
+        for i in range(n):
+            dlt.transform_bc1_with_settings(data1, out1, dlt.Bc1TransformSettings())
+            dlt.untransform_bc3_with_settings(data3, out3, dlt.Bc3TransformSettings())
+            if i % 4 == 0:
+                dlt.transform_bc1_auto(data1, out1, est)
+                dlt.transform_bc3_auto(data3, out3, cb)
+                dlt.transform_auto_batch([(1, data1, out1), (3, data3, out3)], False)
+                dlt.transform_batch([(1, data1, out1, dlt.Bc1TransformSettings())])
+
+    burst(200)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    rss0 = psutil.Process().memory_info().rss
+    burst(1500)
+    torch.cuda.synchronize()
+    assert free0 - torch.cuda.mem_get_info()[0] < (8 << 20)
+    assert psutil.Process().memory_info().rss - rss0 < (64 << 20)
