@@ -121,7 +121,7 @@ Status create_context(int device, Context** out) {
 
 const HostPathConfig& host_path_config() {
     static const HostPathConfig cfg = [] {
-        HostPathConfig c{kChunkBytes, kStages, true, (size_t)4 << 20, true};
+        HostPathConfig c{kChunkBytes, kStages, true, (size_t)4 << 20, true, true};
         if (const char* v = std::getenv("DLTCUDA_CHUNK_MIB")) {
             const long mib = std::atol(v);
             if (mib >= 1 && (size_t)mib << 20 <= kChunkBytes) c.chunk_bytes = (size_t)mib << 20;
@@ -132,6 +132,7 @@ const HostPathConfig& host_path_config() {
         }
         if (const char* v = std::getenv("DLTCUDA_ZEROCOPY")) c.zero_copy = std::atol(v) != 0;
         if (const char* v = std::getenv("DLTCUDA_RAMP")) c.ramp = std::atol(v) != 0;
+        if (const char* v = std::getenv("DLTCUDA_STRIDED")) c.strided = std::atol(v) != 0;
         if (const char* v = std::getenv("DLTCUDA_ZEROCOPY_MAX_KIB")) {
             const long kib = std::atol(v);
             if (kib >= 0) c.zero_copy_max_bytes = (size_t)kib << 10;
@@ -364,6 +365,18 @@ public:
         // same stream inside a chunk (streams 256-byte aligned: chunk_blocks is a tile multiple).
         auto host_off = [&](int k, size_t b) { return n * (size_t)pre[k] + (size_t)w[k] * b; };
         auto slot_off = [&](int k) { return chunk_blocks * (size_t)pre[k]; };
+        // Consecutive streams of equal width (c0|c1, a0|a1, colours|indices) sit one pitch apart on both sides — N*w in
+        // the payload, chunk_blocks*w in the slot — so a run of them is ONE strided copy with a row per stream; every
+        // copy costs the copy engine 10-30 us of turnaround, whatever its size.  (2D copies need pitch < 2 GiB.)
+        int run_of[kMaxStreams];
+        for (int k = 0; k < ns;) {
+            int r = 1;
+            while (cfg_.strided && k + r < ns && w[k + r] == w[k] && pre[k + r] == pre[k] + r * w[k] &&
+                   n * (size_t)w[k] < ((size_t)1 << 31))
+                r++;
+            run_of[k] = r;
+            k += r;
+        }
 
         for (const auto& chunk : chunks) {
             const int slot = (int)(seq_++ % cfg_.stages);
@@ -384,19 +397,33 @@ public:
                 }
                 DLT_CUDA(cudaMemcpyAsync(slots_.blocks[slot], src, nb * bpb, cudaMemcpyHostToDevice, s));
                 DLT_CUDA(launch_transform(st, slots_.blocks[slot], sp, nb, s));
-                for (int k = 0; k < ns; k++) {
-                    uint8_t* dst = out_pinned ? job.out + host_off(k, b0) : ctx_->h_out[slot] + slot_off(k);
-                    DLT_CUDA(cudaMemcpyAsync(dst, sp.p[k], (size_t)w[k] * nb, cudaMemcpyDeviceToHost, s));
-                    if (!out_pinned) pend.copy[pend.ncopy++] = {job.out + host_off(k, b0), dst, (size_t)w[k] * nb};
+                for (int k = 0; k < ns; k += run_of[k]) {
+                    if (out_pinned && run_of[k] > 1) {   // equal-width neighbours: one strided copy (rows = streams)
+                        DLT_CUDA(cudaMemcpy2DAsync(job.out + host_off(k, b0), n * (size_t)w[k], sp.p[k], chunk_blocks * (size_t)w[k],
+                                                   (size_t)w[k] * nb, (size_t)run_of[k], cudaMemcpyDeviceToHost, s));
+                        continue;
+                    }
+                    for (int j = k; j < k + run_of[k]; j++) {
+                        uint8_t* dst = out_pinned ? job.out + host_off(j, b0) : ctx_->h_out[slot] + slot_off(j);
+                        DLT_CUDA(cudaMemcpyAsync(dst, sp.p[j], (size_t)w[j] * nb, cudaMemcpyDeviceToHost, s));
+                        if (!out_pinned) pend.copy[pend.ncopy++] = {job.out + host_off(j, b0), dst, (size_t)w[j] * nb};
+                    }
                 }
             } else {
-                for (int k = 0; k < ns; k++) {
-                    const uint8_t* src = job.in + host_off(k, b0);
-                    if (!in_pinned) {
-                        staged_copy(ctx_->h_in[slot] + slot_off(k), src, (size_t)w[k] * nb);
-                        src = ctx_->h_in[slot] + slot_off(k);
+                for (int k = 0; k < ns; k += run_of[k]) {
+                    if (in_pinned && run_of[k] > 1) {
+                        DLT_CUDA(cudaMemcpy2DAsync(sp.p[k], chunk_blocks * (size_t)w[k], job.in + host_off(k, b0), n * (size_t)w[k],
+                                                   (size_t)w[k] * nb, (size_t)run_of[k], cudaMemcpyHostToDevice, s));
+                        continue;
                     }
-                    DLT_CUDA(cudaMemcpyAsync(sp.p[k], src, (size_t)w[k] * nb, cudaMemcpyHostToDevice, s));
+                    for (int j = k; j < k + run_of[k]; j++) {
+                        const uint8_t* src = job.in + host_off(j, b0);
+                        if (!in_pinned) {
+                            staged_copy(ctx_->h_in[slot] + slot_off(j), src, (size_t)w[j] * nb);
+                            src = ctx_->h_in[slot] + slot_off(j);
+                        }
+                        DLT_CUDA(cudaMemcpyAsync(sp.p[j], src, (size_t)w[j] * nb, cudaMemcpyHostToDevice, s));
+                    }
                 }
                 DLT_CUDA(launch_untransform(st, sp, slots_.blocks[slot], nb, s));
                 uint8_t* dst = out_pinned ? job.out + b0 * bpb : ctx_->h_out[slot];

@@ -31,6 +31,7 @@ constexpr size_t kStagedChunkBytes = 16u << 20; // chunk when caller memory is p
 //   DLTCUDA_ZEROCOPY_MAX_KIB  largest payload that takes the zero-copy path (default 4096)
 //   DLTCUDA_RAMP       1 (default): a large payload starts and ends with short chunks (1/8, 1/4, 1/2) so the
 //                      un-overlapped first upload / last download are short; 0: equal chunks
+//   DLTCUDA_STRIDED    1 (default): neighbouring streams of equal width travel as one strided (2D) copy; 0: one copy each
 //   DLTCUDA_COPY_THREADS      threads used for staging copies of pageable caller memory
 struct HostPathConfig {
     size_t chunk_bytes;
@@ -38,6 +39,7 @@ struct HostPathConfig {
     bool zero_copy;
     size_t zero_copy_max_bytes;
     bool ramp;
+    bool strided;
 };
 const HostPathConfig& host_path_config();
 

@@ -162,16 +162,17 @@ print("ok")
 """
 
 
-@pytest.mark.parametrize("ramp", ["0", "1"])
-def test_host_pipeline_with_many_small_chunks(ramp):
+@pytest.mark.parametrize("ramp,strided", [("0", "1"), ("1", "1"), ("1", "0")])
+def test_host_pipeline_with_many_small_chunks(ramp, strided):
     """The copy pipeline's chunk schedule (ring of slots wrapping many times, short-chunk ramp at both ends, ragged
-    last chunk) — forced by 1 MiB chunks in a child process, because the host-path configuration is read once."""
+    last chunk, strided copies of equal-width neighbouring streams) — forced by 1 MiB chunks in a child process, because
+    the host-path configuration is read once."""
     import os
     import subprocess
     import sys
 
     root = str(Path(__file__).resolve().parent.parent)
-    env = dict(os.environ, DLTCUDA_CHUNK_MIB="1", DLTCUDA_RAMP=ramp)
+    env = dict(os.environ, DLTCUDA_CHUNK_MIB="1", DLTCUDA_RAMP=ramp, DLTCUDA_STRIDED=strided)
     r = subprocess.run([sys.executable, "-c", _SMALL_CHUNK_SCRIPT, root], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
 
