@@ -529,8 +529,7 @@ __global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS) transform_tiled_batch(
 // Tiled untransform kernel
 // ------------------------------------------------------------------------------------------------
 template <int FMT, bool SA, bool SC, int VAR>
-__global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
-    untransform_tiled(const StreamPtrs in, uint8_t* __restrict__ out, const uint64_t nblocks) {
+__device__ __forceinline__ void untransform_tile(const StreamPtrs& in, uint8_t* __restrict__ out, const uint64_t nblocks) {
     using L = Lay<FMT, SA, SC>;
     __shared__ __align__(16) uint8_t stage[L::kStageBytes];
 
@@ -631,6 +630,21 @@ __global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
             stg_stream16(tout + (size_t)j * 16, r);
         }
     }
+}
+
+
+template <int FMT, bool SA, bool SC, int VAR>
+__global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS)
+    untransform_tiled(const StreamPtrs in, uint8_t* __restrict__ out, const uint64_t nblocks) {
+    untransform_tile<FMT, SA, SC, VAR>(in, out, nblocks);
+}
+// Many payloads with the same settings in one launch (see transform_tiled_batch).
+template <int FMT, bool SA, bool SC, int VAR>
+__global__ void __launch_bounds__(kThreads, DLT_MIN_CTAS) untransform_tiled_batch(const UntransformBatchItem* __restrict__ items) {
+    const UntransformBatchItem it = items[blockIdx.y];
+    using L = Lay<FMT, SA, SC>;
+    if ((uint64_t)blockIdx.x * L::T >= it.nblocks) return;
+    untransform_tile<FMT, SA, SC, VAR>(it.in, it.out, it.nblocks);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -840,23 +854,45 @@ cudaError_t dispatch(const Settings& st, bool inverse, const uint8_t* bi, uint8_
 }
 
 template <int FMT, bool SA, bool SC, int VAR>
-cudaError_t run_batch(const TransformBatchItem* d_items, int nitems, uint64_t max_blocks, bool ragged, cudaStream_t stream) {
+cudaError_t run_batch(bool inverse, const void* d_items, int nitems, uint64_t max_blocks, bool ragged, cudaStream_t stream) {
     using L = Lay<FMT, SA, SC>;
     const uint64_t tiles = (max_blocks + L::T - 1) / L::T;
     if (tiles > 0x7fffffffull || nitems > 65535) return cudaErrorInvalidValue;
     const dim3 grid((unsigned)tiles, (unsigned)nitems);
-    if (ragged) transform_tiled_batch<FMT, SA, SC, VAR, true><<<grid, kThreads, 0, stream>>>(d_items);
-    else transform_tiled_batch<FMT, SA, SC, VAR, false><<<grid, kThreads, 0, stream>>>(d_items);
+    if (inverse) untransform_tiled_batch<FMT, SA, SC, VAR><<<grid, kThreads, 0, stream>>>(static_cast<const UntransformBatchItem*>(d_items));
+    else if (ragged) transform_tiled_batch<FMT, SA, SC, VAR, true><<<grid, kThreads, 0, stream>>>(static_cast<const TransformBatchItem*>(d_items));
+    else transform_tiled_batch<FMT, SA, SC, VAR, false><<<grid, kThreads, 0, stream>>>(static_cast<const TransformBatchItem*>(d_items));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 template <int FMT, bool SA, bool SC>
-cudaError_t run_batch_var(int var, const TransformBatchItem* d, int n, uint64_t mb, bool ragged, cudaStream_t s) {
+cudaError_t run_batch_var(int var, bool inverse, const void* d, int n, uint64_t mb, bool ragged, cudaStream_t s) {
     switch (var) {
-        case kNone: return run_batch<FMT, SA, SC, kNone>(d, n, mb, ragged, s);
-        case kVariant1: return run_batch<FMT, SA, SC, kVariant1>(d, n, mb, ragged, s);
-        case kVariant2: return run_batch<FMT, SA, SC, kVariant2>(d, n, mb, ragged, s);
-        case kVariant3: return run_batch<FMT, SA, SC, kVariant3>(d, n, mb, ragged, s);
+        case kNone: return run_batch<FMT, SA, SC, kNone>(inverse, d, n, mb, ragged, s);
+        case kVariant1: return run_batch<FMT, SA, SC, kVariant1>(inverse, d, n, mb, ragged, s);
+        case kVariant2: return run_batch<FMT, SA, SC, kVariant2>(inverse, d, n, mb, ragged, s);
+        case kVariant3: return run_batch<FMT, SA, SC, kVariant3>(inverse, d, n, mb, ragged, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+cudaError_t dispatch_batch(const Settings& st, bool inverse, const void* d_items, int nitems, uint64_t max_blocks, bool ragged,
+                           cudaStream_t stream) {
+    if (nitems <= 0 || max_blocks == 0) return cudaSuccess;
+    if (st.normalize != kNormNone) return cudaErrorInvalidValue;
+    const bool sc = st.split_colour, sa = st.split_alpha;
+    switch (st.format) {
+        case 1:
+            return sc ? run_batch_var<1, false, true>(st.variant, inverse, d_items, nitems, max_blocks, ragged, stream)
+                      : run_batch_var<1, false, false>(st.variant, inverse, d_items, nitems, max_blocks, ragged, stream);
+        case 2:
+            return sc ? run_batch_var<2, false, true>(st.variant, inverse, d_items, nitems, max_blocks, ragged, stream)
+                      : run_batch_var<2, false, false>(st.variant, inverse, d_items, nitems, max_blocks, ragged, stream);
+        case 3:
+            if (sa)
+                return sc ? run_batch_var<3, true, true>(st.variant, inverse, d_items, nitems, max_blocks, ragged, stream)
+                          : run_batch_var<3, true, false>(st.variant, inverse, d_items, nitems, max_blocks, ragged, stream);
+            return sc ? run_batch_var<3, false, true>(st.variant, inverse, d_items, nitems, max_blocks, ragged, stream)
+                      : run_batch_var<3, false, false>(st.variant, inverse, d_items, nitems, max_blocks, ragged, stream);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -876,24 +912,17 @@ bool transform_batch_item_ok(const Settings& st, const TransformBatchItem& it, b
 
 cudaError_t launch_transform_batch(const Settings& st, const TransformBatchItem* d_items, int nitems, uint64_t max_blocks,
                                    bool ragged, cudaStream_t stream) {
-    if (nitems <= 0 || max_blocks == 0) return cudaSuccess;
-    if (st.normalize != kNormNone) return cudaErrorInvalidValue;
-    const bool sc = st.split_colour, sa = st.split_alpha;
-    switch (st.format) {
-        case 1:
-            return sc ? run_batch_var<1, false, true>(st.variant, d_items, nitems, max_blocks, ragged, stream)
-                      : run_batch_var<1, false, false>(st.variant, d_items, nitems, max_blocks, ragged, stream);
-        case 2:
-            return sc ? run_batch_var<2, false, true>(st.variant, d_items, nitems, max_blocks, ragged, stream)
-                      : run_batch_var<2, false, false>(st.variant, d_items, nitems, max_blocks, ragged, stream);
-        case 3:
-            if (sa)
-                return sc ? run_batch_var<3, true, true>(st.variant, d_items, nitems, max_blocks, ragged, stream)
-                          : run_batch_var<3, true, false>(st.variant, d_items, nitems, max_blocks, ragged, stream);
-            return sc ? run_batch_var<3, false, true>(st.variant, d_items, nitems, max_blocks, ragged, stream)
-                      : run_batch_var<3, false, false>(st.variant, d_items, nitems, max_blocks, ragged, stream);
-        default: return cudaErrorInvalidValue;
-    }
+    return dispatch_batch(st, false, d_items, nitems, max_blocks, ragged, stream);
+}
+
+bool untransform_batch_item_ok(const Settings& st, const UntransformBatchItem& it) {
+    bool ragged = false;   // the untransform only reads the streams: any natural alignment goes
+    return transform_batch_item_ok(st, TransformBatchItem{it.out, it.in, it.nblocks}, &ragged);
+}
+
+cudaError_t launch_untransform_batch(const Settings& st, const UntransformBatchItem* d_items, int nitems, uint64_t max_blocks,
+                                     cudaStream_t stream) {
+    return dispatch_batch(st, true, d_items, nitems, max_blocks, false, stream);
 }
 
 cudaError_t launch_transform(const Settings& st, const uint8_t* in, const StreamPtrs& out, uint64_t nblocks,

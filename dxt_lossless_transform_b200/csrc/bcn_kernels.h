@@ -25,6 +25,16 @@ bool transform_batch_item_ok(const Settings& st, const TransformBatchItem& item,
 cudaError_t launch_transform_batch(const Settings& st, const TransformBatchItem* d_items, int nitems, uint64_t max_blocks,
                                    bool ragged, cudaStream_t stream);
 
+// ... and the inverse: item.in = the payload's streams, item.out = its blocks (16-byte aligned).
+struct UntransformBatchItem {
+    StreamPtrs in;
+    uint8_t* out;
+    uint64_t nblocks;
+};
+bool untransform_batch_item_ok(const Settings& st, const UntransformBatchItem& item);
+cudaError_t launch_untransform_batch(const Settings& st, const UntransformBatchItem* d_items, int nitems, uint64_t max_blocks,
+                                     cudaStream_t stream);
+
 // Exact inverse: gathers the streams back into `nblocks` blocks at `out`.
 cudaError_t launch_untransform(const Settings& st, const StreamPtrs& in, uint8_t* out, uint64_t nblocks,
                                cudaStream_t stream);

@@ -10,6 +10,8 @@
 #include <utility>
 #include <vector>
 
+#include <cuda.h>   // types of cuPointerGetAttributes only; the entry point comes from cudaGetDriverEntryPoint
+
 #include "bcn_kernels.h"
 
 namespace dlt {
@@ -246,6 +248,99 @@ bool is_pinned_host(const void* p) {
 
 namespace {
 
+// Page-locked ranges the current call has seen: one driver query tells whether a pointer is page-locked host memory,
+// where its allocation starts and ends and what its device alias is, so the thousands of payloads of a batch that
+// were carved out of a few pinned pools cost one query per pool instead of four per payload.  The cache lives for ONE
+// call (the caller cannot free memory it has handed to a running call), so it can never go stale.
+class PinnedRanges {
+public:
+    // True when [p, p + len) is page-locked host memory; *dev (optional) receives the device alias of p.
+    bool covers(const uint8_t* p, size_t len, uint8_t** dev) {
+        if (len == 0) return false;
+        for (int i = 0; i < n_; i++) {
+            const Range& r = r_[i];
+            if (p >= r.host && p + len <= r.host + r.size) {
+                if (dev) *dev = r.dev + (p - r.host);
+                return true;
+            }
+        }
+        Range r{};
+        if (!query(p, &r)) return false;
+        if (r.size > 1) {
+            if (n_ < kMax) r_[n_++] = r;
+            else r_[next_++ % kMax] = r;
+        }
+        if (p + len <= r.host + r.size) {
+            if (dev) *dev = r.dev + (p - r.host);
+            return true;
+        }
+        // no range information (fallback query): accept when the last byte is page-locked too
+        if (r.size == 1 && is_pinned_host(p + len - 1)) {
+            if (dev) *dev = r.dev;
+            return true;
+        }
+        return false;
+    }
+
+private:
+    struct Range {
+        const uint8_t* host;
+        size_t size;
+        uint8_t* dev;
+    };
+    static bool query(const uint8_t* p, Range* out) {
+        using Fn = CUresult (*)(unsigned int, CUpointer_attribute*, void**, CUdeviceptr);
+        static Fn fn = [] {
+            void* f = nullptr;
+            cudaDriverEntryPointQueryResult q{};
+            if (cudaGetDriverEntryPoint("cuPointerGetAttributes", &f, cudaEnableDefault, &q) != cudaSuccess ||
+                q != cudaDriverEntryPointSuccess)
+                f = nullptr;
+            (void)cudaGetLastError();
+            return reinterpret_cast<Fn>(f);
+        }();
+        if (fn) {
+            unsigned int type = 0;
+            CUdeviceptr dptr = 0, start = 0;
+            void* hptr = nullptr;
+            size_t size = 0;
+            CUpointer_attribute attrs[5] = {CU_POINTER_ATTRIBUTE_MEMORY_TYPE, CU_POINTER_ATTRIBUTE_DEVICE_POINTER,
+                                            CU_POINTER_ATTRIBUTE_HOST_POINTER, CU_POINTER_ATTRIBUTE_RANGE_START_ADDR,
+                                            CU_POINTER_ATTRIBUTE_RANGE_SIZE};
+            void* data[5] = {&type, &dptr, &hptr, &start, &size};
+            if (fn(5, attrs, data, reinterpret_cast<CUdeviceptr>(p)) == CUDA_SUCCESS && type == CU_MEMORYTYPE_HOST && dptr && size &&
+                hptr == p) {
+                // the range start is reported in the address space of the queried pointer (host) or of its device alias;
+                // with unified addressing the two coincide.  Host and device aliases share offsets.
+                const CUdeviceptr hp = reinterpret_cast<CUdeviceptr>(p);
+                size_t before = SIZE_MAX;
+                if (start <= hp && hp - start < size) before = (size_t)(hp - start);
+                else if (start <= dptr && dptr - start < size) before = (size_t)(dptr - start);
+                if (before != SIZE_MAX) {
+                    out->host = p - before;
+                    out->size = size;
+                    out->dev = reinterpret_cast<uint8_t*>(dptr) - before;
+                    return true;
+                }
+            }
+            if (type != CU_MEMORYTYPE_HOST) return false;
+        }
+        // fallback: the runtime's per-pointer query, a range of one byte (the caller then checks the last byte too)
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return false;
+        }
+        if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+        out->host = p, out->size = 1, out->dev = static_cast<uint8_t*>(a.devicePointer);
+        return true;
+    }
+    static constexpr int kMax = 8;
+    Range r_[kMax];
+    int n_ = 0;
+    unsigned next_ = 0;
+};
+
 // Device-side chunk slots: blocks in one buffer, the chunk's streams compacted in another with
 // every stream 256-byte aligned (chunk block counts are powers of two), so the tiled kernels always
 // run their aligned path no matter what N is.
@@ -277,24 +372,29 @@ class HostPipeline {
 public:
     explicit HostPipeline(Context* ctx) : ctx_(ctx), cfg_(host_path_config()) {}
 
-    // Largest chunk a job will use (slots must be sized before the first submit()).
-    size_t chunk_bytes_for(const HostJob& job, bool* in_pinned, bool* out_pinned) const {
-        *in_pinned = is_pinned_host(job.in) && is_pinned_host(job.in + job.len - 1);
-        *out_pinned = is_pinned_host(job.out) && is_pinned_host(job.out + job.len - 1);
-        size_t c = *in_pinned && *out_pinned ? cfg_.chunk_bytes : std::min(cfg_.chunk_bytes, kStagedChunkBytes);
-        return std::min(c, (job.len + (size_t)kTileBytes - 1) / kTileBytes * kTileBytes);
-    }
+    // What prepare() learns about a job: where its buffers live and the largest chunk it will use.
+    struct JobInfo {
+        bool in_pinned = false, out_pinned = false, zero_copy = false;
+        uint8_t *in_dev = nullptr, *out_dev = nullptr;   // device aliases of page-locked buffers
+        size_t chunk_bytes = 0;
+    };
 
     Status prepare(const HostJob* jobs, size_t count) {
         size_t max_chunk = 0;
         bool staged = false;
+        info_.assign(count, JobInfo{});
         for (size_t i = 0; i < count; i++) {
-            if (jobs[i].len == 0) continue;
-            bool ip, op;
-            const size_t c = chunk_bytes_for(jobs[i], &ip, &op);
-            if (cfg_.zero_copy && jobs[i].len <= cfg_.zero_copy_max_bytes && ip && op) continue;
-            max_chunk = std::max(max_chunk, c);
-            staged |= !ip || !op;
+            const HostJob& job = jobs[i];
+            if (job.len == 0) continue;
+            JobInfo& f = info_[i];
+            f.in_pinned = pinned_.covers(job.in, job.len, &f.in_dev);
+            f.out_pinned = pinned_.covers(job.out, job.len, &f.out_dev);
+            const size_t c = f.in_pinned && f.out_pinned ? cfg_.chunk_bytes : std::min(cfg_.chunk_bytes, kStagedChunkBytes);
+            f.chunk_bytes = std::min(c, (job.len + (size_t)kTileBytes - 1) / kTileBytes * kTileBytes);
+            f.zero_copy = cfg_.zero_copy && job.len <= cfg_.zero_copy_max_bytes && f.in_pinned && f.out_pinned;
+            if (f.zero_copy) continue;
+            max_chunk = std::max(max_chunk, f.chunk_bytes);
+            staged |= !f.in_pinned || !f.out_pinned;
         }
         if (max_chunk) {
             const Status st = ensure_slots(ctx_, &slots_, max_chunk);
@@ -303,32 +403,51 @@ public:
         return staged ? ensure_staging(ctx_) : Status::kOk;
     }
 
-    Status submit(const HostJob& job) {
+    Status submit(const HostJob& job, size_t index) {
         if (job.len == 0) return Status::kOk;
+        const JobInfo& info = info_[index];
         const Settings& st = job.st;
         const int bpb = block_bytes(st.format);
         const int ns = num_streams(st.format, st.split_alpha, st.split_colour);
         const size_t n = job.len / bpb;
-        bool in_pinned, out_pinned;
-        const size_t chunk_bytes = chunk_bytes_for(job, &in_pinned, &out_pinned);
+        const bool in_pinned = info.in_pinned, out_pinned = info.out_pinned;
+        const size_t chunk_bytes = info.chunk_bytes;
 
-        // Small page-locked payloads: the kernel reads the blocks and writes the streams straight over
-        // the host link (mapped memory) — one launch, no staging copies, lowest latency.
-        if (cfg_.zero_copy && job.len <= cfg_.zero_copy_max_bytes && in_pinned && out_pinned) {
-            void *d_in = nullptr, *d_out = nullptr;
-            if (cudaHostGetDevicePointer(&d_in, const_cast<uint8_t*>(job.in), 0) == cudaSuccess &&
-                cudaHostGetDevicePointer(&d_out, job.out, 0) == cudaSuccess) {
-                const int slot = (int)(seq_++ % cfg_.stages);
-                cudaStream_t s = ctx_->stream[slot];
-                if (!job.inverse)
-                    DLT_CUDA(launch_transform(st, static_cast<const uint8_t*>(d_in),
-                                              reference_layout(static_cast<uint8_t*>(d_out), n, 0, st), n, s));
-                else
-                    DLT_CUDA(launch_untransform(st, reference_layout(static_cast<uint8_t*>(d_in), n, 0, st),
-                                                static_cast<uint8_t*>(d_out), n, s));
+        // Small page-locked payloads: the kernel reads the blocks and writes the streams straight over the host link
+        // (mapped memory) — no staging copies, lowest latency.  They are not launched one by one: all payloads of the
+        // call that share a settings combination go out as ONE launch (grid.y = payload) when the call drains.
+        if (info.zero_copy) {
+            ZeroCopyGroup* g = nullptr;
+            for (ZeroCopyGroup& c : groups_)
+                if (c.inverse == job.inverse && c.st.format == st.format && c.st.variant == st.variant &&
+                    c.st.split_alpha == st.split_alpha && c.st.split_colour == st.split_colour && c.st.normalize == st.normalize &&
+                    c.count() < 65535)
+                    g = &c;
+            if (!g) {
+                groups_.emplace_back();
+                g = &groups_.back();
+                g->st = st, g->inverse = job.inverse;
+            }
+            bool batched = st.normalize == kNormNone;
+            if (!job.inverse) {
+                TransformBatchItem item{info.in_dev, reference_layout(info.out_dev, n, 0, st), n};
+                bool ragged = false;
+                batched = batched && transform_batch_item_ok(st, item, &ragged);
+                if (batched) g->fwd.push_back(item), g->ragged |= ragged;
+            } else {
+                UntransformBatchItem item{reference_layout(info.in_dev, n, 0, st), info.out_dev, n};
+                batched = batched && untransform_batch_item_ok(st, item);
+                if (batched) g->inv.push_back(item);
+            }
+            if (batched) {
+                g->max_blocks = std::max<uint64_t>(g->max_blocks, n);
                 return Status::kOk;
             }
-            (void)cudaGetLastError();
+            // pointers the tiled kernels cannot take: its own launch (byte-granular kernel)
+            cudaStream_t s = ctx_->stream[(int)(seq_++ % cfg_.stages)];
+            if (!job.inverse) DLT_CUDA(launch_transform(st, info.in_dev, reference_layout(info.out_dev, n, 0, st), n, s));
+            else DLT_CUDA(launch_untransform(st, reference_layout(info.in_dev, n, 0, st), info.out_dev, n, s));
+            return Status::kOk;
         }
 
         const size_t chunk_blocks = chunk_bytes / bpb;
@@ -437,8 +556,36 @@ public:
         return Status::kOk;
     }
 
+    // The grouped zero-copy payloads: descriptors to the device, one launch per settings combination.
+    Status flush_groups() {
+        size_t bytes = 0;
+        for (const ZeroCopyGroup& g : groups_) bytes += g.fwd.size() * sizeof(TransformBatchItem) + g.inv.size() * sizeof(UntransformBatchItem);
+        if (bytes == 0) return Status::kOk;
+        const Status st = ensure_scratch(ctx_, bytes);
+        if (st != Status::kOk) return st;
+        cudaStream_t s = ctx_->stream[0];
+        uint8_t* d = ctx_->d_scratch;
+        for (const ZeroCopyGroup& g : groups_) {
+            if (!g.fwd.empty()) {
+                const size_t nb = g.fwd.size() * sizeof(TransformBatchItem);
+                DLT_CUDA(cudaMemcpyAsync(d, g.fwd.data(), nb, cudaMemcpyHostToDevice, s));
+                DLT_CUDA(launch_transform_batch(g.st, reinterpret_cast<const TransformBatchItem*>(d), (int)g.fwd.size(), g.max_blocks,
+                                                g.ragged, s));
+                d += nb;
+            }
+            if (!g.inv.empty()) {
+                const size_t nb = g.inv.size() * sizeof(UntransformBatchItem);
+                DLT_CUDA(cudaMemcpyAsync(d, g.inv.data(), nb, cudaMemcpyHostToDevice, s));
+                DLT_CUDA(launch_untransform_batch(g.st, reinterpret_cast<const UntransformBatchItem*>(d), (int)g.inv.size(),
+                                                  g.max_blocks, s));
+                d += nb;
+            }
+        }
+        return Status::kOk;
+    }
+
     Status drain() {
-        Status result = Status::kOk;
+        Status result = flush_groups();
         for (int i = 0; i < cfg_.stages; i++) {
             // oldest first: slots are used round-robin starting at seq_ % stages
             const Status f = finish((int)((seq_ + i) % cfg_.stages));
@@ -472,11 +619,23 @@ private:
         return Status::kOk;
     }
 
+    struct ZeroCopyGroup {
+        Settings st{};
+        bool inverse = false, ragged = false;
+        uint64_t max_blocks = 0;
+        std::vector<TransformBatchItem> fwd;
+        std::vector<UntransformBatchItem> inv;
+        size_t count() const { return fwd.size() + inv.size(); }
+    };
+
     Context* ctx_;
     const HostPathConfig& cfg_;
     Slots slots_{};
     Pending pending_[kStages];
     size_t seq_ = 0;
+    PinnedRanges pinned_;
+    std::vector<JobInfo> info_;
+    std::vector<ZeroCopyGroup> groups_;
 };
 
 }  // namespace
@@ -490,7 +649,7 @@ Status run_host_batch(const HostJob* jobs, size_t count, int device) {
     if (!ctx) return status;
     HostPipeline pipe(ctx);
     status = pipe.prepare(jobs, count);
-    for (size_t i = 0; i < count && status == Status::kOk; i++) status = pipe.submit(jobs[i]);
+    for (size_t i = 0; i < count && status == Status::kOk; i++) status = pipe.submit(jobs[i], i);
     const Status d = pipe.drain();
     release_context(ctx);
     return status != Status::kOk ? status : d;

@@ -442,6 +442,45 @@ def test_concurrent_host_threads(dlt):
     assert not errors, errors
 
 
+def test_batch_of_small_pinned_payloads_is_grouped_by_settings(dlt):
+    """Many small payloads carved out of ONE page-locked pool (a directory of textures): the host path launches one
+    kernel per settings combination over all of them (mapped memory, no copies).  Mixed formats, settings, sizes (odd
+    block counts) and a few payloads at offsets the tiled kernels cannot take; both directions; guard gaps untouched."""
+    rng = np.random.default_rng(77)
+    pool_bytes = 24 << 20
+    pin_in, pin_out, pin_back = dlt.alloc_pinned(pool_bytes), dlt.alloc_pinned(pool_bytes), dlt.alloc_pinned(pool_bytes)
+    pin_in.array[:] = rng.integers(0, 256, pool_bytes, dtype=np.uint8)
+    pin_out.array[:] = 0xEE
+    pin_back.array[:] = 0xEE
+    items, back_items, spans = [], [], []
+    off = 0
+    for i in range(300):
+        fmt = 1 + i % 3
+        all_s = settings_list(dlt, fmt)
+        s = all_s[int(rng.integers(0, len(all_s)))]
+        nb = int(rng.choice([1, 2, 31, 257, 1024, 2049, 4097]))
+        nbytes = nb * bpb(fmt)
+        off = (off + 15) // 16 * 16 + (4 if i % 37 == 0 else 0)    # now and then a 4-byte aligned payload
+        if off + nbytes + 64 > pool_bytes:
+            break
+        src, dst, back = (a.array[off:off + nbytes] for a in (pin_in, pin_out, pin_back))
+        items.append((fmt, src, dst, s))
+        back_items.append((fmt, dst, back, s))
+        spans.append((off, nbytes, fmt, s))
+        off += nbytes + 48                                          # a guard gap after every payload
+    dlt.transform_batch(items)
+    dlt.transform_batch(back_items, untransform=True)
+    covered = np.zeros(pool_bytes, bool)
+    for o, nbytes, fmt, s in spans:
+        covered[o:o + nbytes] = True
+        expect = oracle.transform(fmt, pin_in.array[o:o + nbytes], *orc_args(s))
+        assert np.array_equal(pin_out.array[o:o + nbytes], expect), (o, nbytes, fmt, s)
+        assert np.array_equal(pin_back.array[o:o + nbytes], pin_in.array[o:o + nbytes]), (o, nbytes, fmt, s)
+    assert (pin_out.array[~covered] == 0xEE).all() and (pin_back.array[~covered] == 0xEE).all()
+    for a in (pin_in, pin_out, pin_back):
+        a.free()
+
+
 def test_repeated_calls_do_not_leak(dlt, torch):
     """Contexts, staging buffers and scratch are pooled: thousands of calls through every kind of entry point must leave
     device memory and host RSS where they were after the first few hundred."""
