@@ -23,6 +23,7 @@
 //     segment (< 16 bytes each) move bytewise.
 #include "bcn_kernels.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 
@@ -1085,6 +1086,30 @@ cudaError_t launch_normalize_split_blocks(uint8_t* colors, uint8_t* indices, uin
     if (ctas > 0x7fffffffull) return cudaErrorInvalidValue;
     const bool aligned = ((reinterpret_cast<uintptr_t>(colors) | reinterpret_cast<uintptr_t>(indices)) & 3) == 0;
     normalize_split_kernel<<<(unsigned)ctas, kThreads, 0, stream>>>(colors, indices, nblocks, mode, aligned);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// Gather: many small host->device (or any device-visible) copies as ONE launch — grid.y = copy, 8-byte vectors (BCn
+// payloads are multiples of 8 bytes; the pointers must be 8-byte aligned).
+namespace {
+__global__ void __launch_bounds__(kThreads) copy_batch_kernel(const CopyBatchItem* __restrict__ items) {
+    const CopyBatchItem it = items[blockIdx.y];
+    const uint64_t words = it.bytes / 8;
+    const uint2* src = reinterpret_cast<const uint2*>(it.src);
+    uint2* dst = reinterpret_cast<uint2*>(it.dst);
+    for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < words; i += (uint64_t)gridDim.x * kThreads) {
+        const uint2 v = ldg_stream8(src + i);
+        stg_stream8(dst + i, v);
+    }
+}
+}  // namespace
+
+cudaError_t launch_copy_batch(const CopyBatchItem* d_items, int nitems, uint64_t max_bytes, cudaStream_t stream) {
+    if (nitems <= 0 || max_bytes == 0) return cudaSuccess;
+    if (nitems > 65535) return cudaErrorInvalidValue;
+    const uint64_t ctas = std::min<uint64_t>((max_bytes / 8 + kThreads - 1) / kThreads, 1024);
+    copy_batch_kernel<<<dim3((unsigned)ctas, (unsigned)nitems), kThreads, 0, stream>>>(d_items);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

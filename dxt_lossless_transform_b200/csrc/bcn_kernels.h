@@ -35,6 +35,15 @@ bool untransform_batch_item_ok(const Settings& st, const UntransformBatchItem& i
 cudaError_t launch_untransform_batch(const Settings& st, const UntransformBatchItem* d_items, int nitems, uint64_t max_blocks,
                                      cudaStream_t stream);
 
+// Many small copies between device-visible buffers (mapped host memory included) in one launch; 8-byte aligned
+// pointers, sizes multiples of 8.  `d_items` is a DEVICE array, `max_bytes` the largest size among them.
+struct CopyBatchItem {
+    const uint8_t* src;
+    uint8_t* dst;
+    uint64_t bytes;
+};
+cudaError_t launch_copy_batch(const CopyBatchItem* d_items, int nitems, uint64_t max_bytes, cudaStream_t stream);
+
 // Exact inverse: gathers the streams back into `nblocks` blocks at `out`.
 cudaError_t launch_untransform(const Settings& st, const StreamPtrs& in, uint8_t* out, uint64_t nblocks,
                                cudaStream_t stream);

@@ -229,6 +229,17 @@ Status ensure_host_scratch(Context* ctx, size_t bytes) {
     return Status::kOk;
 }
 
+Status ensure_desc(Context* ctx, size_t bytes) {
+    if (ctx->d_desc_cap >= bytes && ctx->d_desc) return Status::kOk;
+    if (ctx->d_desc) cudaFree(ctx->d_desc);
+    ctx->d_desc = nullptr;
+    ctx->d_desc_cap = 0;
+    const size_t cap = (bytes + 65535) & ~(size_t)65535;
+    DLT_CUDA(cudaMalloc(&ctx->d_desc, cap));
+    ctx->d_desc_cap = cap;
+    return Status::kOk;
+}
+
 Status ensure_staging(Context* ctx) {
     for (int i = 0; i < kStages; i++) {
         if (!ctx->h_in[i]) DLT_CUDA(cudaMallocHost(&ctx->h_in[i], kStagingSlotBytes));
@@ -248,98 +259,84 @@ bool is_pinned_host(const void* p) {
 
 namespace {
 
-// Page-locked ranges the current call has seen: one driver query tells whether a pointer is page-locked host memory,
-// where its allocation starts and ends and what its device alias is, so the thousands of payloads of a batch that
-// were carved out of a few pinned pools cost one query per pool instead of four per payload.  The cache lives for ONE
-// call (the caller cannot free memory it has handed to a running call), so it can never go stale.
-class PinnedRanges {
-public:
-    // True when [p, p + len) is page-locked host memory; *dev (optional) receives the device alias of p.
-    bool covers(const uint8_t* p, size_t len, uint8_t** dev) {
-        if (len == 0) return false;
-        for (int i = 0; i < n_; i++) {
-            const Range& r = r_[i];
-            if (p >= r.host && p + len <= r.host + r.size) {
-                if (dev) *dev = r.dev + (p - r.host);
-                return true;
-            }
-        }
-        Range r{};
-        if (!query(p, &r)) return false;
-        if (r.size > 1) {
-            if (n_ < kMax) r_[n_++] = r;
-            else r_[next_++ % kMax] = r;
-        }
-        if (p + len <= r.host + r.size) {
+}  // namespace
+
+bool PinnedRanges::covers(const uint8_t* p, size_t len, uint8_t** dev) {
+    if (len == 0) return false;
+    for (int i = 0; i < n_; i++) {
+        const Range& r = r_[i];
+        if (p >= r.host && p + len <= r.host + r.size) {
             if (dev) *dev = r.dev + (p - r.host);
             return true;
         }
-        // no range information (fallback query): accept when the last byte is page-locked too
-        if (r.size == 1 && is_pinned_host(p + len - 1)) {
-            if (dev) *dev = r.dev;
-            return true;
-        }
-        return false;
     }
-
-private:
-    struct Range {
-        const uint8_t* host;
-        size_t size;
-        uint8_t* dev;
-    };
-    static bool query(const uint8_t* p, Range* out) {
-        using Fn = CUresult (*)(unsigned int, CUpointer_attribute*, void**, CUdeviceptr);
-        static Fn fn = [] {
-            void* f = nullptr;
-            cudaDriverEntryPointQueryResult q{};
-            if (cudaGetDriverEntryPoint("cuPointerGetAttributes", &f, cudaEnableDefault, &q) != cudaSuccess ||
-                q != cudaDriverEntryPointSuccess)
-                f = nullptr;
-            (void)cudaGetLastError();
-            return reinterpret_cast<Fn>(f);
-        }();
-        if (fn) {
-            unsigned int type = 0;
-            CUdeviceptr dptr = 0, start = 0;
-            void* hptr = nullptr;
-            size_t size = 0;
-            CUpointer_attribute attrs[5] = {CU_POINTER_ATTRIBUTE_MEMORY_TYPE, CU_POINTER_ATTRIBUTE_DEVICE_POINTER,
-                                            CU_POINTER_ATTRIBUTE_HOST_POINTER, CU_POINTER_ATTRIBUTE_RANGE_START_ADDR,
-                                            CU_POINTER_ATTRIBUTE_RANGE_SIZE};
-            void* data[5] = {&type, &dptr, &hptr, &start, &size};
-            if (fn(5, attrs, data, reinterpret_cast<CUdeviceptr>(p)) == CUDA_SUCCESS && type == CU_MEMORYTYPE_HOST && dptr && size &&
-                hptr == p) {
-                // the range start is reported in the address space of the queried pointer (host) or of its device alias;
-                // with unified addressing the two coincide.  Host and device aliases share offsets.
-                const CUdeviceptr hp = reinterpret_cast<CUdeviceptr>(p);
-                size_t before = SIZE_MAX;
-                if (start <= hp && hp - start < size) before = (size_t)(hp - start);
-                else if (start <= dptr && dptr - start < size) before = (size_t)(dptr - start);
-                if (before != SIZE_MAX) {
-                    out->host = p - before;
-                    out->size = size;
-                    out->dev = reinterpret_cast<uint8_t*>(dptr) - before;
-                    return true;
-                }
-            }
-            if (type != CU_MEMORYTYPE_HOST) return false;
-        }
-        // fallback: the runtime's per-pointer query, a range of one byte (the caller then checks the last byte too)
-        cudaPointerAttributes a{};
-        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-            (void)cudaGetLastError();
-            return false;
-        }
-        if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
-        out->host = p, out->size = 1, out->dev = static_cast<uint8_t*>(a.devicePointer);
+    Range r{};
+    if (!query(p, &r)) return false;
+    if (r.size > 1) {
+        if (n_ < kMax) r_[n_++] = r;
+        else r_[next_++ % kMax] = r;
+    }
+    if (p + len <= r.host + r.size) {
+        if (dev) *dev = r.dev + (p - r.host);
         return true;
     }
-    static constexpr int kMax = 8;
-    Range r_[kMax];
-    int n_ = 0;
-    unsigned next_ = 0;
-};
+    // no range information (fallback query): accept when the last byte is page-locked too
+    if (r.size == 1 && is_pinned_host(p + len - 1)) {
+        if (dev) *dev = r.dev;
+        return true;
+    }
+    return false;
+}
+
+bool PinnedRanges::query(const uint8_t* p, Range* out) {
+    using Fn = CUresult (*)(unsigned int, CUpointer_attribute*, void**, CUdeviceptr);
+    static Fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q{};
+        if (cudaGetDriverEntryPoint("cuPointerGetAttributes", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<Fn>(f);
+    }();
+    if (fn) {
+        unsigned int type = 0;
+        CUdeviceptr dptr = 0, start = 0;
+        void* hptr = nullptr;
+        size_t size = 0;
+        CUpointer_attribute attrs[5] = {CU_POINTER_ATTRIBUTE_MEMORY_TYPE, CU_POINTER_ATTRIBUTE_DEVICE_POINTER,
+                                        CU_POINTER_ATTRIBUTE_HOST_POINTER, CU_POINTER_ATTRIBUTE_RANGE_START_ADDR,
+                                        CU_POINTER_ATTRIBUTE_RANGE_SIZE};
+        void* data[5] = {&type, &dptr, &hptr, &start, &size};
+        if (fn(5, attrs, data, reinterpret_cast<CUdeviceptr>(p)) == CUDA_SUCCESS && type == CU_MEMORYTYPE_HOST && dptr && size &&
+            hptr == p) {
+            // the range start is reported in the address space of the queried pointer (host) or of its device alias;
+            // with unified addressing the two coincide.  Host and device aliases share offsets.
+            const CUdeviceptr hp = reinterpret_cast<CUdeviceptr>(p);
+            size_t before = SIZE_MAX;
+            if (start <= hp && hp - start < size) before = (size_t)(hp - start);
+            else if (start <= dptr && dptr - start < size) before = (size_t)(dptr - start);
+            if (before != SIZE_MAX) {
+                out->host = p - before;
+                out->size = size;
+                out->dev = reinterpret_cast<uint8_t*>(dptr) - before;
+                return true;
+            }
+        }
+        if (type != CU_MEMORYTYPE_HOST) return false;
+    }
+    // fallback: the runtime's per-pointer query, a range of one byte (the caller then checks the last byte too)
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+    out->host = p, out->size = 1, out->dev = static_cast<uint8_t*>(a.devicePointer);
+    return true;
+}
+
+namespace {
 
 // Device-side chunk slots: blocks in one buffer, the chunk's streams compacted in another with
 // every stream 256-byte aligned (chunk block counts are powers of two), so the tiled kernels always

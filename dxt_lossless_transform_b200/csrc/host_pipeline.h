@@ -56,6 +56,8 @@ struct Context {
     size_t d_scratch_cap = 0;
     uint8_t* h_scratch = nullptr;  // pinned host scratch kept between calls (zstd search: candidate images)
     size_t h_scratch_cap = 0;
+    uint8_t* d_desc = nullptr;     // small device buffer for launch descriptors (batched search: gather lists)
+    size_t d_desc_cap = 0;
     Context* next_free = nullptr;
 };
 
@@ -68,6 +70,7 @@ Status ensure_device_buffers(Context* ctx, size_t len);
 Status ensure_scratch(Context* ctx, size_t bytes);
 Status ensure_staging(Context* ctx);
 Status ensure_host_scratch(Context* ctx, size_t bytes);
+Status ensure_desc(Context* ctx, size_t bytes);
 
 // transform (inverse=false) or untransform (inverse=true) `len` bytes of host memory; blocks until
 // `out` holds the result.
@@ -93,5 +96,27 @@ void set_thread_device(int device);
 int thread_device();
 
 bool is_pinned_host(const void* p);
+
+// Page-locked ranges the current call has seen: one driver query tells whether a pointer is page-locked host memory,
+// where its allocation starts and ends and what its device alias is, so the thousands of payloads of a batch that
+// were carved out of a few pinned pools cost one query per pool instead of four per payload.  An instance lives for
+// ONE call (the caller cannot free memory it has handed to a running call), so it can never go stale.
+class PinnedRanges {
+public:
+    // True when [p, p + len) is page-locked host memory; *dev (optional) receives the device alias of p.
+    bool covers(const uint8_t* p, size_t len, uint8_t** dev);
+
+private:
+    struct Range {
+        const uint8_t* host;
+        size_t size;
+        uint8_t* dev;
+    };
+    static bool query(const uint8_t* p, Range* out);
+    static constexpr int kMax = 8;
+    Range r_[kMax];
+    int n_ = 0;
+    unsigned next_ = 0;
+};
 
 }  // namespace dlt
