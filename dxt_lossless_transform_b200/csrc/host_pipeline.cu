@@ -389,6 +389,17 @@ public:
             const size_t c = f.in_pinned && f.out_pinned ? cfg_.chunk_bytes : std::min(cfg_.chunk_bytes, kStagedChunkBytes);
             f.chunk_bytes = std::min(c, (job.len + (size_t)kTileBytes - 1) / kTileBytes * kTileBytes);
             f.zero_copy = cfg_.zero_copy && job.len <= cfg_.zero_copy_max_bytes && f.in_pinned && f.out_pinned;
+            if (f.zero_copy) {
+                // mapped memory only where the tiled kernels can take the pointers as they are (a DDS payload behind a
+                // 148-byte DX10 header is 4-byte aligned): the byte-granular kernel over the host link would crawl, the
+                // copy pipeline re-aligns the payload in its device slot instead
+                const Settings& st = job.st;
+                const size_t n = job.len / block_bytes(st.format);
+                bool ragged = false;
+                f.zero_copy = !job.inverse
+                                  ? transform_batch_item_ok(st, TransformBatchItem{f.in_dev, reference_layout(f.out_dev, n, 0, st), n}, &ragged)
+                                  : untransform_batch_item_ok(st, UntransformBatchItem{reference_layout(f.in_dev, n, 0, st), f.out_dev, n});
+            }
             if (f.zero_copy) continue;
             max_chunk = std::max(max_chunk, f.chunk_bytes);
             staged |= !f.in_pinned || !f.out_pinned;
@@ -425,25 +436,21 @@ public:
                 g = &groups_.back();
                 g->st = st, g->inverse = job.inverse;
             }
-            bool batched = st.normalize == kNormNone;
             if (!job.inverse) {
-                TransformBatchItem item{info.in_dev, reference_layout(info.out_dev, n, 0, st), n};
+                const TransformBatchItem item{info.in_dev, reference_layout(info.out_dev, n, 0, st), n};
                 bool ragged = false;
-                batched = batched && transform_batch_item_ok(st, item, &ragged);
-                if (batched) g->fwd.push_back(item), g->ragged |= ragged;
+                (void)transform_batch_item_ok(st, item, &ragged);
+                if (st.normalize == kNormNone) {
+                    g->fwd.push_back(item), g->ragged |= ragged;
+                    g->max_blocks = std::max<uint64_t>(g->max_blocks, n);
+                    return Status::kOk;
+                }
+                // (normalizing transforms have no batch instantiation: one launch each)
+                DLT_CUDA(launch_transform(st, item.in, item.out, n, ctx_->stream[(int)(seq_++ % cfg_.stages)]));
             } else {
-                UntransformBatchItem item{reference_layout(info.in_dev, n, 0, st), info.out_dev, n};
-                batched = batched && untransform_batch_item_ok(st, item);
-                if (batched) g->inv.push_back(item);
-            }
-            if (batched) {
+                g->inv.push_back(UntransformBatchItem{reference_layout(info.in_dev, n, 0, st), info.out_dev, n});
                 g->max_blocks = std::max<uint64_t>(g->max_blocks, n);
-                return Status::kOk;
             }
-            // pointers the tiled kernels cannot take: its own launch (byte-granular kernel)
-            cudaStream_t s = ctx_->stream[(int)(seq_++ % cfg_.stages)];
-            if (!job.inverse) DLT_CUDA(launch_transform(st, info.in_dev, reference_layout(info.out_dev, n, 0, st), n, s));
-            else DLT_CUDA(launch_untransform(st, reference_layout(info.in_dev, n, 0, st), info.out_dev, n, s));
             return Status::kOk;
         }
 
