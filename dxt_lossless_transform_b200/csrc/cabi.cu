@@ -865,7 +865,8 @@ int auto_batch_host(DltcudaAutoJob* jobs, size_t count, bool use_all) {
             if (j.len == 0 || j.len > kMappedMax) continue;
             if ((reinterpret_cast<uintptr_t>(j.input) & 7) == 0 && pinned.covers(j.input, j.len, &in_dev[i])) g++;
             else in_dev[i] = nullptr;
-            if (!pinned.covers(j.output, j.len, &out_dev[i])) out_dev[i] = nullptr;
+            // (a 16-byte aligned base keeps every stream of the reference layout naturally aligned: the tiled kernels apply)
+            if ((reinterpret_cast<uintptr_t>(j.output) & 15) != 0 || !pinned.covers(j.output, j.len, &out_dev[i])) out_dev[i] = nullptr;
         }
         max_gather = std::max(max_gather, g);
     }
