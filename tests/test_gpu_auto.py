@@ -263,6 +263,40 @@ def test_auto_batch_rounds_overlap_without_mixing_payloads(dlt):
         assert np.array_equal(out, want_out), (i, fmt)
 
 
+def test_auto_batch_with_page_locked_payloads_uses_mapped_memory_and_still_matches(dlt):
+    """Small payloads in ONE page-locked pool: inputs are gathered by a kernel over the mapped memory and the winners are
+    written straight into the mapped outputs (no per-payload copies) — same choices and bytes as the oracle.  Some
+    buffers sit at 8-byte offsets (they take the copy path) and some payloads are above the mapped-memory threshold."""
+    from dxt_lossless_transform_b200 import synth
+
+    rng = np.random.default_rng(5)
+    pool = 40 << 20
+    pin_in, pin_out = dlt.alloc_pinned(pool), dlt.alloc_pinned(pool)
+    pin_out.array[:] = 0xCD
+    items, spans, off = [], [], 0
+    for i in range(48):
+        fmt = 1 + i % 3
+        nb = int(rng.choice([5, 300, 2048, 4097, 16384, 40_000]))
+        nbytes = nb * (8 if fmt == 1 else 16)
+        off = (off + 255) // 256 * 256 + (8 if i % 7 == 3 else 0)
+        if off + nbytes + 64 > pool:
+            break
+        pin_in.array[off:off + nbytes] = synth.texture_blocks(fmt, nb, seed=300 + i, smooth=[0.2, 1.0, 5.0][i % 3])
+        items.append((fmt, pin_in.array[off:off + nbytes], pin_out.array[off:off + nbytes]))
+        spans.append((off, nbytes))
+        off += nbytes + 32
+    best = dlt.transform_auto_batch(items, False)
+    covered = np.zeros(pool, bool)
+    for (fmt, data, out), b, (o, nbytes) in zip(items, best, spans):
+        covered[o:o + nbytes] = True
+        want_out, want = oracle.auto(fmt, np.array(data), False)
+        got = (int(b.decorrelation_mode), bool(getattr(b, "split_alpha_endpoints", False)), bool(b.split_colour_endpoints))
+        assert got == want, (fmt, o, nbytes)
+        assert np.array_equal(out, want_out), (fmt, o, nbytes)
+    assert (pin_out.array[~covered] == 0xCD).all()
+    pin_in.free(), pin_out.free()
+
+
 def test_dds_batch_with_auto_bundle_shares_one_search(dlt):
     """DdsHandler.transform_bundle_batch with auto builders + the LTU estimator: per-file results equal the single-file
     calls (which equal the oracle), through the batched search."""
