@@ -1095,12 +1095,50 @@ cudaError_t launch_normalize_split_blocks(uint8_t* colors, uint8_t* indices, uin
 namespace {
 __global__ void __launch_bounds__(kThreads) copy_batch_kernel(const CopyBatchItem* __restrict__ items) {
     const CopyBatchItem it = items[blockIdx.y];
-    const uint64_t words = it.bytes / 8;
-    const uint2* src = reinterpret_cast<const uint2*>(it.src);
-    uint2* dst = reinterpret_cast<uint2*>(it.dst);
-    for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < words; i += (uint64_t)gridDim.x * kThreads) {
-        const uint2 v = ldg_stream8(src + i);
-        stg_stream8(dst + i, v);
+    const uint64_t first = (uint64_t)blockIdx.x * kThreads + threadIdx.x, step = (uint64_t)gridDim.x * kThreads;
+    if (((reinterpret_cast<uintptr_t>(it.src) | reinterpret_cast<uintptr_t>(it.dst)) & 7) == 0) {
+        const uint2* src = reinterpret_cast<const uint2*>(it.src);
+        uint2* dst = reinterpret_cast<uint2*>(it.dst);
+        for (uint64_t i = first; i < it.bytes / 8; i += step) stg_stream8(dst + i, ldg_stream8(src + i));
+    } else if (reinterpret_cast<uintptr_t>(it.src) & 15) {
+        // Gather from a 4-byte aligned source (a payload behind a 148-byte header, in mapped host memory): the host side is
+        // read as whole aligned 128-bit vectors (4-byte reads over the host link crawl), the device side takes words.
+        const uintptr_t shift = reinterpret_cast<uintptr_t>(it.src) & 15;
+        const uint8_t* a0 = it.src - shift;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(it.dst);
+        const uint64_t nvec = (shift + it.bytes + 15) / 16;
+        for (uint64_t t = first; t < nvec; t += step) {
+            const uint4 v = ldg_stream16(a0 + 16 * t);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int64_t pos = (int64_t)(16 * t + 4 * k) - (int64_t)shift;
+                if (pos >= 0 && (uint64_t)pos < it.bytes) dst[pos / 4] = w[k];
+            }
+        }
+    } else {
+        // Scatter to a 4-byte aligned destination: whole aligned 128-bit vectors on the host side, words on the device side.
+        const uintptr_t shift = reinterpret_cast<uintptr_t>(it.dst) & 15;
+        uint8_t* a0 = it.dst - shift;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(it.src);
+        const uint64_t nvec = (shift + it.bytes + 15) / 16;
+        for (uint64_t t = first; t < nvec; t += step) {
+            uint32_t w[4];
+            bool ok[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int64_t pos = (int64_t)(16 * t + 4 * k) - (int64_t)shift;
+                ok[k] = pos >= 0 && (uint64_t)pos < it.bytes;
+                w[k] = ok[k] ? src[pos / 4] : 0u;
+            }
+            if (ok[0] && ok[3]) {
+                stg_stream16(a0 + 16 * t, make_uint4(w[0], w[1], w[2], w[3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (ok[k]) reinterpret_cast<uint32_t*>(a0 + 16 * t)[k] = w[k];
+            }
+        }
     }
 }
 }  // namespace
@@ -1108,7 +1146,7 @@ __global__ void __launch_bounds__(kThreads) copy_batch_kernel(const CopyBatchIte
 cudaError_t launch_copy_batch(const CopyBatchItem* d_items, int nitems, uint64_t max_bytes, cudaStream_t stream) {
     if (nitems <= 0 || max_bytes == 0) return cudaSuccess;
     if (nitems > 65535) return cudaErrorInvalidValue;
-    const uint64_t ctas = std::min<uint64_t>((max_bytes / 8 + kThreads - 1) / kThreads, 1024);
+    const uint64_t ctas = std::min<uint64_t>((max_bytes / 4 + kThreads - 1) / kThreads, 1024);
     copy_batch_kernel<<<dim3((unsigned)ctas, (unsigned)nitems), kThreads, 0, stream>>>(d_items);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();

@@ -35,8 +35,8 @@ bool untransform_batch_item_ok(const Settings& st, const UntransformBatchItem& i
 cudaError_t launch_untransform_batch(const Settings& st, const UntransformBatchItem* d_items, int nitems, uint64_t max_blocks,
                                      cudaStream_t stream);
 
-// Many small copies between device-visible buffers (mapped host memory included) in one launch; 8-byte aligned
-// pointers, sizes multiples of 8.  `d_items` is a DEVICE array, `max_bytes` the largest size among them.
+// Many small copies between device-visible buffers (mapped host memory included) in one launch; 4-byte aligned
+// pointers (8-byte vectors when both are 8-byte aligned), sizes multiples of 8.  `d_items` is a DEVICE array, `max_bytes` the largest size among them.
 struct CopyBatchItem {
     const uint8_t* src;
     uint8_t* dst;

@@ -372,14 +372,18 @@ public:
     // What prepare() learns about a job: where its buffers live and the largest chunk it will use.
     struct JobInfo {
         bool in_pinned = false, out_pinned = false, zero_copy = false;
+        // zero_copy, but a side the tiled kernels cannot address as it lies in host memory (blocks not 16-byte aligned,
+        // a stream without its natural alignment): that side passes through a piece of a device arena
+        bool in_arena = false, out_arena = false;
         uint8_t *in_dev = nullptr, *out_dev = nullptr;   // device aliases of page-locked buffers
-        size_t chunk_bytes = 0;
+        size_t chunk_bytes = 0, in_off = 0, out_off = 0;
     };
 
     Status prepare(const HostJob* jobs, size_t count) {
         size_t max_chunk = 0;
         bool staged = false;
         info_.assign(count, JobInfo{});
+        constexpr size_t kArenaBudget = (size_t)1 << 30;
         for (size_t i = 0; i < count; i++) {
             const HostJob& job = jobs[i];
             if (job.len == 0) continue;
@@ -390,15 +394,29 @@ public:
             f.chunk_bytes = std::min(c, (job.len + (size_t)kTileBytes - 1) / kTileBytes * kTileBytes);
             f.zero_copy = cfg_.zero_copy && job.len <= cfg_.zero_copy_max_bytes && f.in_pinned && f.out_pinned;
             if (f.zero_copy) {
-                // mapped memory only where the tiled kernels can take the pointers as they are (a DDS payload behind a
-                // 148-byte DX10 header is 4-byte aligned): the byte-granular kernel over the host link would crawl, the
-                // copy pipeline re-aligns the payload in its device slot instead
+                // Mapped memory directly where the tiled kernels can take the pointers: the streams need their natural
+                // alignment, the blocks 16 bytes.  A DDS payload behind a 148-byte DX10 header is 4-byte aligned: such a
+                // side passes through a 256-byte aligned piece of a device arena — ONE gather kernel before and ONE scatter
+                // kernel after the launches serve all such payloads of the call — while the other side still travels
+                // over the mapped memory.  Sides that are not even 4-byte aligned take the copy pipeline.
                 const Settings& st = job.st;
                 const size_t n = job.len / block_bytes(st.format);
+                alignas(16) static uint8_t aligned_dummy[16];
                 bool ragged = false;
-                f.zero_copy = !job.inverse
-                                  ? transform_batch_item_ok(st, TransformBatchItem{f.in_dev, reference_layout(f.out_dev, n, 0, st), n}, &ragged)
-                                  : untransform_batch_item_ok(st, UntransformBatchItem{reference_layout(f.in_dev, n, 0, st), f.out_dev, n});
+                auto streams_ok = [&](uint8_t* base) {
+                    return transform_batch_item_ok(st, TransformBatchItem{aligned_dummy, reference_layout(base, n, 0, st), n}, &ragged);
+                };
+                const bool in_ok = job.inverse ? streams_ok(f.in_dev) : (reinterpret_cast<uintptr_t>(f.in_dev) & 15) == 0;
+                const bool out_ok = job.inverse ? (reinterpret_cast<uintptr_t>(f.out_dev) & 15) == 0 : streams_ok(f.out_dev);
+                const size_t piece = (job.len + 255) / 256 * 256;
+                const size_t need = (in_ok ? 0 : piece) + (out_ok ? 0 : piece);
+                if ((!in_ok && (reinterpret_cast<uintptr_t>(f.in_dev) & 3)) || (!out_ok && (reinterpret_cast<uintptr_t>(f.out_dev) & 3)) ||
+                    arena_bytes_ + need > kArenaBudget) {
+                    f.zero_copy = false;
+                } else {
+                    if (!in_ok) f.in_arena = true, f.in_off = arena_bytes_, arena_bytes_ += piece;
+                    if (!out_ok) f.out_arena = true, f.out_off = arena_bytes_, arena_bytes_ += piece;
+                }
             }
             if (f.zero_copy) continue;
             max_chunk = std::max(max_chunk, f.chunk_bytes);
@@ -436,19 +454,27 @@ public:
                 g = &groups_.back();
                 g->st = st, g->inverse = job.inverse;
             }
+            // A side that goes through the arena is an OFFSET into it until flush_groups() knows where the arena is (the
+            // arena is 256-byte aligned, so alignment-dependent decisions can be taken on the offsets).
+            uint8_t* in_ptr = info.in_arena ? reinterpret_cast<uint8_t*>(info.in_off) : info.in_dev;
+            uint8_t* out_ptr = info.out_arena ? reinterpret_cast<uint8_t*>(info.out_off) : info.out_dev;
+            if (info.in_arena) gather_.push_back(CopyBatchItem{info.in_dev, in_ptr, job.len});
+            if (info.out_arena) scatter_.push_back(CopyBatchItem{out_ptr, info.out_dev, job.len});
+            const char flags = (char)((info.in_arena ? 1 : 0) | (info.out_arena ? 2 : 0));
             if (!job.inverse) {
-                const TransformBatchItem item{info.in_dev, reference_layout(info.out_dev, n, 0, st), n};
+                const TransformBatchItem item{in_ptr, reference_layout(out_ptr, n, 0, st), n};
                 bool ragged = false;
                 (void)transform_batch_item_ok(st, item, &ragged);
                 if (st.normalize == kNormNone) {
-                    g->fwd.push_back(item), g->ragged |= ragged;
+                    g->fwd.push_back(item), g->fwd_arena.push_back(flags), g->ragged |= ragged;
                     g->max_blocks = std::max<uint64_t>(g->max_blocks, n);
                     return Status::kOk;
                 }
-                // (normalizing transforms have no batch instantiation: one launch each)
-                DLT_CUDA(launch_transform(st, item.in, item.out, n, ctx_->stream[(int)(seq_++ % cfg_.stages)]));
+                // (normalizing transforms have no batch instantiation: one launch each, at flush time)
+                late_.push_back(LateTransform{st, item, flags});
             } else {
-                g->inv.push_back(UntransformBatchItem{reference_layout(info.in_dev, n, 0, st), info.out_dev, n});
+                g->inv.push_back(UntransformBatchItem{reference_layout(in_ptr, n, 0, st), out_ptr, n});
+                g->inv_arena.push_back(flags);
                 g->max_blocks = std::max<uint64_t>(g->max_blocks, n);
             }
             return Status::kOk;
@@ -560,17 +586,44 @@ public:
         return Status::kOk;
     }
 
-    // The grouped zero-copy payloads: descriptors to the device, one launch per settings combination.
+    // The grouped zero-copy payloads: descriptors to the device, one launch per settings combination; the payloads whose
+    // blocks are not 16-byte aligned in host memory are gathered into / scattered from the device arena by one kernel each.
     Status flush_groups() {
-        size_t bytes = 0;
-        for (const ZeroCopyGroup& g : groups_) bytes += g.fwd.size() * sizeof(TransformBatchItem) + g.inv.size() * sizeof(UntransformBatchItem);
-        if (bytes == 0) return Status::kOk;
-        const Status st = ensure_scratch(ctx_, bytes);
+        size_t desc = (gather_.size() + scatter_.size()) * sizeof(CopyBatchItem);
+        for (const ZeroCopyGroup& g : groups_) desc += g.fwd.size() * sizeof(TransformBatchItem) + g.inv.size() * sizeof(UntransformBatchItem);
+        if (desc == 0 && late_.empty()) return Status::kOk;
+        desc = (desc + 255) / 256 * 256;
+        const Status st = ensure_scratch(ctx_, desc + arena_bytes_);
         if (st != Status::kOk) return st;
         cudaStream_t s = ctx_->stream[0];
         uint8_t* d = ctx_->d_scratch;
-        for (const ZeroCopyGroup& g : groups_) {
+        uint8_t* arena = ctx_->d_scratch + desc;
+        auto in_arena = [arena](const uint8_t* off) { return arena + reinterpret_cast<uintptr_t>(off); };
+        auto streams_in_arena = [&](StreamPtrs& sp, const Settings& st) {
+            for (int k = 0; k < num_streams(st.format, st.split_alpha, st.split_colour); k++) sp.p[k] = in_arena(sp.p[k]);
+        };
+        auto run_copies = [&](std::vector<CopyBatchItem>& list, bool src_in_arena) -> cudaError_t {
+            if (list.empty()) return cudaSuccess;
+            uint64_t max_bytes = 0;
+            for (CopyBatchItem& c : list) {
+                if (src_in_arena) c.src = in_arena(c.src);
+                else c.dst = in_arena(c.dst);
+                max_bytes = std::max<uint64_t>(max_bytes, c.bytes);
+            }
+            const size_t nb = list.size() * sizeof(CopyBatchItem);
+            cudaError_t e = cudaMemcpyAsync(d, list.data(), nb, cudaMemcpyHostToDevice, s);
+            for (size_t at = 0; e == cudaSuccess && at < list.size(); at += 65535)
+                e = launch_copy_batch(reinterpret_cast<const CopyBatchItem*>(d) + at, (int)std::min<size_t>(65535, list.size() - at), max_bytes, s);
+            d += nb;
+            return e;
+        };
+        DLT_CUDA(run_copies(gather_, false));
+        for (ZeroCopyGroup& g : groups_) {
             if (!g.fwd.empty()) {
+                for (size_t i = 0; i < g.fwd.size(); i++) {
+                    if (g.fwd_arena[i] & 1) g.fwd[i].in = in_arena(g.fwd[i].in);
+                    if (g.fwd_arena[i] & 2) streams_in_arena(g.fwd[i].out, g.st);
+                }
                 const size_t nb = g.fwd.size() * sizeof(TransformBatchItem);
                 DLT_CUDA(cudaMemcpyAsync(d, g.fwd.data(), nb, cudaMemcpyHostToDevice, s));
                 DLT_CUDA(launch_transform_batch(g.st, reinterpret_cast<const TransformBatchItem*>(d), (int)g.fwd.size(), g.max_blocks,
@@ -578,6 +631,10 @@ public:
                 d += nb;
             }
             if (!g.inv.empty()) {
+                for (size_t i = 0; i < g.inv.size(); i++) {
+                    if (g.inv_arena[i] & 1) streams_in_arena(g.inv[i].in, g.st);
+                    if (g.inv_arena[i] & 2) g.inv[i].out = in_arena(g.inv[i].out);
+                }
                 const size_t nb = g.inv.size() * sizeof(UntransformBatchItem);
                 DLT_CUDA(cudaMemcpyAsync(d, g.inv.data(), nb, cudaMemcpyHostToDevice, s));
                 DLT_CUDA(launch_untransform_batch(g.st, reinterpret_cast<const UntransformBatchItem*>(d), (int)g.inv.size(),
@@ -585,6 +642,11 @@ public:
                 d += nb;
             }
         }
+        for (LateTransform& t : late_) {
+            if (t.flags & 2) streams_in_arena(t.item.out, t.st);
+            DLT_CUDA(launch_transform(t.st, (t.flags & 1) ? in_arena(t.item.in) : t.item.in, t.item.out, t.item.nblocks, s));
+        }
+        DLT_CUDA(run_copies(scatter_, true));
         return Status::kOk;
     }
 
@@ -629,7 +691,13 @@ private:
         uint64_t max_blocks = 0;
         std::vector<TransformBatchItem> fwd;
         std::vector<UntransformBatchItem> inv;
+        std::vector<char> fwd_arena, inv_arena;   // per item: bit 0 = input side, bit 1 = output side is an arena offset
         size_t count() const { return fwd.size() + inv.size(); }
+    };
+    struct LateTransform {
+        Settings st;
+        TransformBatchItem item;
+        char flags;
     };
 
     Context* ctx_;
@@ -640,6 +708,9 @@ private:
     PinnedRanges pinned_;
     std::vector<JobInfo> info_;
     std::vector<ZeroCopyGroup> groups_;
+    std::vector<CopyBatchItem> gather_, scatter_;
+    std::vector<LateTransform> late_;
+    size_t arena_bytes_ = 0;
 };
 
 }  // namespace
