@@ -592,6 +592,13 @@ public:
         size_t desc = (gather_.size() + scatter_.size()) * sizeof(CopyBatchItem);
         for (const ZeroCopyGroup& g : groups_) desc += g.fwd.size() * sizeof(TransformBatchItem) + g.inv.size() * sizeof(UntransformBatchItem);
         if (desc == 0 && late_.empty()) return Status::kOk;
+        if (groups_.size() == 1 && groups_[0].count() == 1 && gather_.empty() && scatter_.empty() && late_.empty()) {
+            // a single small payload (the plain synchronous call): no descriptor upload, the ordinary launch
+            const ZeroCopyGroup& g = groups_[0];
+            if (!g.fwd.empty()) DLT_CUDA(launch_transform(g.st, g.fwd[0].in, g.fwd[0].out, g.fwd[0].nblocks, ctx_->stream[0]));
+            else DLT_CUDA(launch_untransform(g.st, g.inv[0].in, g.inv[0].out, g.inv[0].nblocks, ctx_->stream[0]));
+            return Status::kOk;
+        }
         desc = (desc + 255) / 256 * 256;
         const Status st = ensure_scratch(ctx_, desc + arena_bytes_);
         if (st != Status::kOk) return st;
