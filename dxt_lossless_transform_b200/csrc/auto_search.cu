@@ -54,8 +54,46 @@ int estimate_ranges(int format, size_t len, EstimateRange out[2]) {
     return 2;
 }
 
-// Transforms `k` candidate settings of one device-resident payload into scratch images and estimates the endpoint
-// streams of each (in batches that fit the scratch budget): totals[i] = estimate of candidate i.
+// Which candidates really differ in an estimated range?  The bytes of a range depend on part of the settings only:
+// the BC3 alpha-endpoint range [0, 2N) on split_alpha alone, every colour range on (variant, split_colour, normalize).
+// The reference transforms and estimates every candidate (BC3: 8 / 16 x two ranges); estimates are a function of the
+// bytes, so estimating each DISTINCT range once and adding the shared results per candidate gives the same totals:
+// BC3 needs 2 alpha + 4 / 8 colour estimates and 4-5 / 9 transforms instead of 16 / 32 and 8 / 16.
+struct DistinctPlan {
+    struct Seg {
+        int cand, range;   // the candidate whose image holds the range
+    };
+    std::vector<Seg> segs;       // distinct ranges
+    std::vector<int> seg_of;     // [cand * nr + range] -> index into segs
+    std::vector<int> images;     // candidates that must be transformed (in candidate order)
+};
+static DistinctPlan plan_distinct(int format, const Settings* order, int k, int nr) {
+    DistinctPlan p;
+    p.seg_of.assign((size_t)k * nr, -1);
+    auto key_of = [format](const Settings& s, int r) {
+        if (format == 3 && r == 0) return (int)s.split_alpha;
+        return ((s.variant * 2 + (int)s.split_colour) << 3) | s.normalize;
+    };
+    std::vector<char> need((size_t)k, 0);
+    for (int i = 0; i < k; i++)
+        for (int r = 0; r < nr; r++) {
+            int found = -1;
+            for (size_t j = 0; j < p.segs.size() && found < 0; j++)
+                if (p.segs[j].range == r && key_of(order[p.segs[j].cand], r) == key_of(order[i], r)) found = (int)j;
+            if (found < 0) {
+                found = (int)p.segs.size();
+                p.segs.push_back({i, r});
+                need[i] = 1;
+            }
+            p.seg_of[(size_t)i * nr + r] = found;
+        }
+    for (int i = 0; i < k; i++)
+        if (need[i]) p.images.push_back(i);
+    return p;
+}
+
+// Transforms the candidates of one device-resident payload that hold a distinct estimated range into scratch images and
+// estimates those ranges (in batches that fit the scratch budget): totals[i] = estimate of candidate i.
 static Status estimate_candidates(Context* ctx, int format, const uint8_t* d_in, size_t len, const Settings* order, int k,
                                   size_t* totals, cudaStream_t stream) {
     const size_t n = len / block_bytes(format);
@@ -63,16 +101,19 @@ static Status estimate_candidates(Context* ctx, int format, const uint8_t* d_in,
     const int nr = estimate_ranges(format, len, ranges);
     for (int i = 0; i < k; i++) totals[i] = 0;
     if (len == 0) return Status::kOk;
-    // scratch = [m images][estimator buffers for m*nr segments]; all candidates at once when they fit
+    const DistinctPlan plan = plan_distinct(format, order, k, nr);
+    const int nimg = (int)plan.images.size();
+    // scratch = [m images][estimator buffers for their distinct ranges]; all images at once when they fit
     const size_t img = (len + 255) / 256 * 256;
     constexpr size_t kScratchBudget = (size_t)12 << 30;
-    std::vector<LtuSegment> segs((size_t)k * nr);
-    auto scratch_for = [&](int m) {
+    std::vector<LtuSegment> segs;
+    auto scratch_for = [&](int m) {   // worst case: every range of m images is distinct
+        segs.clear();
         for (int c = 0; c < m; c++)
-            for (int r = 0; r < nr; r++) segs[(size_t)c * nr + r] = LtuSegment{nullptr, ranges[r].len};
-        return (size_t)m * img + ltu_scratch_bytes(segs.data(), m * nr);
+            for (int r = 0; r < nr; r++) segs.push_back(LtuSegment{nullptr, ranges[r].len});
+        return (size_t)m * img + ltu_scratch_bytes(segs.data(), (int)segs.size());
     };
-    int m = k;
+    int m = nimg;
     while (m > 1 && scratch_for(m) > kScratchBudget) m--;
     Status st;
     while ((st = ensure_scratch(ctx, scratch_for(m))) == Status::kOutOfMemory && m > 1) m = (m + 1) / 2;
@@ -80,24 +121,33 @@ static Status estimate_candidates(Context* ctx, int format, const uint8_t* d_in,
     uint8_t* est_scratch = ctx->d_scratch + (size_t)m * img;
     const size_t est_bytes = ctx->d_scratch_cap - (size_t)m * img;
 
-    for (int c0 = 0; c0 < k; c0 += m) {
-        const int mb = k - c0 < m ? k - c0 : m;
+    std::vector<size_t> seg_estimate(plan.segs.size(), 0);
+    for (int c0 = 0; c0 < nimg; c0 += m) {
+        const int mb = nimg - c0 < m ? nimg - c0 : m;
+        segs.clear();
+        std::vector<int> which;   // index into plan.segs of every segment of this batch
         for (int c = 0; c < mb; c++) {
+            const int cand = plan.images[c0 + c];
             uint8_t* image = ctx->d_scratch + (size_t)c * img;
-            cudaError_t e = launch_transform(order[c0 + c], d_in, reference_layout(image, n, 0, order[c0 + c]), n, stream);
+            cudaError_t e = launch_transform(order[cand], d_in, reference_layout(image, n, 0, order[cand]), n, stream);
             if (e != cudaSuccess) {
                 note_cuda_error(e);
                 return Status::kCudaError;
             }
-            for (int r = 0; r < nr; r++) segs[(size_t)c * nr + r] = LtuSegment{image + ranges[r].offset, ranges[r].len};
+            for (size_t j = 0; j < plan.segs.size(); j++)
+                if (plan.segs[j].cand == cand) {
+                    const EstimateRange& rg = ranges[plan.segs[j].range];
+                    segs.push_back(LtuSegment{image + rg.offset, rg.len});
+                    which.push_back((int)j);
+                }
         }
-        std::vector<uint64_t> matches((size_t)mb * nr, 0);
-        st = ltu_matches_device(segs.data(), mb * nr, matches.data(), stream, est_scratch, est_bytes);
+        std::vector<uint64_t> matches(segs.size(), 0);
+        st = ltu_matches_device(segs.data(), (int)segs.size(), matches.data(), stream, est_scratch, est_bytes);
         if (st != Status::kOk) return st;
-        for (int c = 0; c < mb; c++)
-            for (int r = 0; r < nr; r++)
-                totals[c0 + c] += ltu_estimate_from_matches(ranges[r].len, matches[(size_t)c * nr + r]);
+        for (size_t q = 0; q < which.size(); q++) seg_estimate[which[q]] = ltu_estimate_from_matches(segs[q].len, matches[q]);
     }
+    for (int i = 0; i < k; i++)
+        for (int r = 0; r < nr; r++) totals[i] += seg_estimate[plan.seg_of[(size_t)i * nr + r]];
     return Status::kOk;
 }
 
@@ -234,37 +284,47 @@ Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_al
         return Status::kCudaError;
     };
     struct Cand {
-        int job, index;      // candidate `index` of job `job`
+        int job, index;      // candidate `index` of job `job` (only candidates that hold a distinct estimated range)
         uint8_t* image;      // its transformed image in the scratch
-        int first_seg, nseg;
+    };
+    struct JobSegs {
+        DistinctPlan plan;   // which ranges of which candidates are distinct (plan_distinct)
+        int first_seg = 0;   // the job's distinct ranges are segs[first_seg ...)
+        int nr = 0;
     };
     int j0 = 0;
     while (j0 < njobs) {
         // ---- the largest group [j0, j1) whose images + estimator scratch fit the budget
         std::vector<LtuSegment> segs;
         std::vector<Cand> cands;
+        std::vector<JobSegs> plans;   // one per job of the group, index j - j0
         LtuScratchMeter meter;
         size_t image_bytes = 0;
         int j1 = j0;
         for (; j1 < njobs; j1++) {
             const AutoJob& job = jobs[j1];
-            if (job.len == 0) continue;
+            JobSegs js;
+            if (job.len == 0) {
+                plans.push_back(js);
+                continue;
+            }
             Settings order[kMaxCandidates];
             const int k = candidate_order(job.format, use_all, order);
             EstimateRange ranges[2];
-            const int nr = estimate_ranges(job.format, job.len, ranges);
+            js.nr = estimate_ranges(job.format, job.len, ranges);
+            js.plan = plan_distinct(job.format, order, k, js.nr);
+            js.first_seg = (int)segs.size();
+            const size_t nimg = js.plan.images.size();
             const size_t img = (job.len + 255) / 256 * 256;
             LtuScratchMeter with_job = meter;
-            for (int c = 0; c < k; c++)
-                for (int r = 0; r < nr; r++) with_job.add(ranges[r].len);
-            const size_t need = image_bytes + (size_t)k * img + desc_bytes(cands.size() + k) + with_job.bytes();
+            for (const DistinctPlan::Seg& sg : js.plan.segs) with_job.add(ranges[sg.range].len);
+            const size_t need = image_bytes + nimg * img + desc_bytes(cands.size() + nimg) + with_job.bytes();
             if (need > kScratchBudget && j1 > j0) break;   // this job starts the next group
             meter = with_job;
-            for (int c = 0; c < k; c++) {
-                cands.push_back(Cand{j1, c, nullptr, (int)segs.size(), nr});
-                for (int r = 0; r < nr; r++) segs.push_back(LtuSegment{nullptr, ranges[r].len});
-            }
-            image_bytes += (size_t)k * img;
+            for (int c : js.plan.images) cands.push_back(Cand{j1, c, nullptr});
+            for (const DistinctPlan::Seg& sg : js.plan.segs) segs.push_back(LtuSegment{nullptr, ranges[sg.range].len});
+            image_bytes += nimg * img;
+            plans.push_back(std::move(js));
         }
         if (!cands.empty() && image_bytes + desc_bytes(cands.size()) + meter.bytes() > kScratchBudget) {
             // a single job that is too large for one group: the single-payload path batches its candidates itself
@@ -274,17 +334,18 @@ Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_al
             j0 = j0 + 1;
             continue;
         }
-        const size_t est_offset = image_bytes + desc_bytes(cands.size());
+        const size_t est_offset = image_bytes + desc_bytes(std::max<size_t>(cands.size(), (size_t)(j1 - j0)));
         Status st = ensure_scratch(ctx, est_offset + meter.bytes());
         if (st != Status::kOk) return st;
         TransformBatchItem* d_desc = reinterpret_cast<TransformBatchItem*>(ctx->d_scratch + image_bytes);
 
-        // ---- transform every candidate of every job of the group, point the segments at the endpoint streams
+        // ---- transform the candidates that hold a distinct range, point the segments at those ranges
         uint8_t* next_image = ctx->d_scratch;
         std::vector<BatchedTransform> work;
         work.reserve(cands.size());
         for (Cand& cd : cands) {
             const AutoJob& job = jobs[cd.job];
+            const JobSegs& js = plans[(size_t)(cd.job - j0)];
             Settings order[kMaxCandidates];
             candidate_order(job.format, use_all, order);
             EstimateRange ranges[2];
@@ -292,7 +353,8 @@ Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_al
             cd.image = next_image;
             next_image += (job.len + 255) / 256 * 256;
             work.push_back(BatchedTransform{order[cd.index], job.d_in, cd.image, job.len});
-            for (int r = 0; r < cd.nseg; r++) segs[cd.first_seg + r].d_ptr = cd.image + ranges[r].offset;
+            for (size_t q = 0; q < js.plan.segs.size(); q++)
+                if (js.plan.segs[q].cand == cd.index) segs[(size_t)js.first_seg + q].d_ptr = cd.image + ranges[js.plan.segs[q].range].offset;
         }
         cudaError_t qe = queue_transforms(work.data(), (int)work.size(), d_desc, stream);
         if (qe != cudaSuccess) return cuda_fail(qe);
@@ -305,21 +367,24 @@ Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_al
 
         // ---- winners (strict '<': the first candidate in test order wins ties) and their final transforms
         for (int j = j0; j < j1; j++) {
+            AutoJob& job = jobs[j];
+            const JobSegs& js = plans[(size_t)(j - j0)];
+            Settings order[kMaxCandidates];
+            const int k = candidate_order(job.format, use_all, order);
             // an empty payload: every estimate is 0, the first candidate in test order wins (as in the reference)
-            Settings order[kMaxCandidates];
-            candidate_order(jobs[j].format, use_all, order);
-            jobs[j].best = order[0];
-            for (int c = 0; c < kMaxCandidates; c++) jobs[j].sizes[c] = 0;
-        }
-        std::vector<size_t> best_size((size_t)(j1 - j0), SIZE_MAX);
-        for (const Cand& cd : cands) {
-            AutoJob& job = jobs[cd.job];
-            Settings order[kMaxCandidates];
-            candidate_order(job.format, use_all, order);
-            size_t total = 0;
-            for (int r = 0; r < cd.nseg; r++) total += ltu_estimate_from_matches(segs[cd.first_seg + r].len, matches[cd.first_seg + r]);
-            job.sizes[cd.index] = total;
-            if (total < best_size[cd.job - j0]) best_size[cd.job - j0] = total, job.best = order[cd.index];
+            job.best = order[0];
+            for (int c = 0; c < kMaxCandidates; c++) job.sizes[c] = 0;
+            if (job.len == 0) continue;
+            size_t best_size = SIZE_MAX;
+            for (int c = 0; c < k; c++) {
+                size_t total = 0;
+                for (int r = 0; r < js.nr; r++) {
+                    const size_t q = (size_t)js.first_seg + (size_t)js.plan.seg_of[(size_t)c * js.nr + r];
+                    total += ltu_estimate_from_matches(segs[q].len, matches[q]);
+                }
+                job.sizes[c] = total;
+                if (total < best_size) best_size = total, job.best = order[c];
+            }
         }
         work.clear();
         for (int j = j0; j < j1; j++)
