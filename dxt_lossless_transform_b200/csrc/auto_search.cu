@@ -59,15 +59,7 @@ int estimate_ranges(int format, size_t len, EstimateRange out[2]) {
 // The reference transforms and estimates every candidate (BC3: 8 / 16 x two ranges); estimates are a function of the
 // bytes, so estimating each DISTINCT range once and adding the shared results per candidate gives the same totals:
 // BC3 needs 2 alpha + 4 / 8 colour estimates and 4-5 / 9 transforms instead of 16 / 32 and 8 / 16.
-struct DistinctPlan {
-    struct Seg {
-        int cand, range;   // the candidate whose image holds the range
-    };
-    std::vector<Seg> segs;       // distinct ranges
-    std::vector<int> seg_of;     // [cand * nr + range] -> index into segs
-    std::vector<int> images;     // candidates that must be transformed (in candidate order)
-};
-static DistinctPlan plan_distinct(int format, const Settings* order, int k, int nr) {
+DistinctPlan plan_distinct(int format, const Settings* order, int k, int nr) {
     DistinctPlan p;
     p.seg_of.assign((size_t)k * nr, -1);
     auto key_of = [format](const Settings& s, int r) {

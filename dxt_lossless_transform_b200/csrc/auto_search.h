@@ -12,6 +12,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 
 #include "bcn_layout.h"
 #include "host_pipeline.h"
@@ -31,6 +32,18 @@ struct EstimateRange {
     size_t offset, len;
 };
 int estimate_ranges(int format, size_t len, EstimateRange out[2]);
+
+// Which candidates really differ in an estimated range (see auto_search.cu): segs = the distinct ranges, each held by
+// the image of candidate `cand`; seg_of[cand * nr + range] = its index in segs; images = the candidates to transform.
+struct DistinctPlan {
+    struct Seg {
+        int cand, range;
+    };
+    std::vector<Seg> segs;
+    std::vector<int> seg_of;
+    std::vector<int> images;
+};
+DistinctPlan plan_distinct(int format, const Settings* order, int k, int nr);
 
 // Device-resident search with the GPU LTU estimator.  d_in: len bytes of blocks; d_out: len bytes,
 // holds the winner's transform on return.  `sizes` (optional) receives the per-candidate estimates

@@ -188,63 +188,72 @@ Outcome auto_host(int format, const uint8_t* in, size_t in_len, uint8_t* out, si
         // dltzstd_new_size_estimator (zstd_estimator.cu): the callback is thread-safe and known, so every candidate is
         // compressed by its own host thread as soon as its endpoint streams have arrived — the reference's loop
         // (transform_auto.rs:230-262) compresses them one after another.  Same estimates, same strict-'<' selection.
+        // Only DISTINCT ranges are compressed (BC3: the alpha range depends on split_alpha alone, the colour range on
+        // variant + split_colour: 2 + 4 / 8 zstd passes instead of 16 / 32); zstd is deterministic, the per-candidate
+        // totals are the reference's.
         const int level = zstd_estimator_level(est);
-        size_t per = 0;
-        for (int r = 0; r < nr; r++) per += ranges[r].len;
-        constexpr size_t kHostBudget = (size_t)4 << 30;   // pinned candidate images + compression buffers in flight
-        const int wave = (int)std::min<size_t>((size_t)k, std::max<size_t>(1, kHostBudget / (per + max_comp + 1)));
-        if ((st = ensure_host_scratch(ctx, (size_t)wave * (per + max_comp))) != Status::kOk) return from_status(st);
-        uint8_t* images = ctx->h_scratch;
-        size_t totals[kMaxCandidates] = {};
-        uint32_t rcs[kMaxCandidates] = {};
-        cudaEvent_t arrived[kMaxCandidates] = {};
+        const DistinctPlan plan = plan_distinct(format, order, k, nr);
+        const int nseg = (int)plan.segs.size();
+        size_t largest = 0;
+        for (int r = 0; r < nr; r++) largest = std::max(largest, ranges[r].len);
+        const size_t per = (largest + 255) / 256 * 256 + (max_comp + 255) / 256 * 256;   // one range + its compression buffer
+        constexpr size_t kHostBudget = (size_t)4 << 30;   // pinned ranges + compression buffers in flight
+        const int wave = (int)std::min<size_t>((size_t)nseg, std::max<size_t>(1, kHostBudget / per));
+        if ((st = ensure_host_scratch(ctx, (size_t)wave * per)) != Status::kOk) return from_status(st);
+        std::vector<size_t> seg_size((size_t)nseg, 0);
+        std::vector<uint32_t> seg_rc((size_t)nseg, 0);
+        std::vector<cudaEvent_t> arrived((size_t)nseg, nullptr);
         Outcome failed = Outcome::kOk;
-        for (int c0 = 0; c0 < k && failed == Outcome::kOk; c0 += wave) {
-            const int wb = std::min(wave, k - c0);
+        int transformed = -1;   // candidate whose image currently sits in ctx->d_out
+        for (int q0 = 0; q0 < nseg && failed == Outcome::kOk; q0 += wave) {
+            const int wb = std::min(wave, nseg - q0);
             std::vector<std::thread> workers;
             workers.reserve(wb);
             for (int c = 0; c < wb; c++) {
-                const int i = c0 + c;
-                uint8_t* img = images + (size_t)c * (per + max_comp);
-                e = launch_transform(order[i], ctx->d_in, reference_layout(ctx->d_out, n, 0, order[i]), n, s);
-                size_t at = 0;
-                for (int r = 0; r < nr && e == cudaSuccess; r++) {
-                    e = cudaMemcpyAsync(img + at, ctx->d_out + ranges[r].offset, ranges[r].len, cudaMemcpyDeviceToHost, s);
-                    at += ranges[r].len;
+                const int q = q0 + c;
+                const DistinctPlan::Seg sg = plan.segs[q];   // segments are in candidate order: one transform per candidate
+                uint8_t* buf = ctx->h_scratch + (size_t)c * per;
+                e = cudaSuccess;
+                if (transformed != sg.cand) {
+                    e = launch_transform(order[sg.cand], ctx->d_in, reference_layout(ctx->d_out, n, 0, order[sg.cand]), n, s);
+                    transformed = sg.cand;
                 }
-                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&arrived[i], cudaEventDisableTiming);
-                if (e == cudaSuccess) e = cudaEventRecord(arrived[i], s);
+                const size_t rlen = ranges[sg.range].len;
+                if (e == cudaSuccess) e = cudaMemcpyAsync(buf, ctx->d_out + ranges[sg.range].offset, rlen, cudaMemcpyDeviceToHost, s);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&arrived[q], cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaEventRecord(arrived[q], s);
                 if (e != cudaSuccess) {
                     failed = cuda_fail(e);
                     break;
                 }
-                cudaEvent_t ev = arrived[i];
+                cudaEvent_t ev = arrived[q];
                 const int dev = ctx->device;
-                workers.emplace_back([=, &totals, &rcs, &ranges] {
+                uint8_t* comp_buf = buf + (largest + 255) / 256 * 256;
+                workers.emplace_back([=, &seg_size, &seg_rc] {
                     if (cudaSetDevice(dev) != cudaSuccess || cudaEventSynchronize(ev) != cudaSuccess) {
-                        rcs[i] = 3;
+                        seg_rc[q] = 3;
                         return;
                     }
-                    size_t off = 0, total = 0;
-                    for (int r = 0; r < nr; r++) {
-                        size_t sz = 0;
-                        const uint32_t rc = zstd_compressed_size(level, img + off, ranges[r].len, img + per, max_comp, &sz);
-                        if (rc != 0) rcs[i] = rc;
-                        total += sz, off += ranges[r].len;
-                    }
-                    totals[i] = total;
+                    size_t sz = 0;
+                    seg_rc[q] = zstd_compressed_size(level, buf, rlen, comp_buf, max_comp, &sz);
+                    seg_size[q] = sz;
                 });
             }
             for (auto& w : workers) w.join();
             if (cudaStreamSynchronize(s) != cudaSuccess && failed == Outcome::kOk) failed = Outcome::kDevice;
         }
-        for (int i = 0; i < k; i++)
-            if (arrived[i]) cudaEventDestroy(arrived[i]);
+        for (cudaEvent_t ev : arrived)
+            if (ev) cudaEventDestroy(ev);
         if (failed != Outcome::kOk) return failed;
         size_t best_size = SIZE_MAX;
         for (int i = 0; i < k; i++) {
-            if (rcs[i] != 0) return Outcome::kEstimator;
-            if (totals[i] < best_size) best_size = totals[i], best_s = order[i];
+            size_t total = 0;
+            for (int r = 0; r < nr; r++) {
+                const int q = plan.seg_of[(size_t)i * nr + r];
+                if (seg_rc[q] != 0) return Outcome::kEstimator;
+                total += seg_size[q];
+            }
+            if (total < best_size) best_size = total, best_s = order[i];
         }
         e = launch_transform(best_s, ctx->d_in, reference_layout(ctx->d_out, n, 0, best_s), n, s);
         if (e != cudaSuccess) return cuda_fail(e);
