@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(32) ltu_scan_filter_kernel(const SmallBatch ba
 // nskip > 0 ("follower") sees what the first same-bucket record of its group ("leader") saw, which the thread keeps
 // in a three-record history.  A follower belongs to the piece that owns its leader, so pieces hand over cleanly: a
 // piece skips leading followers of a foreign leader and processes up to three trailing followers of its own.
-constexpr int kMaxSegs = 64;               // segments per launch set (the batch descriptor is a ~7 KiB kernel parameter)
+constexpr int kMaxSegs = 256;              // segments per launch set (the batch descriptor is a ~28 KiB kernel parameter; limit 32,764 B)
 constexpr int kTile = 8192;              // records per CTA tile of the partition pass
 constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;

@@ -39,7 +39,7 @@ public:
     size_t bytes() const;
 
 private:
-    static constexpr int kSet = 64;   // == kMaxSegs of estimator.cu (static_assert there)
+    static constexpr int kSet = 256;   // == kMaxSegs of estimator.cu (static_assert there)
     size_t nseg_ = 0, closed_bytes_ = 0, open_len_[kSet] = {};
     int open_ = 0;
 };
