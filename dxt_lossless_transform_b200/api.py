@@ -631,6 +631,19 @@ def ltu_estimate_device(d_data: int, nbytes: int) -> int:
     return out.value
 
 
+def ltu_set_params(hash_bits: int = 16, index_top: bool = True, group: int = 4) -> None:
+    """Process-wide parameters of the LTU-semantics estimator (dltcuda_ltu_set_params): the parts of the restated
+    third-party algorithm that are unverified.  Defaults = the restatement."""
+    if N.lib().dltcuda_ltu_set_params(hash_bits, index_top, group) != 0:
+        raise ValueError(f"unsupported LTU parameters: hash_bits={hash_bits} index_top={index_top} group={group}")
+
+
+def ltu_get_params():
+    h, t, g = C.c_int(0), C.c_bool(False), C.c_int(0)
+    N.lib().dltcuda_ltu_get_params(C.byref(h), C.byref(t), C.byref(g))
+    return h.value, t.value, g.value
+
+
 def auto_candidates(fmt: int, use_all: bool):
     arr = (N.DltcudaSettings * 16)()
     k = N.lib().dltcuda_auto_candidates(fmt, use_all, arr)

@@ -14,16 +14,15 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libdxt_lossless_transform_cuda.so"
-SOURCES = ["bcn_kernels.cu", "host_pipeline.cu", "estimator.cu", "auto_search.cu", "cabi.cu", "file_formats.cu", "zstd_estimator.cu"]
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
-    "--threads", "0",
-    "-ldl",
-    "-diag-suppress", "177",  # unused static members of the layout helper in some instantiations
-]
+
+def _lines(name: str) -> list[str]:
+    return [l.strip() for l in (CSRC / name).read_text().splitlines() if l.strip() and not l.startswith("#")]
+
+
+# One list of sources and flags for this build and for the Rust crate's build.rs (rust/dxt-lossless-transform-cuda).
+SOURCES = _lines("SOURCES.txt")
+NVCC_FLAGS = _lines("NVCC_FLAGS.txt")  # -diag-suppress 177: unused static members of the layout helper in some instantiations
 
 
 def find_nvcc() -> str:
@@ -37,7 +36,7 @@ def needs_build() -> bool:
     if not LIB_PATH.exists():
         return True
     built = LIB_PATH.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [Path(__file__)]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.txt")) + [Path(__file__)]
     return any(p.stat().st_mtime > built for p in deps)
 
 

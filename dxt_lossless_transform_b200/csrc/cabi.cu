@@ -759,6 +759,19 @@ DLT_EXPORT int dltcuda_ltu_estimate_device(const uint8_t* d_data, size_t len, si
     return dltcuda_status(st);
 }
 
+// The unverified parts of the restated LTU algorithm as run-time parameters (estimator.h LtuParams).
+DLT_EXPORT int dltcuda_ltu_set_params(int hash_bits, bool index_from_top_bits, int group) {
+    LtuParams p;
+    p.hash_bits = hash_bits, p.index_top = index_from_top_bits, p.group = group;
+    return ltu_set_params(p) ? kDltcudaOk : kDltcudaInvalidSettings;
+}
+DLT_EXPORT void dltcuda_ltu_get_params(int* hash_bits, bool* index_from_top_bits, int* group) {
+    const LtuParams p = ltu_params();
+    if (hash_bits) *hash_bits = p.hash_bits;
+    if (index_from_top_bits) *index_from_top_bits = p.index_top;
+    if (group) *group = p.group;
+}
+
 // transform_bcN_auto with the GPU LTU estimator on device-resident buffers.  out_estimates (optional)
 // receives the per-candidate estimates in the reference's test order (4/8 for BC1,BC2; 8/16 for BC3).
 // Synchronous; d_output holds the winner's transform on return.

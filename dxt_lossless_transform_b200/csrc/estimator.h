@@ -4,7 +4,7 @@
 // (extensions/estimators/dxt-lossless-transform-ltu/src/lib.rs:67-119):
 //     estimate(data) = data.len().saturating_sub(estimate_num_lz_matches_fast(data)),  0 if empty
 // where estimate_num_lz_matches_fast lives in the third-party crate lossless-transform-utils 0.1.3
-// (not under /root/reference; restated — PARITY UNPINNED, see DESIGN.md and the LTU_* constants).
+// (not under /root/reference; restated — PARITY UNPINNED, see DESIGN.md and LtuParams below).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -15,33 +15,46 @@
 
 namespace dlt {
 
-// The five constants of the restated algorithm (kept in one place; oracle/ltu_params.h mirrors them).
-constexpr int kLtuHashBits = 16;
+// Fixed parts of the restated algorithm (oracle/ltu_params.h mirrors them).
 constexpr uint32_t kLtuGoldenRatio = 0x9E3779B1u;
 constexpr uint32_t kLtuKeyMask = 0x00FFFFFFu;
-constexpr int kLtuGroup = 4;      // positions compared, then written, per loop iteration
 constexpr int kLtuTailGuard = 7;  // loop runs while i < len.saturating_sub(7)
+
+// The parts of the restatement that could not be checked against the crate's source are RUN-TIME parameters of
+// the estimator (and of the oracle, oracle/bcn_oracle.c orc_ltu_num_lz_matches_params): the day the crate's
+// source is at hand, parity is a call to ltu_set_params(), not a redesign.
+//   hash_bits  : log2 of the table size, 12..17
+//   index_top  : true  -> index = (key * GOLDEN) >> (32 - hash_bits)
+//                false -> index = (key * GOLDEN) & ((1 << hash_bits) - 1)
+//   group      : positions per loop iteration (all compares of a group see the table as it was before the group,
+//                then the group's updates are applied in order): 4 or 1
+struct LtuParams {
+    int hash_bits = 16;
+    bool index_top = true;
+    int group = 4;
+};
+bool ltu_params_supported(const LtuParams& p);
+bool ltu_set_params(const LtuParams& p);   // process-wide; false (and no change) if unsupported
+LtuParams ltu_params();
 
 struct LtuSegment {
     const uint8_t* d_ptr;  // device pointer
     size_t len;
 };
 
-// Device scratch the call below needs for these segments (sort buffers: ~8.2 bytes per position).
+// Device scratch the call below needs for these segments (chunk descriptors and, for segments that are cut into
+// several chunks, 640 KiB of hand-over state per chunk: far below one byte per position).
 size_t ltu_scratch_bytes(const LtuSegment* segs, int nseg);
 
-// The same figure kept incrementally while a caller appends segments (launch sets are formed in input order, so
-// appending a segment only changes the last, still open set): O(1) per segment instead of re-planning all of them.
-// bytes() == ltu_scratch_bytes() of the segments added so far.  Cheap to copy (try a job, keep or drop the copy).
+// An upper bound of the same figure kept incrementally while a caller appends segments: O(1) per segment.
+// bytes() >= ltu_scratch_bytes() of the segments added so far.  Cheap to copy (try a job, keep or drop the copy).
 class LtuScratchMeter {
 public:
     void add(size_t len);
     size_t bytes() const;
 
 private:
-    static constexpr int kSet = 256;   // == kMaxSegs of estimator.cu (static_assert there)
-    size_t nseg_ = 0, closed_bytes_ = 0, open_len_[kSet] = {};
-    int open_ = 0;
+    size_t nseg_ = 0, batches_ = 0;
 };
 
 // Number of LZ matches of each device-resident segment, written to host `matches[0..nseg)`.

@@ -123,6 +123,17 @@ int dltcuda_transform_batch_multi_gpu(const DltcudaPayload *payloads, size_t cou
 /* ---- estimator / best-settings search, device resident ------------------------------------------ */
 /* LTU-semantics estimate (dxt_lossless_transform_ltu.h) of `len` device bytes.  Synchronous. */
 int dltcuda_ltu_estimate_device(const uint8_t *d_data, size_t len, size_t *out_size);
+/* The estimator restates `estimate_num_lz_matches_fast` of the third-party crate lossless-transform-utils 0.1.3, whose
+ * source is not in the reference tree (PARITY UNPINNED).  The parts of the restatement that could not
+ * be checked are run-time parameters, process-wide, so that pinning parity later is a call, not a redesign:
+ *   hash_bits 12..17 (table of 1 << hash_bits entries; default 16)
+ *   index_from_top_bits: true  -> index = (key * 0x9E3779B1) >> (32 - hash_bits)   (default)
+ *                        false -> index = (key * 0x9E3779B1) & ((1 << hash_bits) - 1)
+ *   group 4 or 1: positions per loop iteration (all compares of an iteration precede its updates; default 4)
+ * Returns DltcudaStatus_Ok, or DltcudaStatus_InvalidSettings (nothing changed) for an unsupported combination.
+ * Must not be called while another thread is inside an estimating call. */
+int dltcuda_ltu_set_params(int hash_bits, bool index_from_top_bits, int group);
+void dltcuda_ltu_get_params(int *hash_bits, bool *index_from_top_bits, int *group);
 /* transform_bcN_auto (bc1 transform_auto.rs:200, bc2 :196, bc3 :196) with the LTU estimator, all on
  * the device.  out_estimates (optional, >= 16 entries) receives the per-candidate estimates in the
  * reference's test order.  Synchronous; d_output holds the winner's transform on return. */

@@ -316,6 +316,315 @@ static void bc1_range_avx2(int inverse, const uint8_t *in, uint8_t *out, size_t 
 #endif
 int orc_cpu_baseline_uses_avx2(void) { return have_avx2(); }
 
+/* ------------------------------------------------------------------------------------------
+ * AVX-512 paths for the CPU BASELINE timing — what the reference itself runs on an AVX-512 host (its best tier):
+ *   BC1  32 blocks per iteration: four 64-byte loads, vpermt2d (colours / indices), vpermt2w (c0 / c1), YCoCg-R on 32
+ *        16-bit lanes — the shape of core/dxt-lossless-transform-bc1/src/transform/with_split_colour_and_recorr/
+ *        transform/avx512bw.rs and standard/transform/avx512f.rs:40-106, restated;
+ *   BC2  16 blocks per iteration: vpermt2q (alpha), vpermt2d (colour part) — bc2 standard/transform/avx512*.rs;
+ *   BC3  16 blocks per iteration: one vpermt2b per eight blocks gathers the alpha endpoints and the 6-byte alpha
+ *        indices — core/dxt-lossless-transform-bc3/src/transform/standard/transform/avx512vbmi.rs, restated; the five
+ *        variants the reference only has in scalar form get the same vector loop here, so the CPU arm is
+ *        never slower than the reference would be.
+ * Selected at run time (avx512bw + avx512vbmi); tests/test_oracle.py checks every settings combination, both
+ * directions, odd block counts and unaligned buffers against the scalar restatement above.
+ * ---------------------------------------------------------------------------------------- */
+#if defined(__x86_64__)
+#define ORC_AVX512 __attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,avx512vbmi")))
+
+ORC_AVX512 static inline __m512i decorr32(__m512i v, int variant) {
+    const __m512i m5 = _mm512_set1_epi16(31), m1 = _mm512_set1_epi16(1);
+    __m512i r = _mm512_srli_epi16(v, 11), g = _mm512_and_si512(_mm512_srli_epi16(v, 6), m5);
+    __m512i gl = _mm512_and_si512(_mm512_srli_epi16(v, 5), m1), b = _mm512_and_si512(v, m5);
+    __m512i co = _mm512_and_si512(_mm512_sub_epi16(r, b), m5);
+    __m512i t = _mm512_and_si512(_mm512_add_epi16(b, _mm512_srli_epi16(co, 1)), m5);
+    __m512i cg = _mm512_and_si512(_mm512_sub_epi16(g, t), m5);
+    __m512i y = _mm512_and_si512(_mm512_add_epi16(t, _mm512_srli_epi16(cg, 1)), m5);
+    if (variant == ORC_VARIANT_1)
+        return _mm512_or_si512(_mm512_or_si512(_mm512_slli_epi16(y, 11), _mm512_slli_epi16(co, 6)), _mm512_or_si512(_mm512_slli_epi16(gl, 5), cg));
+    if (variant == ORC_VARIANT_2)
+        return _mm512_or_si512(_mm512_or_si512(_mm512_slli_epi16(gl, 15), _mm512_slli_epi16(y, 10)), _mm512_or_si512(_mm512_slli_epi16(co, 5), cg));
+    return _mm512_or_si512(_mm512_or_si512(_mm512_slli_epi16(y, 11), _mm512_slli_epi16(co, 6)), _mm512_or_si512(_mm512_slli_epi16(cg, 1), gl));
+}
+ORC_AVX512 static inline __m512i recorr32(__m512i v, int variant) {
+    const __m512i m5 = _mm512_set1_epi16(31), m1 = _mm512_set1_epi16(1);
+    __m512i y, co, cg, gl;
+    if (variant == ORC_VARIANT_1) {
+        y = _mm512_srli_epi16(v, 11), co = _mm512_and_si512(_mm512_srli_epi16(v, 6), m5);
+        gl = _mm512_and_si512(_mm512_srli_epi16(v, 5), m1), cg = _mm512_and_si512(v, m5);
+    } else if (variant == ORC_VARIANT_2) {
+        gl = _mm512_srli_epi16(v, 15), y = _mm512_and_si512(_mm512_srli_epi16(v, 10), m5);
+        co = _mm512_and_si512(_mm512_srli_epi16(v, 5), m5), cg = _mm512_and_si512(v, m5);
+    } else {
+        y = _mm512_srli_epi16(v, 11), co = _mm512_and_si512(_mm512_srli_epi16(v, 6), m5);
+        cg = _mm512_and_si512(_mm512_srli_epi16(v, 1), m5), gl = _mm512_and_si512(v, m1);
+    }
+    __m512i t = _mm512_and_si512(_mm512_sub_epi16(y, _mm512_srli_epi16(cg, 1)), m5);
+    __m512i g = _mm512_and_si512(_mm512_add_epi16(cg, t), m5);
+    __m512i b = _mm512_and_si512(_mm512_sub_epi16(t, _mm512_srli_epi16(co, 1)), m5);
+    __m512i r = _mm512_and_si512(_mm512_add_epi16(b, co), m5);
+    return _mm512_or_si512(_mm512_or_si512(_mm512_slli_epi16(r, 11), _mm512_slli_epi16(g, 6)), _mm512_or_si512(_mm512_slli_epi16(gl, 5), b));
+}
+
+/* index vectors (built once per call; a few dozen scalar stores against megabytes of payload) */
+typedef struct {
+    __m512i even_d, odd_d;        /* dwords 0,2,..,30 / 1,3,..,31 of a register pair */
+    __m512i even_w, odd_w;        /* words 0,2,..,62 / 1,3,..,63 of a pair */
+    __m512i zip_w_lo, zip_w_hi;   /* words (0,32,1,33,..) / (16,48,17,49,..): c0|c1 -> pairs */
+    __m512i zip_d_lo, zip_d_hi;   /* dwords (0,16,1,17,..) / (8,24,..): colours|indices -> blocks */
+    __m512i split_w, unsplit_w;   /* one register: words (0,2,..,30,1,3,..,31) and its inverse */
+    __m512i even_q;               /* qwords 0,2,..,14 of a pair */
+    __m512i colidx_d;             /* BC2/BC3: dwords 2,6,..,30 then 3,7,..,31 of a pair */
+    __m512i lo_q, hi_q;           /* qwords (0,1,2,3,8,9,10,11) / (4,..,7,12,..,15) of a pair */
+    __m512i bc2_z_lo, bc2_z_hi;   /* (alpha qwords, colour|index) -> blocks 0..3 / 4..7 */
+} orc_idx512;
+
+ORC_AVX512 static void orc_idx512_init(orc_idx512 *t) {
+    uint32_t d[16];
+    uint16_t w[32];
+    uint64_t q[8];
+    for (int i = 0; i < 16; i++) d[i] = 2 * i;
+    t->even_d = _mm512_loadu_si512(d);
+    for (int i = 0; i < 16; i++) d[i] = 2 * i + 1;
+    t->odd_d = _mm512_loadu_si512(d);
+    for (int i = 0; i < 32; i++) w[i] = 2 * i;
+    t->even_w = _mm512_loadu_si512(w);
+    for (int i = 0; i < 32; i++) w[i] = 2 * i + 1;
+    t->odd_w = _mm512_loadu_si512(w);
+    for (int i = 0; i < 16; i++) w[2 * i] = i, w[2 * i + 1] = 32 + i;
+    t->zip_w_lo = _mm512_loadu_si512(w);
+    for (int i = 0; i < 16; i++) w[2 * i] = 16 + i, w[2 * i + 1] = 48 + i;
+    t->zip_w_hi = _mm512_loadu_si512(w);
+    for (int i = 0; i < 8; i++) d[2 * i] = i, d[2 * i + 1] = 16 + i;
+    t->zip_d_lo = _mm512_loadu_si512(d);
+    for (int i = 0; i < 8; i++) d[2 * i] = 8 + i, d[2 * i + 1] = 24 + i;
+    t->zip_d_hi = _mm512_loadu_si512(d);
+    for (int i = 0; i < 16; i++) w[i] = 2 * i, w[16 + i] = 2 * i + 1;
+    t->split_w = _mm512_loadu_si512(w);
+    for (int i = 0; i < 16; i++) w[2 * i] = i, w[2 * i + 1] = 16 + i;
+    t->unsplit_w = _mm512_loadu_si512(w);
+    for (int i = 0; i < 8; i++) q[i] = 2 * i;
+    t->even_q = _mm512_loadu_si512(q);
+    for (int i = 0; i < 8; i++) d[i] = 4 * i + 2, d[8 + i] = 4 * i + 3;
+    t->colidx_d = _mm512_loadu_si512(d);
+    for (int i = 0; i < 4; i++) q[i] = i, q[4 + i] = 8 + i;
+    t->lo_q = _mm512_loadu_si512(q);
+    for (int i = 0; i < 4; i++) q[i] = 4 + i, q[4 + i] = 12 + i;
+    t->hi_q = _mm512_loadu_si512(q);
+    for (int k = 0; k < 4; k++) d[4 * k] = 2 * k, d[4 * k + 1] = 2 * k + 1, d[4 * k + 2] = 16 + k, d[4 * k + 3] = 24 + k;
+    t->bc2_z_lo = _mm512_loadu_si512(d);
+    for (int k = 0; k < 4; k++) d[4 * k] = 8 + 2 * k, d[4 * k + 1] = 9 + 2 * k, d[4 * k + 2] = 20 + k, d[4 * k + 3] = 28 + k;
+    t->bc2_z_hi = _mm512_loadu_si512(d);
+}
+
+#define BC1_AVX512_LOOP(VARIANT)                                                                                     \
+    for (; i + 32 <= b1; i += 32) {                                                                                  \
+        if (!inverse) {                                                                                              \
+            const __m512i z0 = _mm512_loadu_si512(in + 8 * i), z1 = _mm512_loadu_si512(in + 8 * i + 64);             \
+            const __m512i z2 = _mm512_loadu_si512(in + 8 * i + 128), z3 = _mm512_loadu_si512(in + 8 * i + 192);      \
+            __m512i ca = _mm512_permutex2var_epi32(z0, T.even_d, z1), cb = _mm512_permutex2var_epi32(z2, T.even_d, z3); \
+            const __m512i xa = _mm512_permutex2var_epi32(z0, T.odd_d, z1), xb = _mm512_permutex2var_epi32(z2, T.odd_d, z3); \
+            if (VARIANT) ca = decorr32(ca, VARIANT), cb = decorr32(cb, VARIANT);                                     \
+            if (split) {                                                                                             \
+                _mm512_storeu_si512(out + 2 * i, _mm512_permutex2var_epi16(ca, T.even_w, cb));                       \
+                _mm512_storeu_si512(out + len / 4 + 2 * i, _mm512_permutex2var_epi16(ca, T.odd_w, cb));              \
+            } else {                                                                                                 \
+                _mm512_storeu_si512(out + 4 * i, ca);                                                                \
+                _mm512_storeu_si512(out + 4 * i + 64, cb);                                                           \
+            }                                                                                                        \
+            _mm512_storeu_si512(out + len / 2 + 4 * i, xa);                                                          \
+            _mm512_storeu_si512(out + len / 2 + 4 * i + 64, xb);                                                     \
+        } else {                                                                                                     \
+            __m512i ca, cb;                                                                                          \
+            if (split) {                                                                                             \
+                const __m512i c0 = _mm512_loadu_si512(in + 2 * i), c1 = _mm512_loadu_si512(in + len / 4 + 2 * i);    \
+                ca = _mm512_permutex2var_epi16(c0, T.zip_w_lo, c1), cb = _mm512_permutex2var_epi16(c0, T.zip_w_hi, c1); \
+            } else ca = _mm512_loadu_si512(in + 4 * i), cb = _mm512_loadu_si512(in + 4 * i + 64);                    \
+            const __m512i xa = _mm512_loadu_si512(in + len / 2 + 4 * i), xb = _mm512_loadu_si512(in + len / 2 + 4 * i + 64); \
+            if (VARIANT) ca = recorr32(ca, VARIANT), cb = recorr32(cb, VARIANT);                                     \
+            _mm512_storeu_si512(out + 8 * i, _mm512_permutex2var_epi32(ca, T.zip_d_lo, xa));                         \
+            _mm512_storeu_si512(out + 8 * i + 64, _mm512_permutex2var_epi32(ca, T.zip_d_hi, xa));                    \
+            _mm512_storeu_si512(out + 8 * i + 128, _mm512_permutex2var_epi32(cb, T.zip_d_lo, xb));                   \
+            _mm512_storeu_si512(out + 8 * i + 192, _mm512_permutex2var_epi32(cb, T.zip_d_hi, xb));                   \
+        }                                                                                                            \
+    }
+
+ORC_AVX512 static void bc1_range_avx512(int inverse, const uint8_t *restrict in, uint8_t *restrict out, size_t n, size_t b0,
+                                        size_t b1, int variant, int split) {
+    const size_t len = n * 8;
+    orc_idx512 T;
+    orc_idx512_init(&T);
+    size_t i = b0;
+    switch (variant) {
+    case ORC_VARIANT_NONE: BC1_AVX512_LOOP(0) break;
+    case ORC_VARIANT_1: BC1_AVX512_LOOP(1) break;
+    case ORC_VARIANT_2: BC1_AVX512_LOOP(2) break;
+    default: BC1_AVX512_LOOP(3) break;
+    }
+    if (i < b1) bc1_range_fast(inverse, in, out, n, i, b1, variant, split);   /* < 32 blocks left */
+}
+
+/* colour part shared by BC2 and BC3: 16 blocks, colours at byte 8 and indices at byte 12 of every 16-byte block;
+ * cso / c1o / ixo are the byte offsets of the colour (or c0), c1 and index sections */
+#define BCX_COLOURS_FWD(VARIANT)                                                                                     \
+    {                                                                                                                \
+        const __m512i t01 = _mm512_permutex2var_epi32(z0, T.colidx_d, z1), t23 = _mm512_permutex2var_epi32(z2, T.colidx_d, z3); \
+        __m512i col = _mm512_permutex2var_epi64(t01, T.lo_q, t23);                                                   \
+        const __m512i idx = _mm512_permutex2var_epi64(t01, T.hi_q, t23);                                             \
+        if (VARIANT) col = decorr32(col, VARIANT);                                                                   \
+        if (split_c) {                                                                                               \
+            const __m512i s = _mm512_permutexvar_epi16(T.split_w, col);                                              \
+            _mm256_storeu_si256((__m256i *)(out + cso + 2 * i), _mm512_castsi512_si256(s));                          \
+            _mm256_storeu_si256((__m256i *)(out + c1o + 2 * i), _mm512_extracti64x4_epi64(s, 1));                    \
+        } else _mm512_storeu_si512(out + cso + 4 * i, col);                                                          \
+        _mm512_storeu_si512(out + ixo + 4 * i, idx);                                                                 \
+    }
+#define BCX_COLOURS_INV(VARIANT)                                                                                     \
+    __m512i col;                                                                                                     \
+    if (split_c) {                                                                                                   \
+        const __m512i s = _mm512_inserti64x4(_mm512_castsi256_si512(_mm256_loadu_si256((const __m256i *)(in + cso + 2 * i))), \
+                                             _mm256_loadu_si256((const __m256i *)(in + c1o + 2 * i)), 1);           \
+        col = _mm512_permutexvar_epi16(T.unsplit_w, s);                                                              \
+    } else col = _mm512_loadu_si512(in + cso + 4 * i);                                                               \
+    const __m512i idx = _mm512_loadu_si512(in + ixo + 4 * i);                                                        \
+    if (VARIANT) col = recorr32(col, VARIANT);                                                                       \
+    const __m512i t01 = _mm512_permutex2var_epi64(col, T.lo_q, idx), t23 = _mm512_permutex2var_epi64(col, T.hi_q, idx);
+
+#define BC2_AVX512_LOOP(VARIANT)                                                                                     \
+    for (; i + 16 <= b1; i += 16) {                                                                                  \
+        if (!inverse) {                                                                                              \
+            const __m512i z0 = _mm512_loadu_si512(in + 16 * i), z1 = _mm512_loadu_si512(in + 16 * i + 64);           \
+            const __m512i z2 = _mm512_loadu_si512(in + 16 * i + 128), z3 = _mm512_loadu_si512(in + 16 * i + 192);    \
+            _mm512_storeu_si512(out + 8 * i, _mm512_permutex2var_epi64(z0, T.even_q, z1));                           \
+            _mm512_storeu_si512(out + 8 * i + 64, _mm512_permutex2var_epi64(z2, T.even_q, z3));                      \
+            BCX_COLOURS_FWD(VARIANT)                                                                                 \
+        } else {                                                                                                     \
+            const __m512i a01 = _mm512_loadu_si512(in + 8 * i), a23 = _mm512_loadu_si512(in + 8 * i + 64);           \
+            BCX_COLOURS_INV(VARIANT)                                                                                 \
+            _mm512_storeu_si512(out + 16 * i, _mm512_permutex2var_epi32(a01, T.bc2_z_lo, t01));                      \
+            _mm512_storeu_si512(out + 16 * i + 64, _mm512_permutex2var_epi32(a01, T.bc2_z_hi, t01));                 \
+            _mm512_storeu_si512(out + 16 * i + 128, _mm512_permutex2var_epi32(a23, T.bc2_z_lo, t23));                \
+            _mm512_storeu_si512(out + 16 * i + 192, _mm512_permutex2var_epi32(a23, T.bc2_z_hi, t23));                \
+        }                                                                                                            \
+    }
+
+ORC_AVX512 static void bc2_range_avx512(int inverse, const uint8_t *restrict in, uint8_t *restrict out, size_t n, size_t b0,
+                                        size_t b1, int variant, int split_c) {
+    const size_t len = n * 16, cso = len / 2, c1o = len / 2 + len / 8, ixo = len / 2 + len / 4;
+    orc_idx512 T;
+    orc_idx512_init(&T);
+    size_t i = b0;
+    switch (variant) {
+    case ORC_VARIANT_NONE: BC2_AVX512_LOOP(0) break;
+    case ORC_VARIANT_1: BC2_AVX512_LOOP(1) break;
+    case ORC_VARIANT_2: BC2_AVX512_LOOP(2) break;
+    default: BC2_AVX512_LOOP(3) break;
+    }
+    if (i < b1) bc2_range(inverse, in, out, n, i, b1, variant, split_c);
+}
+
+/* BC3 alpha part, eight blocks (two registers) at a time with vpermt2b.
+ *   forward : P = [endpoint bytes: 16 | alpha index bytes: 48]   (split_a: a0 x 8 | a1 x 8 | indices)
+ *   inverse : block register = vpermt2b(P, sel, T) with T = [colours of 8 blocks : 32 | indices : 32]            */
+typedef struct {
+    __m512i fwd;          /* (z_lo, z_hi) -> P */
+    __m512i inv_lo, inv_hi; /* (P, T) -> blocks 0..3 / 4..7 */
+} orc_bc3_sel;
+ORC_AVX512 static void orc_bc3_sel_init(orc_bc3_sel *s, int split_a) {
+    uint8_t f[64], lo[64], hi[64];
+    for (int b = 0; b < 8; b++) {
+        const int src = 16 * b;   /* byte index in the concatenation (z_lo, z_hi): vpermt2b takes 7 index bits */
+        const int e0 = split_a ? b : 2 * b, e1 = split_a ? 8 + b : 2 * b + 1;
+        f[e0] = (uint8_t)src, f[e1] = (uint8_t)(src + 1);
+        for (int k = 0; k < 6; k++) f[16 + 6 * b + k] = (uint8_t)(src + 2 + k);
+        uint8_t *z = b < 4 ? lo + 16 * b : hi + 16 * (b - 4);
+        z[0] = (uint8_t)e0, z[1] = (uint8_t)e1;
+        for (int k = 0; k < 6; k++) z[2 + k] = (uint8_t)(16 + 6 * b + k);
+        for (int k = 0; k < 4; k++) z[8 + k] = (uint8_t)(64 + 4 * b + k), z[12 + k] = (uint8_t)(64 + 32 + 4 * b + k);
+    }
+    s->fwd = _mm512_loadu_si512(f), s->inv_lo = _mm512_loadu_si512(lo), s->inv_hi = _mm512_loadu_si512(hi);
+}
+
+#define BC3_AVX512_LOOP(VARIANT)                                                                                     \
+    for (; i + 16 <= b1; i += 16) {                                                                                  \
+        if (!inverse) {                                                                                              \
+            const __m512i z0 = _mm512_loadu_si512(in + 16 * i), z1 = _mm512_loadu_si512(in + 16 * i + 64);           \
+            const __m512i z2 = _mm512_loadu_si512(in + 16 * i + 128), z3 = _mm512_loadu_si512(in + 16 * i + 192);    \
+            const __m512i p01 = _mm512_permutex2var_epi8(z0, S.fwd, z1), p23 = _mm512_permutex2var_epi8(z2, S.fwd, z3); \
+            const __m128i e01 = _mm512_castsi512_si128(p01), e23 = _mm512_castsi512_si128(p23);                      \
+            if (split_a) {                                                                                           \
+                _mm_storeu_si128((__m128i *)(out + i), _mm_unpacklo_epi64(e01, e23));                                \
+                _mm_storeu_si128((__m128i *)(out + n + i), _mm_unpackhi_epi64(e01, e23));                            \
+            } else {                                                                                                 \
+                _mm_storeu_si128((__m128i *)(out + 2 * i), e01);                                                     \
+                _mm_storeu_si128((__m128i *)(out + 2 * i + 16), e23);                                                \
+            }                                                                                                        \
+            /* 48 index bytes each: bytes 16..63 of the register land at aio + 6 i (the masked-off bytes are never touched) */ \
+            _mm512_mask_storeu_epi8(out + aio + 6 * i - 16, 0xFFFFFFFFFFFF0000ull, p01);                             \
+            _mm512_mask_storeu_epi8(out + aio + 6 * i + 48 - 16, 0xFFFFFFFFFFFF0000ull, p23);                        \
+            BCX_COLOURS_FWD(VARIANT)                                                                                 \
+        } else {                                                                                                     \
+            __m128i e01, e23;                                                                                        \
+            if (split_a) {                                                                                           \
+                const __m128i a0 = _mm_loadu_si128((const __m128i *)(in + i)), a1 = _mm_loadu_si128((const __m128i *)(in + n + i)); \
+                e01 = _mm_unpacklo_epi64(a0, a1), e23 = _mm_unpackhi_epi64(a0, a1);                                  \
+            } else e01 = _mm_loadu_si128((const __m128i *)(in + 2 * i)), e23 = _mm_loadu_si128((const __m128i *)(in + 2 * i + 16)); \
+            const __m512i p01 = _mm512_mask_loadu_epi8(_mm512_castsi128_si512(e01), 0xFFFFFFFFFFFF0000ull, in + aio + 6 * i - 16); \
+            const __m512i p23 = _mm512_mask_loadu_epi8(_mm512_castsi128_si512(e23), 0xFFFFFFFFFFFF0000ull, in + aio + 6 * i + 48 - 16); \
+            BCX_COLOURS_INV(VARIANT)                                                                                 \
+            _mm512_storeu_si512(out + 16 * i, _mm512_permutex2var_epi8(p01, S.inv_lo, t01));                         \
+            _mm512_storeu_si512(out + 16 * i + 64, _mm512_permutex2var_epi8(p01, S.inv_hi, t01));                    \
+            _mm512_storeu_si512(out + 16 * i + 128, _mm512_permutex2var_epi8(p23, S.inv_lo, t23));                   \
+            _mm512_storeu_si512(out + 16 * i + 192, _mm512_permutex2var_epi8(p23, S.inv_hi, t23));                   \
+        }                                                                                                            \
+    }
+
+ORC_AVX512 static void bc3_range_avx512(int inverse, const uint8_t *restrict in, uint8_t *restrict out, size_t n, size_t b0,
+                                        size_t b1, int variant, int split_a, int split_c) {
+    const size_t aio = 2 * n, cso = 8 * n, c1o = 10 * n, ixo = 12 * n;
+    orc_idx512 T;
+    orc_bc3_sel S;
+    orc_idx512_init(&T);
+    orc_bc3_sel_init(&S, split_a);
+    size_t i = b0;
+    switch (variant) {
+    case ORC_VARIANT_NONE: BC3_AVX512_LOOP(0) break;
+    case ORC_VARIANT_1: BC3_AVX512_LOOP(1) break;
+    case ORC_VARIANT_2: BC3_AVX512_LOOP(2) break;
+    default: BC3_AVX512_LOOP(3) break;
+    }
+    if (i < b1) bc3_range(inverse, in, out, n, i, b1, variant, split_a, split_c);
+}
+static int have_avx512(void) {
+    return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") &&
+           __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512vbmi");
+}
+#else
+static int have_avx512(void) { return 0; }
+static void bc1_range_avx512(int inverse, const uint8_t *in, uint8_t *out, size_t n, size_t b0, size_t b1, int variant, int split) {
+    bc1_range_fast(inverse, in, out, n, b0, b1, variant, split);
+}
+static void bc2_range_avx512(int inverse, const uint8_t *in, uint8_t *out, size_t n, size_t b0, size_t b1, int variant, int split) {
+    bc2_range(inverse, in, out, n, b0, b1, variant, split);
+}
+static void bc3_range_avx512(int inverse, const uint8_t *in, uint8_t *out, size_t n, size_t b0, size_t b1, int variant, int sa, int sc) {
+    bc3_range(inverse, in, out, n, b0, b1, variant, sa, sc);
+}
+#endif
+/* 0: scalar / word-wise, 2: AVX2 (BC1 only), 5: AVX-512 (BC1, BC2, BC3).  ORC_ISA=scalar|avx2 caps it (tests). */
+static int baseline_isa(void) {
+    static int isa = -1;
+    if (isa < 0) {
+        int best = have_avx512() ? 5 : have_avx2() ? 2 : 0;
+        const char *cap = getenv("ORC_ISA");
+        if (cap && !strcmp(cap, "scalar")) best = 0;
+        if (cap && !strcmp(cap, "avx2") && best > 2) best = 2;
+        isa = best;
+    }
+    return isa;
+}
+int orc_cpu_baseline_isa(void) { return baseline_isa(); }
+
 void orc_bc1_transform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc1_range(0, in, out, len / 8, 0, len / 8, v, s); }
 void orc_bc1_untransform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc1_range(1, in, out, len / 8, 0, len / 8, v, s); }
 void orc_bc2_transform(const uint8_t *in, uint8_t *out, size_t len, int v, int s) { bc2_range(0, in, out, len / 16, 0, len / 16, v, s); }
@@ -340,22 +649,39 @@ static inline uint32_t rd32(const uint8_t *p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 
-size_t orc_ltu_num_lz_matches(const uint8_t *data, size_t len) {
-    uint32_t *table = (uint32_t *)calloc((size_t)1 << LTU_HASH_BITS, sizeof(uint32_t));
+/* The parts of the restatement that are unverified against the crate are run-time parameters (defaults: ltu_params.h),
+ * so that every variant the product's estimator supports has a CPU checker:
+ *   hash_bits 12..17; index_top != 0: index = product >> (32 - hash_bits), else index = product & mask;
+ *   group = positions per loop iteration (all compares, then all updates): 4 or 1. */
+static int g_ltu_hash_bits = LTU_HASH_BITS, g_ltu_index_top = 1, g_ltu_group = LTU_GROUP;
+
+int orc_ltu_set_params(int hash_bits, int index_top, int group) {
+    if (hash_bits < 8 || hash_bits > 24 || group < 1 || group > 8) return 1;
+    g_ltu_hash_bits = hash_bits, g_ltu_index_top = index_top != 0, g_ltu_group = group;
+    return 0;
+}
+
+size_t orc_ltu_num_lz_matches_params(const uint8_t *data, size_t len, int hash_bits, int index_top, int group) {
+    uint32_t *table = (uint32_t *)calloc((size_t)1 << hash_bits, sizeof(uint32_t));
     if (!table) abort();
     size_t end = len > LTU_TAIL_GUARD ? len - LTU_TAIL_GUARD : 0;
     size_t matches = 0;
-    for (size_t i = 0; i < end; i += LTU_GROUP) {
-        uint32_t d[LTU_GROUP], idx[LTU_GROUP];
-        for (int k = 0; k < LTU_GROUP; k++) {
+    for (size_t i = 0; i < end; i += (size_t)group) {
+        uint32_t d[8], idx[8];
+        for (int k = 0; k < group; k++) {
             d[k] = rd32(data + i + k) & LTU_KEY_MASK;
-            idx[k] = (uint32_t)(d[k] * LTU_GOLDEN_RATIO) >> (32 - LTU_HASH_BITS);
+            const uint32_t product = (uint32_t)(d[k] * LTU_GOLDEN_RATIO);
+            idx[k] = index_top ? product >> (32 - hash_bits) : product & (((uint32_t)1 << hash_bits) - 1u);
         }
-        for (int k = 0; k < LTU_GROUP; k++) matches += table[idx[k]] == d[k];
-        for (int k = 0; k < LTU_GROUP; k++) table[idx[k]] = d[k];
+        for (int k = 0; k < group; k++) matches += table[idx[k]] == d[k];
+        for (int k = 0; k < group; k++) table[idx[k]] = d[k];
     }
     free(table);
     return matches;
+}
+
+size_t orc_ltu_num_lz_matches(const uint8_t *data, size_t len) {
+    return orc_ltu_num_lz_matches_params(data, len, g_ltu_hash_bits, g_ltu_index_top, g_ltu_group);
 }
 
 /* estimate_size / estimate_compressed_size: extensions/estimators/dxt-lossless-transform-ltu/src/lib.rs:67-119
@@ -720,17 +1046,25 @@ typedef struct {
     const uint8_t *in;
     uint8_t *out;
     size_t n, b0, b1;
+    int isa;   /* baseline_isa() */
 } mt_job;
 
 static void *mt_worker(void *arg) {
     mt_job *j = (mt_job *)arg;
     switch (j->format) {
     case 1:
-        if (have_avx2()) bc1_range_avx2(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c);
+        if (j->isa == 5) bc1_range_avx512(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c);
+        else if (j->isa == 2) bc1_range_avx2(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c);
         else bc1_range_fast(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c);
         break;
-    case 2: bc2_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c); break;
-    default: bc3_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_a, j->split_c); break;
+    case 2:
+        if (j->isa == 5) bc2_range_avx512(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c);
+        else bc2_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_c);
+        break;
+    default:
+        if (j->isa == 5) bc3_range_avx512(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_a, j->split_c);
+        else bc3_range(j->direction, j->in, j->out, j->n, j->b0, j->b1, j->variant, j->split_a, j->split_c);
+        break;
     }
     return NULL;
 }
@@ -738,7 +1072,7 @@ static void *mt_worker(void *arg) {
 /* One contiguous block range [b0, b1) of a payload of len bytes (what one shard / one GPU owns). */
 void orc_bcn_run_range(int format, int direction, const uint8_t *in, uint8_t *out, size_t len, int variant,
                        int split_a, int split_c, size_t b0, size_t b1) {
-    mt_job j = {format, direction, variant, split_a, split_c, in, out, len / (format == 1 ? 8 : 16), b0, b1};
+    mt_job j = {format, direction, variant, split_a, split_c, in, out, len / (format == 1 ? 8 : 16), b0, b1, baseline_isa()};
     mt_worker(&j);
 }
 
@@ -751,7 +1085,7 @@ void orc_bcn_run_mt(int format, int direction, const uint8_t *in, uint8_t *out, 
     mt_job jobs[256];
     for (int t = 0; t < threads; t++) {
         jobs[t] = (mt_job){format, direction, variant, split_a, split_c, in, out, n, n * (size_t)t / (size_t)threads,
-                           n * (size_t)(t + 1) / (size_t)threads};
+                           n * (size_t)(t + 1) / (size_t)threads, baseline_isa()};
         if (t + 1 < threads) pthread_create(&tid[t], NULL, mt_worker, &jobs[t]);
     }
     mt_worker(&jobs[threads - 1]);

@@ -52,6 +52,9 @@ void orc_split_color_endpoints(const uint8_t *in, uint8_t *out, size_t len_bytes
 
 /* lossless_transform_utils::match_estimator::estimate_num_lz_matches_fast (restated, unpinned). */
 size_t orc_ltu_num_lz_matches(const uint8_t *data, size_t len);
+/* The same with explicit parameters / process-wide parameters for everything that calls the estimator (see bcn_oracle.c). */
+size_t orc_ltu_num_lz_matches_params(const uint8_t *data, size_t len, int hash_bits, int index_top, int group);
+int orc_ltu_set_params(int hash_bits, int index_top, int group);
 /* LosslessTransformUtilsSizeEstimation::estimate_compressed_size (ltu/src/lib.rs:67-119). */
 size_t orc_ltu_estimate(const uint8_t *data, size_t len);
 

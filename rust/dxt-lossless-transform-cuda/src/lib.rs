@@ -110,20 +110,44 @@ fn core12(variant: YCoCgVariant, split: bool) -> DltCoreSettings {
     DltCoreSettings { split_colour_endpoints: split, decorrelation_mode: variant as u8 }
 }
 
-/// Same contract as `dxt_lossless_transform_bc1::transform_bc1_with_settings` (raw pointers, `len % 8 == 0`).
+/// Same contract as `dxt_lossless_transform_bc1::transform_bc1_with_settings` (raw pointers, `len % 8 == 0`), but a
+/// device failure is RETURNED: prefer this over the signature-compatible function below.
+///
+/// # Safety
+/// As the reference function: both pointers valid for `len` bytes, non-overlapping.
+pub unsafe fn try_transform_bc1_with_settings(
+    input: *const u8, output: *mut u8, len: usize, s: Bc1TransformSettings,
+) -> Result<(), CudaTransformError> {
+    check(dltbc1core_transform(input, len, output, len, core12(s.decorrelation_mode, s.split_colour_endpoints)), len, len)
+}
+
+/// # Safety
+/// As the reference function.
+pub unsafe fn try_untransform_bc1_with_settings(
+    input: *const u8, output: *mut u8, len: usize, s: Bc1TransformSettings,
+) -> Result<(), CudaTransformError> {
+    check(dltbc1core_untransform(input, len, output, len, core12(s.decorrelation_mode, s.split_colour_endpoints)), len, len)
+}
+
+/// Signature-compatible with the reference (`unsafe fn(*const u8, *mut u8, usize, Bc1TransformSettings)`, no return
+/// value — transform_with_settings.rs:31).  The reference cannot fail here; a GPU can (no device, out of memory), and
+/// the signature leaves no way to say so: the failure panics, which under the reference's `panic = "abort"` release
+/// profile ends the process.  Callers that can handle an error use `try_transform_bc1_with_settings` or the `_safe` form.
 ///
 /// # Safety
 /// As the reference function: both pointers valid for `len` bytes, non-overlapping.
 pub unsafe fn transform_bc1_with_settings(input: *const u8, output: *mut u8, len: usize, s: Bc1TransformSettings) {
-    let r = dltbc1core_transform(input, len, output, len, core12(s.decorrelation_mode, s.split_colour_endpoints));
-    assert_eq!(r.error_code, 0, "dxt-lossless-transform-cuda: device failure");
+    if let Err(e) = try_transform_bc1_with_settings(input, output, len, s) {
+        panic!("dxt-lossless-transform-cuda: {e}");
+    }
 }
 
 /// # Safety
 /// As the reference function.
 pub unsafe fn untransform_bc1_with_settings(input: *const u8, output: *mut u8, len: usize, s: Bc1TransformSettings) {
-    let r = dltbc1core_untransform(input, len, output, len, core12(s.decorrelation_mode, s.split_colour_endpoints));
-    assert_eq!(r.error_code, 0, "dxt-lossless-transform-cuda: device failure");
+    if let Err(e) = try_untransform_bc1_with_settings(input, output, len, s) {
+        panic!("dxt-lossless-transform-cuda: {e}");
+    }
 }
 
 /// `transform_bc1_with_settings_safe` (safe/transform_with_settings.rs:88).

@@ -41,6 +41,8 @@ def lib() -> C.CDLL:
         L.orc_split_color_endpoints.restype, L.orc_split_color_endpoints.argtypes = None, [p, p, sz]
         L.orc_ltu_num_lz_matches.restype, L.orc_ltu_num_lz_matches.argtypes = sz, [p, sz]
         L.orc_ltu_estimate.restype, L.orc_ltu_estimate.argtypes = sz, [p, sz]
+        L.orc_ltu_num_lz_matches_params.restype, L.orc_ltu_num_lz_matches_params.argtypes = sz, [p, sz, i, i, i]
+        L.orc_ltu_set_params.restype, L.orc_ltu_set_params.argtypes = i, [i, i, i]
         ip = C.POINTER(C.c_int)
         L.orc_bc1_transform_auto.restype, L.orc_bc1_transform_auto.argtypes = i, [p, p, sz, i, p, p, ip, ip]
         L.orc_bc2_transform_auto.restype, L.orc_bc2_transform_auto.argtypes = i, [p, p, sz, i, p, p, ip, ip]
@@ -110,6 +112,16 @@ def ltu_estimate(data: np.ndarray) -> int:
 
 def ltu_matches(data: np.ndarray) -> int:
     return lib().orc_ltu_num_lz_matches(_ptr(data), data.size)
+
+
+def ltu_matches_params(data: np.ndarray, hash_bits: int, index_top: bool, group: int) -> int:
+    return lib().orc_ltu_num_lz_matches_params(_ptr(data), data.size, hash_bits, int(index_top), group)
+
+
+def ltu_set_params(hash_bits: int = 16, index_top: bool = True, group: int = 4) -> None:
+    """Process-wide parameters of the restated estimator (everything that estimates follows them)."""
+    if lib().orc_ltu_set_params(hash_bits, int(index_top), group) != 0:
+        raise ValueError("unsupported LTU parameters")
 
 
 def auto(fmt: int, data: np.ndarray, use_all: bool):

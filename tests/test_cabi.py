@@ -278,3 +278,122 @@ int main() {
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", f"-I{INCLUDE}", str(src), "-o", str(exe), f"-L{libdir}",
                     "-ldxt_lossless_transform_cuda", f"-Wl,-rpath,{libdir}"], check=True)
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+# ---- C code written against the REFERENCE's generated headers (cbindgen's spelling) --------------------------
+CBINDGEN_USER_API = r'''
+/* What a user of the reference's generated `dxt-lossless-transform-bc%(n)d-api` header writes: bare enumerators,
+ * PascalCase fields (.github/cbindgen_c.toml), the documented builder flow (c_api/mod.rs). */
+#include "dxt_lossless_transform_bc%(n)d_api.h"
+#include <stdio.h>
+#include <string.h>
+int main(int argc, char **argv) {
+    enum { BLOCK = %(bpb)d, N = 1024 };
+    static uint8_t in[BLOCK * N], mid[BLOCK * N], back[BLOCK * N];
+    for (size_t i = 0; i < sizeof in; i++) in[i] = (uint8_t)(i * 131u + (i >> 7));
+    Dltbc%(n)dManualTransformBuilder *b = dltbc%(n)d_new_ManualTransformBuilder();
+    if (!b) return 10;
+    dltbc%(n)d_ManualTransformBuilder_SetDecorrelationMode(b, Variant2);
+    dltbc%(n)d_ManualTransformBuilder_SetSplitColourEndpoints(b, false);
+    Dltbc%(n)dTransformSettings s = { .DecorrelationMode = None, .SplitColourEndpoints = true };
+    (void)s;
+    Dltbc%(n)dResult r = dltbc%(n)d_ManualTransformBuilder_Transform(NULL, sizeof in, mid, sizeof mid, b);
+    if (r.ErrorCode != NullDataPointer) return 11;
+    r = dltbc%(n)d_ManualTransformBuilder_Transform(in, sizeof in, NULL, sizeof mid, b);
+    if (r.ErrorCode != NullOutputBufferPointer) return 12;
+    r = dltbc%(n)d_ManualTransformBuilder_Transform(in, sizeof in, mid, sizeof mid, NULL);
+    if (r.ErrorCode != NullManualTransformBuilderPointer) return 13;
+    r = dltbc%(n)d_ManualTransformBuilder_Transform(in, BLOCK + 1, mid, sizeof mid, b);
+    if (r.ErrorCode != InvalidLength) return 14;
+    r = dltbc%(n)d_ManualTransformBuilder_Transform(in, sizeof in, mid, BLOCK, b);
+    if (r.ErrorCode != OutputBufferTooSmall) return 15;
+    if (strcmp(dltbc%(n)d_error_message(Success), dltbc%(n)d_error_message(InvalidLength)) == 0) return 16;
+    DltSizeEstimator *est = dltltu_new_size_estimator();
+    if (!est || !est->MaxCompressedSize || !est->EstimateCompressedSize) return 17;
+    Dltbc%(n)dAutoTransformBuilder *ab = dltbc%(n)d_new_AutoTransformBuilder(est);
+    if (!ab) return 18;
+    if (dltbc%(n)d_AutoTransformBuilder_SetUseAllDecorrelationModes(NULL, true).ErrorCode != NullBuilderPointer) return 19;
+    Dltbc%(n)dManualTransformBuilder *won = (Dltbc%(n)dManualTransformBuilder *)1;
+    r = dltbc%(n)d_AutoTransformBuilder_Transform(ab, NULL, sizeof in, mid, sizeof mid, &won);
+    if (r.ErrorCode != NullDataPointer || won != (Dltbc%(n)dManualTransformBuilder *)1) return 20; /* pointer checks return before *out is written */
+    r = dltbc%(n)d_AutoTransformBuilder_Transform(ab, in, BLOCK + 1, mid, sizeof mid, &won);
+    if (r.ErrorCode != InvalidLength || won != NULL) return 21;                                    /* a failed search nulls it */
+    if (argc > 1) { /* a GPU is present: the full documented flow */
+        r = dltbc%(n)d_ManualTransformBuilder_Transform(in, sizeof in, mid, sizeof mid, b);
+        if (r.ErrorCode != Success) return 30;
+        r = dltbc%(n)d_ManualTransformBuilder_Untransform(mid, sizeof mid, back, sizeof back, b);
+        if (r.ErrorCode != Success || memcmp(in, back, sizeof in)) return 31;
+        r = dltbc%(n)d_AutoTransformBuilder_Transform(ab, in, sizeof in, mid, sizeof mid, &won);
+        if (r.ErrorCode != Success || !won) return 32;
+        r = dltbc%(n)d_ManualTransformBuilder_Untransform(mid, sizeof mid, back, sizeof back, won);
+        if (r.ErrorCode != Success || memcmp(in, back, sizeof in)) return 33;
+        dltbc%(n)d_free_ManualTransformBuilder(won);
+    }
+    dltbc%(n)d_free_AutoTransformBuilder(ab);
+    dltltu_free_size_estimator(est);
+    dltbc%(n)d_free_ManualTransformBuilder(b);
+    return 0;
+}
+'''
+CBINDGEN_USER_CORE = r'''
+/* ... and of the core crate's generated header (`dxt-lossless-transform-bc%(n)d`, feature c-exports): same type names,
+ * different layout and values (SURVEY section 8b). */
+#include "dxt_lossless_transform_bc%(n)d.h"
+#include <string.h>
+int main(int argc, char **argv) {
+    enum { BLOCK = %(bpb)d, N = 777 };
+    static uint8_t in[BLOCK * N], mid[BLOCK * N], back[BLOCK * N];
+    for (size_t i = 0; i < sizeof in; i++) in[i] = (uint8_t)(i * 29u + (i >> 5));
+    Dltbc%(n)dTransformSettings s = { .SplitColourEndpoints = true, .DecorrelationMode = Variant3 };
+    Dltbc%(n)dUntransformSettings u = s;
+    if (sizeof s != 2 || None != 0 || Variant3 != 3) return 10;
+    if (dltbc%(n)dcore_transform(NULL, sizeof in, mid, sizeof mid, s).ErrorCode != NullDataPointer) return 11;
+    if (dltbc%(n)dcore_transform(in, sizeof in, NULL, sizeof mid, s).ErrorCode != NullOutputBufferPointer) return 12;
+    if (dltbc%(n)dcore_transform(in, BLOCK - 1, mid, sizeof mid, s).ErrorCode != InvalidDataLength) return 13;
+    if (dltbc%(n)dcore_untransform(in, sizeof in, mid, BLOCK, u).ErrorCode != OutputBufferTooSmall) return 14;
+    Dltbc%(n)dAutoTransformSettings a = { .UseAllModes = true };
+    Dltbc%(n)dTransformSettings best;
+    if (dltbc%(n)dcore_transform_auto(in, sizeof in, mid, sizeof mid, NULL, a, &best).ErrorCode != NullEstimatorPointer) return 15;
+    if (argc > 1) {
+        if (dltbc%(n)dcore_transform(in, sizeof in, mid, sizeof mid, s).ErrorCode != Success) return 30;
+        if (dltbc%(n)dcore_untransform(mid, sizeof mid, back, sizeof back, u).ErrorCode != Success || memcmp(in, back, sizeof in)) return 31;
+        DltSizeEstimator *est = dltltu_new_size_estimator();
+        if (dltbc%(n)dcore_transform_auto(in, sizeof in, mid, sizeof mid, est, a, &best).ErrorCode != Success) return 32;
+        if (dltbc%(n)dcore_untransform(mid, sizeof mid, back, sizeof back, best).ErrorCode != Success || memcmp(in, back, sizeof in)) return 33;
+        dltltu_free_size_estimator(est);
+    }
+    return 0;
+}
+'''
+
+
+@pytest.mark.parametrize("which", ["bc1_api", "bc2_api", "bc1", "bc2"])
+def test_code_written_against_cbindgen_headers_compiles_and_links(which, tmp_path):
+    """INTEGRATION.md section 1 claims that C code written against the reference's cbindgen headers links unchanged: the
+    generated compatibility headers (include/cbindgen_compat, tools/gen_cbindgen_compat.py) are current, a program in
+    cbindgen's spelling compiles with -Wall -Werror, links to the product library, and sees the reference's error codes
+    (and, on a GPU box, round-trips through the documented builder flow)."""
+    import torch
+
+    assert subprocess.run(["python", str(ROOT / "tools" / "gen_cbindgen_compat.py"), "--check"]).returncode == 0
+    n = 1 if "bc1" in which else 2
+    text = (CBINDGEN_USER_API if which.endswith("_api") else CBINDGEN_USER_CORE) % {"n": n, "bpb": 8 if n == 1 else 16}
+    src, exe = tmp_path / "user.c", tmp_path / "user"
+    src.write_text(text)
+    libdir = N.LIB_PATH.parent
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-Wno-unused-parameter", f"-I{INCLUDE / 'cbindgen_compat'}", str(src), "-o",
+                    str(exe), f"-L{libdir}", "-ldxt_lossless_transform_cuda", f"-Wl,-rpath,{libdir}"], check=True)
+    args = [str(exe)] + (["gpu"] if torch.cuda.is_available() else [])
+    assert subprocess.run(args).returncode == 0
+
+
+def test_the_rust_crate_builds_from_the_same_lists_as_build_py():
+    """rust/dxt-lossless-transform-cuda/build.rs used to carry its own (stale) copy of the source list: both builds
+    now read csrc/SOURCES.txt and csrc/NVCC_FLAGS.txt, and the list is every .cu file of csrc/."""
+    from dxt_lossless_transform_b200 import build
+
+    rs = (ROOT / "rust" / "dxt-lossless-transform-cuda" / "build.rs").read_text()
+    assert "SOURCES.txt" in rs and "NVCC_FLAGS.txt" in rs and ".cu\"" not in rs
+    assert "rustc-link-lib=dylib=dl" in rs
+    assert sorted(build.SOURCES) == sorted(p.name for p in build.CSRC.glob("*.cu"))
+    assert "-ldl" in build.NVCC_FLAGS and "arch=compute_100a,code=sm_100a" in build.NVCC_FLAGS

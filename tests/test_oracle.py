@@ -154,6 +154,33 @@ def test_multithreaded_and_ranged_drivers_equal_single_call(fmt):
         assert np.array_equal(parts, t)
 
 
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_vector_baseline_paths_equal_the_scalar_restatement(fmt):
+    """The CPU baseline (orc_bcn_run_range / _mt: AVX-512 where the host has it, as the reference would pick) against
+    the scalar restatement: every settings combination, both directions, block counts around the vector width, and
+    buffers misaligned by one byte (the reference's own unaligned tests)."""
+    import ctypes as C
+
+    L = oracle.lib()
+    L.orc_cpu_baseline_isa.restype = C.c_int
+    assert L.orc_cpu_baseline_isa() in (0, 2, 5)
+    bpb = 8 if fmt == 1 else 16
+    rng = np.random.default_rng(100 + fmt)
+    for nblocks in (1, 15, 16, 17, 31, 32, 33, 63, 64, 65, 333):
+        raw = rng.integers(0, 256, nblocks * bpb + 1, dtype=np.uint8)
+        for mis in (0, 1):
+            data = raw[mis:mis + nblocks * bpb]
+            for v, sa, sc in all_settings(fmt):
+                want = oracle.transform(fmt, data.copy(), v, sa, sc)
+                buf = np.zeros(nblocks * bpb + 1, np.uint8)
+                got = buf[mis:mis + nblocks * bpb]
+                oracle.run_range(fmt, False, data, got, v, sa, sc, 0, nblocks)
+                assert np.array_equal(got, want), (nblocks, mis, v, sa, sc)
+                back = np.zeros(nblocks * bpb + 1, np.uint8)[mis:mis + nblocks * bpb]
+                oracle.run_range(fmt, True, got, back, v, sa, sc, 0, nblocks)
+                assert np.array_equal(back, data), (nblocks, mis, v, sa, sc)
+
+
 # ---- LTU estimator: the reference's own (inequality) tests -----------------------------------------
 def test_ltu_reference_inequalities():
     # extensions/estimators/dxt-lossless-transform-ltu/src/lib.rs:125-225, tests/integration_test.rs
