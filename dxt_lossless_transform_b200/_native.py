@@ -149,6 +149,7 @@ SIGNATURES.update(
         "dltcuda_transform_batch_multi_gpu": (C.c_int, [C.POINTER(DltcudaPayload), _SZ, C.c_bool, C.POINTER(C.c_int), C.c_int]),
         "dltcuda_shard_first_block": (_SZ, [C.c_int, _SZ, C.c_int, C.c_int]),
         "dltcuda_ltu_estimate_device": (C.c_int, [_P, _SZ, C.POINTER(_SZ)]),
+        "dltcuda_release_cached_memory": (_SZ, []),
         "dltcuda_ltu_set_params": (C.c_int, [C.c_int, C.c_bool, C.c_int]),
         "dltcuda_ltu_get_params": (None, [C.POINTER(C.c_int), C.POINTER(C.c_bool), C.POINTER(C.c_int)]),
         "dltcuda_transform_auto_device": (

@@ -115,15 +115,36 @@ uint32_t ltu_estimate_compressed_size(void* context, const uint8_t* input, size_
             rc = 0;
         }
     }
-    release_context(ctx);
+    release_context_synced(ctx);
     return rc;
 }
 
 bool is_gpu_ltu(const DltSizeEstimator& e) { return e.estimate_compressed_size == &ltu_estimate_compressed_size; }
 
 // ---- transform_bcN_auto on host pointers -----------------------------------------------------------
+// C++ exceptions must not cross the C ABI (std::vector / std::thread allocate): every exported body that can throw runs
+// inside guarded(), which maps bad_alloc to the caller's out-of-memory code and anything else to its failure code.
+template <class F, class R>
+R guarded(F&& f, R oom, R other) noexcept {
+    try {
+        return f();
+    } catch (const std::bad_alloc&) {
+        return oom;
+    } catch (...) {
+        return other;
+    }
+}
+
+Outcome auto_host_impl(int format, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len,
+                       const DltSizeEstimator& est, bool use_all, Settings* best);
 Outcome auto_host(int format, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len,
                   const DltSizeEstimator& est, bool use_all, Settings* best) {
+    return guarded([&] { return auto_host_impl(format, in, in_len, out, out_len, est, use_all, best); }, Outcome::kHostAlloc,
+                   Outcome::kDevice);
+}
+
+Outcome auto_host_impl(int format, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len,
+                       const DltSizeEstimator& est, bool use_all, Settings* best) {
     Outcome v = validate(in_len, out_len, format);
     if (v != Outcome::kOk) return v;
     const size_t len = in_len;
@@ -167,7 +188,7 @@ Outcome auto_host(int format, const uint8_t* in, size_t in_len, uint8_t* out, si
     if (!ctx) return from_status(st);
     struct Releaser {
         Context* c;
-        ~Releaser() { release_context(c); }
+        ~Releaser() { release_context_synced(c); }
     } releaser{ctx};
     if ((st = ensure_device_buffers(ctx, len)) != Status::kOk) return from_status(st);
     cudaStream_t s = ctx->stream[0];
@@ -198,7 +219,10 @@ Outcome auto_host(int format, const uint8_t* in, size_t in_len, uint8_t* out, si
         for (int r = 0; r < nr; r++) largest = std::max(largest, ranges[r].len);
         const size_t per = (largest + 255) / 256 * 256 + (max_comp + 255) / 256 * 256;   // one range + its compression buffer
         constexpr size_t kHostBudget = (size_t)4 << 30;   // pinned ranges + compression buffers in flight
-        const int wave = (int)std::min<size_t>((size_t)nseg, std::max<size_t>(1, kHostBudget / per));
+        // one host thread per range in flight: bounded by the pinned budget AND by the cores of the box (several caller
+        // threads may be searching at the same time; zstd is CPU-bound, more threads than cores only thrash)
+        const size_t cores = std::max(1u, std::thread::hardware_concurrency());
+        const int wave = (int)std::min({(size_t)nseg, std::max<size_t>(1, kHostBudget / per), cores});
         if ((st = ensure_host_scratch(ctx, (size_t)wave * per)) != Status::kOk) return from_status(st);
         std::vector<size_t> seg_size((size_t)nseg, 0);
         std::vector<uint32_t> seg_rc((size_t)nseg, 0);
@@ -207,7 +231,14 @@ Outcome auto_host(int format, const uint8_t* in, size_t in_len, uint8_t* out, si
         int transformed = -1;   // candidate whose image currently sits in ctx->d_out
         for (int q0 = 0; q0 < nseg && failed == Outcome::kOk; q0 += wave) {
             const int wb = std::min(wave, nseg - q0);
-            std::vector<std::thread> workers;
+            struct Joiner {   // a thread that cannot be started must not leave running ones un-joined (std::terminate)
+                std::vector<std::thread> t;
+                ~Joiner() {
+                    for (auto& w : t)
+                        if (w.joinable()) w.join();
+                }
+            } joiner;
+            std::vector<std::thread>& workers = joiner.t;
             workers.reserve(wb);
             for (int c = 0; c < wb; c++) {
                 const int q = q0 + c;
@@ -553,6 +584,8 @@ DLT_EXPORT void dltcuda_set_device(int device) { set_thread_device(device); }
 DLT_EXPORT const char* dltcuda_last_error(void) { return last_error_string(); }
 DLT_EXPORT uint64_t dltcuda_kernel_launch_count(void) { return kernel_launch_count() + estimator_launch_count(); }
 
+DLT_EXPORT size_t dltcuda_release_cached_memory(void) { return release_cached_memory(); }
+
 DLT_EXPORT void* dltcuda_alloc_pinned(size_t bytes) {
     void* p = nullptr;
     const int dev = thread_device();
@@ -600,7 +633,7 @@ DLT_EXPORT int dltcuda_transform_device_range(const uint8_t* d_blocks, uint8_t* 
                                               size_t first_block, size_t num_blocks, DltcudaSettings s, void* stream) {
     Settings st;
     if (!to_settings(s, &st)) return kDltcudaInvalidSettings;
-    if (first_block + num_blocks > total_blocks) return kDltcudaInvalidLength;
+    if (first_block > total_blocks || num_blocks > total_blocks - first_block) return kDltcudaInvalidLength;
     if (num_blocks == 0) return kDltcudaOk;
     if (!d_blocks || !d_streams_base) return kDltcudaNullPointer;
     return dltcuda_status(launch_transform(st, d_blocks, reference_layout(d_streams_base, total_blocks, first_block, st),
@@ -611,7 +644,7 @@ DLT_EXPORT int dltcuda_untransform_device_range(const uint8_t* d_streams_base, u
                                                 void* stream) {
     Settings st;
     if (!to_settings(s, &st)) return kDltcudaInvalidSettings;
-    if (first_block + num_blocks > total_blocks) return kDltcudaInvalidLength;
+    if (first_block > total_blocks || num_blocks > total_blocks - first_block) return kDltcudaInvalidLength;
     if (num_blocks == 0) return kDltcudaOk;
     if (!d_blocks || !d_streams_base) return kDltcudaNullPointer;
     return dltcuda_status(launch_untransform(
@@ -695,7 +728,7 @@ DLT_EXPORT int dltcuda_split_color_endpoints(const uint8_t* colors, uint8_t* col
         if (e == cudaSuccess) e = cudaMemcpyAsync(colors_out, ctx->d_out, len_bytes, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     }
-    release_context(ctx);
+    release_context_synced(ctx);
     return st != Status::kOk ? dltcuda_status(st) : dltcuda_status(e);
 }
 
@@ -703,8 +736,14 @@ DLT_EXPORT int dltcuda_split_color_endpoints(const uint8_t* colors, uint8_t* col
 // chunks of consecutive payloads overlap and there is one wait at the end.  With several devices the
 // payloads are dealt out whole, largest-remaining-capacity first (payload-granular sharding: nothing
 // is exchanged between devices); one host thread drives each device.
-static int batch_impl(const DltcudaPayload* payloads, size_t count, bool untransform, const int* devices,
-                      int num_devices) {
+static int batch_impl_unguarded(const DltcudaPayload* payloads, size_t count, bool untransform, const int* devices,
+                                int num_devices);
+static int batch_impl(const DltcudaPayload* payloads, size_t count, bool untransform, const int* devices, int num_devices) {
+    return guarded([&] { return batch_impl_unguarded(payloads, count, untransform, devices, num_devices); },
+                              (int)kDltcudaOutOfMemory, (int)kDltcudaCudaError);
+}
+static int batch_impl_unguarded(const DltcudaPayload* payloads, size_t count, bool untransform, const int* devices,
+                                int num_devices) {
     if (count == 0) return kDltcudaOk;
     if (!payloads || num_devices < 1) return kDltcudaNullPointer;
     std::vector<std::vector<HostJob>> jobs((size_t)num_devices);
@@ -754,7 +793,7 @@ DLT_EXPORT int dltcuda_ltu_estimate_device(const uint8_t* d_data, size_t len, si
     LtuSegment seg{d_data, len};
     uint64_t m = 0;
     st = ltu_matches_device(ctx, &seg, 1, &m, ctx->stream[0]);
-    release_context(ctx);
+    release_context_synced(ctx);
     if (st == Status::kOk) *out_size = ltu_estimate_from_matches(len, m);
     return dltcuda_status(st);
 }
@@ -789,7 +828,7 @@ DLT_EXPORT int dltcuda_transform_auto_device(int format, const uint8_t* d_input,
         cudaError_t e = cudaStreamSynchronize(ctx->stream[0]);
         if (e != cudaSuccess) st = Status::kCudaError, note_cuda_error(e);
     }
-    release_context(ctx);
+    release_context_synced(ctx);
     if (st == Status::kOk)
         *out_settings = DltcudaSettings{(uint8_t)format, (uint8_t)best.variant, best.split_alpha, best.split_colour};
     return dltcuda_status(st);
@@ -815,7 +854,7 @@ int auto_batch_host(DltcudaAutoJob* jobs, size_t count, bool use_all) {
     if (!ctx) return dltcuda_status(st);
     struct Releaser {
         Context* c;
-        ~Releaser() { release_context(c); }
+        ~Releaser() { release_context_synced(c); }
     } releaser{ctx};
     // Three queues: uploads, the search (transform candidates + estimator + winners), downloads.  The payloads are cut
     // into ROUNDS; round r+1 is uploaded and round r-1 downloaded while round r is searched (two device slots).
@@ -950,14 +989,22 @@ int auto_batch_host(DltcudaAutoJob* jobs, size_t count, bool use_all) {
 }  // namespace dlt
 
 DLT_EXPORT int dltcuda_transform_auto_batch(DltcudaAutoJob* jobs, size_t count, bool use_all_modes) {
-    return dlt::cabi::auto_batch_host(jobs, count, use_all_modes);
+    return guarded([&] { return dlt::cabi::auto_batch_host(jobs, count, use_all_modes); }, (int)kDltcudaOutOfMemory,
+                              (int)kDltcudaCudaError);
 }
 
 // The same over several GPUs of one box: whole payloads are dealt out (least-loaded device first), one host thread
 // per device runs its share through dltcuda_transform_auto_batch; nothing is exchanged between devices (an estimate
 // is a property of a whole payload, so payloads - never one payload's streams - are what gets sharded).
+static int auto_batch_multi_gpu_unguarded(DltcudaAutoJob* jobs, size_t count, bool use_all_modes, const int* devices,
+                                          int num_devices);
 DLT_EXPORT int dltcuda_transform_auto_batch_multi_gpu(DltcudaAutoJob* jobs, size_t count, bool use_all_modes,
                                                       const int* devices, int num_devices) {
+    return guarded([&] { return auto_batch_multi_gpu_unguarded(jobs, count, use_all_modes, devices, num_devices); },
+                   (int)kDltcudaOutOfMemory, (int)kDltcudaCudaError);
+}
+static int auto_batch_multi_gpu_unguarded(DltcudaAutoJob* jobs, size_t count, bool use_all_modes, const int* devices,
+                                          int num_devices) {
     if (count == 0) return kDltcudaOk;
     if (!jobs || !devices || num_devices < 1) return kDltcudaNullPointer;
     std::vector<std::vector<size_t>> share((size_t)num_devices);
@@ -1006,7 +1053,7 @@ int normalize_host(const uint8_t* input, uint8_t* const outs[3], size_t len, boo
     if (!ctx) return dltcuda_status(st);
     struct Releaser {
         Context* c;
-        ~Releaser() { release_context(c); }
+        ~Releaser() { release_context_synced(c); }
     } releaser{ctx};
     if ((st = ensure_device_buffers(ctx, len)) != Status::kOk) return dltcuda_status(st);
     if ((st = ensure_scratch(ctx, 3 * ((len + 255) / 256 * 256) + 256)) != Status::kOk) return dltcuda_status(st);
@@ -1061,7 +1108,7 @@ DLT_EXPORT int dltcuda_bc1_normalize_split_blocks_in_place(uint8_t* colors, uint
     if (!ctx) return dltcuda_status(st);
     struct Releaser {
         Context* c;
-        ~Releaser() { release_context(c); }
+        ~Releaser() { release_context_synced(c); }
     } releaser{ctx};
     const size_t bytes = num_blocks * 4;
     if ((st = ensure_device_buffers(ctx, bytes)) != Status::kOk) return dltcuda_status(st);
@@ -1135,7 +1182,7 @@ DLT_EXPORT int dltcuda_bc1_transform_auto_with_normalization(const uint8_t* inpu
         if (!ctx) return dltcuda_status(st);
         struct Releaser {
             Context* c;
-            ~Releaser() { release_context(c); }
+            ~Releaser() { release_context_synced(c); }
         } releaser{ctx};
         if ((st = ensure_device_buffers(ctx, len)) != Status::kOk) return dltcuda_status(st);
         cudaStream_t s = ctx->stream[0];

@@ -598,8 +598,29 @@ DLT_EXPORT DltffResult dltdds_untransform(const uint8_t* input, size_t input_len
 // builder is manual (and every untransform) share one copy pipeline per device.
 // devices == NULL / num_devices == 0: the calling thread's device.
 // =================================================================================================
+// C++ exceptions (vector growth) must not cross the C ABI: the batch bodies run inside try / catch, 2 = out of memory.
+static int transform_bundle_batch_body(const DltddsFile* files, size_t count, const void* bundle, DltffResult* results,
+                                       const int* devices, int num_devices);
+static int untransform_batch_body(const DltddsFile* files, size_t count, DltffResult* results, const int* devices,
+                                  int num_devices);
 DLT_EXPORT int dltdds_transform_bundle_batch(const DltddsFile* files, size_t count, const void* bundle, DltffResult* results,
                                              const int* devices, int num_devices) {
+    try {
+        return transform_bundle_batch_body(files, count, bundle, results, devices, num_devices);
+    } catch (...) {
+        return 2;
+    }
+}
+DLT_EXPORT int dltdds_untransform_batch(const DltddsFile* files, size_t count, DltffResult* results, const int* devices,
+                                        int num_devices) {
+    try {
+        return untransform_batch_body(files, count, results, devices, num_devices);
+    } catch (...) {
+        return 2;
+    }
+}
+static int transform_bundle_batch_body(const DltddsFile* files, size_t count, const void* bundle, DltffResult* results,
+                                       const int* devices, int num_devices) {
     if (count == 0) return 0;
     if (!files || !bundle || !results) return 1;
     const Bundle& b = *static_cast<const Bundle*>(bundle);
@@ -678,8 +699,8 @@ DLT_EXPORT int dltdds_transform_bundle_batch(const DltddsFile* files, size_t cou
     return 0;
 }
 
-DLT_EXPORT int dltdds_untransform_batch(const DltddsFile* files, size_t count, DltffResult* results, const int* devices,
-                                        int num_devices) {
+static int untransform_batch_body(const DltddsFile* files, size_t count, DltffResult* results, const int* devices,
+                                  int num_devices) {
     if (count == 0) return 0;
     if (!files || !results) return 1;
     std::vector<DdsPlan> plans(count);

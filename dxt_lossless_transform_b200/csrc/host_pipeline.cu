@@ -168,30 +168,71 @@ Context* acquire_context(int device, Status* st) {
         *st = Status::kCudaError;
         return nullptr;
     }
+    // the call runs on `device`; the thread's own current device (torch, another library) is put back on release
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) {
         note_cuda_error(e);
         *st = Status::kCudaError;
         return nullptr;
     }
+    Context* c = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_pool_mutex);
-        if (Context* c = g_free[device]) {
+        if ((c = g_free[device]) != nullptr) {
             g_free[device] = c->next_free;
             c->next_free = nullptr;
-            return c;
         }
     }
-    Context* c = nullptr;
-    *st = create_context(device, &c);
+    if (!c) *st = create_context(device, &c);
+    if (c) c->prev_device = prev;
+    else if (prev >= 0 && prev != device) cudaSetDevice(prev);
     return c;
 }
 
 void release_context(Context* ctx) {
     if (!ctx) return;
+    if (ctx->prev_device >= 0 && ctx->prev_device != ctx->device) cudaSetDevice(ctx->prev_device);
+    ctx->prev_device = -1;
     std::lock_guard<std::mutex> lk(g_pool_mutex);
     ctx->next_free = g_free[ctx->device];
     g_free[ctx->device] = ctx;
+}
+
+void release_context_synced(Context* ctx) {
+    if (!ctx) return;
+    for (int i = 0; i < kStages; i++)
+        if (ctx->stream[i]) cudaStreamSynchronize(ctx->stream[i]);   // errors were reported where they happened
+    release_context(ctx);
+}
+
+size_t release_cached_memory() {
+    size_t freed = 0;
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    for (int d = 0; d < kMaxDevices; d++) {
+        if (!g_free[d] || cudaSetDevice(d) != cudaSuccess) continue;
+        for (Context* c = g_free[d]; c; c = c->next_free) {
+            if (c->d_in) cudaFree(c->d_in), freed += c->d_cap;
+            if (c->d_out) cudaFree(c->d_out), freed += c->d_cap;
+            c->d_in = c->d_out = nullptr, c->d_cap = 0;
+            if (c->d_scratch) cudaFree(c->d_scratch), freed += c->d_scratch_cap;
+            c->d_scratch = nullptr, c->d_scratch_cap = 0;
+            if (c->h_scratch) cudaFreeHost(c->h_scratch), freed += c->h_scratch_cap;
+            c->h_scratch = nullptr, c->h_scratch_cap = 0;
+            if (c->d_desc) cudaFree(c->d_desc), freed += c->d_desc_cap;
+            c->d_desc = nullptr, c->d_desc_cap = 0;
+            for (int i = 0; i < kStages; i++) {
+                if (c->h_in[i]) cudaFreeHost(c->h_in[i]), freed += kStagingSlotBytes;
+                if (c->h_out[i]) cudaFreeHost(c->h_out[i]), freed += kStagingSlotBytes;
+                c->h_in[i] = c->h_out[i] = nullptr;
+            }
+        }
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    return freed;
 }
 
 Status ensure_device_buffers(Context* ctx, size_t len) {
@@ -733,7 +774,8 @@ Status run_host_batch(const HostJob* jobs, size_t count, int device) {
     status = pipe.prepare(jobs, count);
     for (size_t i = 0; i < count && status == Status::kOk; i++) status = pipe.submit(jobs[i], i);
     const Status d = pipe.drain();
-    release_context(ctx);
+    if (status != Status::kOk || d != Status::kOk) release_context_synced(ctx);   // nothing may be in flight in a pooled context
+    else release_context(ctx);
     return status != Status::kOk ? status : d;
 }
 

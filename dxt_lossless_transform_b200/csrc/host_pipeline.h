@@ -58,13 +58,21 @@ struct Context {
     size_t h_scratch_cap = 0;
     uint8_t* d_desc = nullptr;     // small device buffer for launch descriptors (batched search: gather lists)
     size_t d_desc_cap = 0;
+    int prev_device = -1;          // the calling thread's CUDA device before acquire_context() switched it
     Context* next_free = nullptr;
 };
 
 // Borrow a context for `device` (-1 = the calling thread's current CUDA device).  Contexts are
 // pooled per device, so concurrent host threads each get their own streams and buffers.
 Context* acquire_context(int device, Status* st);
-void release_context(Context* ctx);
+void release_context(Context* ctx);   // also restores the calling thread's previous CUDA device
+// The same after waiting for everything queued on the context's streams: what every entry point that may leave
+// through an error path uses, so that a pooled context never goes back with work still in flight (another thread
+// could be handed its buffers, and page-locked caller memory could still be read after the call has returned).
+void release_context_synced(Context* ctx);
+// Frees the device / pinned buffers of every idle pooled context (they are retained between calls and sized to the
+// largest payload seen); streams and events stay.  Returns the number of bytes released.
+size_t release_cached_memory();
 
 Status ensure_device_buffers(Context* ctx, size_t len);
 Status ensure_scratch(Context* ctx, size_t bytes);

@@ -41,6 +41,10 @@ int dltcuda_device_count(void);
 /* Device used by THIS host thread for every entry point of the library (-1 = the thread's current
  * CUDA device, the default). */
 void dltcuda_set_device(int device);
+/* The library keeps its per-device working set between calls (device buffers sized to the largest payload seen, the
+ * estimator's scratch, pinned staging slots): this frees the buffers of every idle pooled context and returns the number
+ * of bytes released.  Safe at any time; buffers are re-allocated on demand. */
+size_t dltcuda_release_cached_memory(void);
 /* Text of the last CUDA error seen by this thread. */
 const char *dltcuda_last_error(void);
 /* Kernels launched by the library in this process so far. */

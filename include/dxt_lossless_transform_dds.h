@@ -75,7 +75,7 @@ DltffResult dltdds_untransform(const uint8_t *input, size_t input_len, uint8_t *
                                size_t output_len);
 
 /* A directory of files at once.  results[i] is what the single-file call would have returned for files[i];
- * the return value is non-zero only for NULL arguments.  devices == NULL: the calling thread's device
+ * the return value is non-zero only for NULL arguments (1) or when the host ran out of memory (2).  devices == NULL: the calling thread's device
  * (dltcuda_set_device); otherwise the payloads are dealt out over `num_devices` GPUs of this box. */
 typedef struct DltddsFile {
   const uint8_t *input;
