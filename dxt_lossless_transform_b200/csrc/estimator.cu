@@ -45,16 +45,19 @@ constexpr uint32_t kUntouched = 0xFFFFu;   // table entry: no position of this b
 constexpr uint32_t kAlias = 0xFFFEu;       // stored instead of a tag of 0xFFFF
 constexpr uint32_t kNoRead = 0x10000u;     // "value seen" of a position that did not read the table: equals no tag
 
-constexpr int kBatchPos = 128;                         // positions per batch: 32 producer lanes x 4
-constexpr int kRowWords = 40;                          // 32 packets + 8 flag words (one per producer lane)
-constexpr int kSlotWords = 4 * kRowWords;              // a batch = 4 rows of 32 positions
-constexpr int kRing = 32;                              // ring slots
+constexpr int kWin = 8;                                // positions per producer lane = one WINDOW = one round of the table warp
+constexpr int kBatchPos = 32 * kWin;                   // positions per batch (one producer warp iteration)
+constexpr int kRows = kBatchPos / 32;                  // rows of 32 commands per batch
+constexpr int kRowPitch = 512 + 64;                    // bytes: 32 commands of 16 B; the skew keeps the producers' stores conflict-free
+constexpr int kSlotBytes = kRows * kRowPitch;          // one batch of commands
+constexpr int kRing = 16;                              // ring slots
+constexpr int kDummyBytes = 128;                       // 64 B that always read "untouched" + 64 B of write sink
 constexpr int kProducers = 15;
 constexpr int kSeqThreads = (kProducers + 1) * 32;     // the table warp is the last one (highest issue priority)
 constexpr int kMaxTableEntries = 1 << 16;              // per CTA: 128 KiB of 16-bit entries
 constexpr int kTargetChunks = 148;                     // one chunk per SM when there is enough work
-constexpr uint32_t kMinChunkBatches = 256;             // 32 Ki positions: below this a chunk's fixed costs dominate
-static_assert(kRing >= 2 * kProducers, "a producer may run at most one ring ahead of the slowest one (mbarrier parity)");
+constexpr uint32_t kMinChunkBatches = 128;             // 32 Ki positions: below this a chunk's fixed costs dominate
+static_assert(kRing >= kProducers, "every producer must be able to hold one batch in the ring");
 
 // Number of positions the reference loop visits: groups starting at i = 0, G, 2G, .. while i < len - 7.
 inline size_t ltu_positions(size_t len, int group) {
@@ -66,7 +69,7 @@ struct SeqParams {
     uint32_t hash_bits;       // H
     uint32_t sb;              // packet = bucket << sb | tag;  sb = 32 - max(H, 16)
     uint32_t tag_mask;        // (1 << sb) - 1
-    uint32_t keep_mask;       // packet bits that reach the ring (the bucket-part bits are dropped)
+    uint32_t keep_mask;       // packet bits that select the table entry of this part (the bucket-part bits are dropped)
     uint32_t part_shift;      // part of a packet = (packet >> part_shift) & part_mask (the top bucket bits)
     uint32_t part_mask;       // parts - 1
     uint32_t table_bytes;     // entries per part * 2
@@ -92,48 +95,28 @@ struct SeqResolve {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+
+// Ring hand-over by sequence numbers in shared memory.  ready[slot] = t + 1 once batch t sits in its slot (a release
+// store by lane 0 after __syncwarp: MEMBAR.CTA + STS); consumed = t + 1 once the table warp has READ batch t (a plain
+// store: it is issued after instructions that used the loaded registers, so the loads have been performed).  Readers
+// poll with acquire loads, which are plain LDS on sm_100: ~30 cycles instead of the 90-150 of an mbarrier wait —
+// the table warp is a single warp and every cycle of its loop is on the critical path.
+__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
+__device__ __forceinline__ void st_volatile_shared(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 // Blocking wait with a guard: a protocol bug must end in a CUDA error, never in a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void wait_at_least(const uint32_t* p, uint32_t want) {
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity))
-        if (++spins > (1u << 24)) __trap();
-}
-
-// The words of the stream a producer lane needs for its four positions (bytes [pos0, pos0 + 6) of the segment):
-// three aligned 32-bit words around them; words past the last needed byte are not read.
-struct Words {
-    uint32_t w0, w1, w2;
-};
-__device__ __forceinline__ Words load_words(const uint32_t* __restrict__ base, unsigned long long widx, unsigned long long maxw) {
-    Words r;
-    r.w0 = widx <= maxw ? __ldg(base + widx) : 0u;
-    r.w1 = widx + 1 <= maxw ? __ldg(base + widx + 1) : 0u;
-    r.w2 = widx + 2 <= maxw ? __ldg(base + widx + 2) : 0u;
-    return r;
+    while ((int32_t)(ld_acquire_shared(p) - want) < 0)
+        if (++spins > (1u << 26)) __trap();
 }
 
 template <bool TOP>
@@ -152,15 +135,124 @@ __device__ __forceinline__ uint32_t make_packet(uint32_t key, const SeqParams& p
     return pkt;
 }
 
+// ---- producers --------------------------------------------------------------------------------------------------
+// One LANE = one window of kWin = 8 consecutive positions: everything that can be decided inside the window is decided
+// here, lane-locally (no shuffles, no ballots).  With pos = position inside the window and grp(pos) = pos / G:
+//   pred(i)  = the latest j < i with grp(j) < grp(i) and the bucket of i   -> i does not read the table: it is a match iff
+//              the packets are equal (same packet <=> same key); no such j -> i is a HEAD and reads the table
+//   later(i) = some j > i has the bucket of i                              -> i never writes; otherwise it is a TAIL
+// The lane then writes one 16-byte command per position: {address to load, address to store, tag, is head}.  A
+// position that is not a head loads the "always untouched" dummy (it matches nothing), one that is not a tail stores
+// into a sink: the table warp needs no data-dependent predicate.
+// FULL: every position of the batch is valid (all batches but the last one of a segment).
+template <int G, bool TOP, bool FULL>
+__device__ __forceinline__ uint32_t produce_window(const uint32_t (&wd)[4], const uint32_t sh, const uint32_t nvalid,
+                                                   const SeqParams& prm, const uint32_t part, const uint32_t table_addr,
+                                                   const uint32_t dummy_addr, const uint32_t sink_addr, uint4 (&cmd)[kWin]) {
+    // bytes 0 .. 11 of the window, then the eight 3-byte keys
+    const uint32_t v0 = __funnelshift_r(wd[0], wd[1], 8 * sh), v1 = __funnelshift_r(wd[1], wd[2], 8 * sh),
+                   v2 = __funnelshift_r(wd[2], wd[3], 8 * sh);
+    uint32_t w[kWin];
+    w[0] = make_packet<TOP>(v0 & kLtuKeyMask, prm);
+    w[1] = make_packet<TOP>(__funnelshift_r(v0, v1, 8) & kLtuKeyMask, prm);
+    w[2] = make_packet<TOP>(__funnelshift_r(v0, v1, 16) & kLtuKeyMask, prm);
+    w[3] = make_packet<TOP>(__funnelshift_r(v0, v1, 24) & kLtuKeyMask, prm);
+    w[4] = make_packet<TOP>(v1 & kLtuKeyMask, prm);
+    w[5] = make_packet<TOP>(__funnelshift_r(v1, v2, 8) & kLtuKeyMask, prm);
+    w[6] = make_packet<TOP>(__funnelshift_r(v1, v2, 16) & kLtuKeyMask, prm);
+    w[7] = make_packet<TOP>(__funnelshift_r(v1, v2, 24) & kLtuKeyMask, prm);
+    uint32_t count = 0;
+#pragma unroll
+    for (int i = 0; i < kWin; i++) {
+        bool has_pred = false, match = false, later = false;
+#pragma unroll
+        for (int j = 0; j < kWin; j++) {
+            if (j == i) continue;
+            const uint32_t x = w[i] ^ w[j];
+            const bool same_bucket = x <= prm.tag_mask;
+            if (j < i) {
+                if (j / G < i / G) {   // ascending j: the last one wins
+                    match = same_bucket ? x == 0 : match;
+                    has_pred |= same_bucket;
+                }
+            } else {
+                later |= same_bucket && (FULL || (uint32_t)j < nvalid);
+            }
+        }
+        bool act = FULL || (uint32_t)i < nvalid;
+        if (prm.part_mask) act = act && ((w[i] >> prm.part_shift) & prm.part_mask) == part;
+        const bool head = act && !has_pred, tail = act && !later;
+        count += act && has_pred && match;
+        const uint32_t entry = table_addr + (((w[i] & prm.keep_mask) >> prm.sb) << 1);
+        cmd[i].x = head ? entry : dummy_addr;
+        cmd[i].y = tail ? entry : sink_addr;
+        cmd[i].z = w[i] & 0xFFFFu;
+        cmd[i].w = head;
+    }
+    return count;
+}
+
+// ---- the table warp ---------------------------------------------------------------------------------------------
+// Lane c handles chunk c of every row: position i = c >> 2 of window (producer lane) c & 3 of the row; round k of a row =
+// window k = the lanes with (c & 3) == k: STATIC predicates.  Per row: load / store for each of the four rounds in
+// program order (a warp's shared-memory instructions are performed in order: this IS the reference's sequential loop).
+// The loads of the four rounds go to four registers (a shared destination would serialise them on the scoreboard), and
+// nothing waits for them before the next row's instructions have been issued: the commands of a whole batch are
+// fetched first, the compares come after the eight rows.
+// UNKNOWN: the chunk does not start its segment; a head that finds its entry untouched records its tag for the resolve.
+template <bool UNKNOWN>
+__device__ __forceinline__ uint32_t table_warp(const SeqChunk& ck, const uint32_t nb, uint16_t* table, const uint8_t* ring,
+                                               const uint32_t* ready, uint32_t* consumed) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t my_round = lane & 3;
+    const uint32_t table_addr = smem_u32(table);
+    uint16_t* fs = ck.first_seen + ((lane >> 2) & 3);   // position & 3
+    uint32_t count = 0;
+    for (uint32_t t = 0; t < nb; t++) {
+        wait_at_least(ready + t % kRing, t + 1);
+        const uint4* sw = reinterpret_cast<const uint4*>(ring + (size_t)(t % kRing) * kSlotBytes) + lane;
+        uint4 c[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; r++) c[r] = sw[r * (kRowPitch / 16)];
+        uint32_t seen[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; r++) {
+            uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            asm volatile(
+                "{\n"
+                " .reg .pred p0, p1, p2, p3;\n"
+                " setp.eq.u32 p0, %4, 0;\n setp.eq.u32 p1, %4, 1;\n setp.eq.u32 p2, %4, 2;\n setp.eq.u32 p3, %4, 3;\n"
+                " @p0 ld.volatile.shared.u16 %0, [%5];\n @p0 st.volatile.shared.u16 [%6], %7;\n"
+                " @p1 ld.volatile.shared.u16 %1, [%5];\n @p1 st.volatile.shared.u16 [%6], %7;\n"
+                " @p2 ld.volatile.shared.u16 %2, [%5];\n @p2 st.volatile.shared.u16 [%6], %7;\n"
+                " @p3 ld.volatile.shared.u16 %3, [%5];\n @p3 st.volatile.shared.u16 [%6], %7;\n"
+                "}\n"
+                : "+r"(s0), "+r"(s1), "+r"(s2), "+r"(s3)
+                : "r"(my_round), "r"(c[r].x), "r"(c[r].y), "r"(c[r].z)
+                : "memory");
+            seen[r] = s0 | s1 | s2 | s3;   // exactly one of them was loaded
+        }
+        // the commands have been used as addresses: their loads are complete and the slot may be refilled
+        if (lane == 0) st_volatile_shared(consumed, t + 1);
+#pragma unroll
+        for (int r = 0; r < kRows; r++) {
+            count += seen[r] == c[r].z;
+            if (UNKNOWN && seen[r] == kUntouched && c[r].w) fs[(size_t)((c[r].x - table_addr) >> 1) * 4] = (uint16_t)c[r].z;
+        }
+    }
+    return count;
+}
+
 // G: positions per group of the reference loop.  TOP: index from the top bits of the product (else: low bits).
 template <int G, bool TOP>
 __global__ void __launch_bounds__(kSeqThreads, 1)
 ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restrict__ matches, const SeqParams prm) {
     extern __shared__ __align__(16) uint8_t seq_smem[];
     uint16_t* table = reinterpret_cast<uint16_t*>(seq_smem);
-    uint32_t* ring = reinterpret_cast<uint32_t*>(seq_smem + prm.table_bytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + kRing * kSlotWords);
-    uint64_t* empty = full + kRing;
+    uint8_t* dummy = seq_smem + prm.table_bytes;          // [0, 64): never written, reads 0xFFFF; [64, 128): write sink
+    uint8_t* ring = dummy + kDummyBytes;
+    uint32_t* ready = reinterpret_cast<uint32_t*>(ring + (size_t)kRing * kSlotBytes);
+    uint32_t* consumed = ready + kRing;
 
     const SeqChunk ck = chunks[blockIdx.x];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -171,12 +263,12 @@ ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restri
     {
         uint4* t4 = reinterpret_cast<uint4*>(table);
         const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
-        for (uint32_t i = tid; i < prm.table_bytes / 16; i += kSeqThreads) t4[i] = ones;
+        for (uint32_t i = tid; i < (prm.table_bytes + kDummyBytes) / 16; i += kSeqThreads) t4[i] = ones;
         if (ck.first_seen) {
             uint4* f4 = reinterpret_cast<uint4*>(ck.first_seen);
             for (uint32_t i = tid; i < prm.table_bytes / 4; i += kSeqThreads) f4[i] = ones;   // entries * 8 bytes
         }
-        if (tid < kRing) mbar_init(full + tid, 1), mbar_init(empty + tid, 1);
+        if (tid <= (unsigned)kRing) ready[tid] = 0;   // ready[0 .. kRing) and consumed
     }
     __syncthreads();
     if (tid == 0 && ck.first && ck.part == 0) table[0] = 0;
@@ -186,109 +278,45 @@ ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restri
     if (warp < (unsigned)kProducers) {
         // =============================== producers ===============================
         const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(ck.data) & 3u);
-        const uint32_t* base = reinterpret_cast<const uint32_t*>(ck.data - sh);
-        const unsigned long long maxw = (sh + ck.npos + 1) >> 2;   // word of the last byte any valid position reads
-        const bool odd = lane & 1u;
-        auto widx_of = [&](uint32_t t) { return (ck.first_pos + (unsigned long long)t * kBatchPos + 4u * lane) >> 2; };
-        Words nxt{0, 0, 0};
-        if (warp < nb) nxt = load_words(base, widx_of(warp), maxw);
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(ck.data - sh) + (ck.first_pos >> 2);   // chunk-relative words
+        // positions of the segment still ahead at the start of the chunk (clamped: batches are 32-bit quantities)
+        const unsigned long long ahead = ck.npos - ck.first_pos;
+        const uint32_t chunk_valid = ahead > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)ahead;
+        const uint32_t maxw = (sh + chunk_valid + 1) >> 2;   // chunk-relative word of the last byte any valid position reads
+        const uint32_t table_addr = smem_u32(table), dummy_addr = smem_u32(dummy);
+        const uint32_t sink_addr = dummy_addr + 64u + 2u * lane;
+        auto load = [&](uint32_t t, uint32_t (&wd)[4]) {
+            const uint32_t widx = t * (kBatchPos / 4) + 2u * lane;   // the window's first byte is 8 * lane into the batch
+#pragma unroll
+            for (int k = 0; k < 4; k++) wd[k] = widx + k <= maxw ? __ldg(base + widx + k) : 0u;
+        };
+        uint32_t nxt[4] = {0, 0, 0, 0};
+        if (warp < nb) load(warp, nxt);
         for (uint32_t t = warp; t < nb; t += kProducers) {
-            const Words cur = nxt;
-            if (t + kProducers < nb) nxt = load_words(base, widx_of(t + kProducers), maxw);
-            const unsigned long long pos0 = ck.first_pos + (unsigned long long)t * kBatchPos + 4u * lane;
-            // bytes pos0 .. pos0+7 of the stream, then the four 3-byte keys
-            const uint32_t v0 = __funnelshift_r(cur.w0, cur.w1, 8 * sh), v1 = __funnelshift_r(cur.w1, cur.w2, 8 * sh);
-            uint32_t w[4], q[4];
-            w[0] = make_packet<TOP>(v0 & kLtuKeyMask, prm);
-            w[1] = make_packet<TOP>(__funnelshift_r(v0, v1, 8) & kLtuKeyMask, prm);
-            w[2] = make_packet<TOP>(__funnelshift_r(v0, v1, 16) & kLtuKeyMask, prm);
-            w[3] = make_packet<TOP>(__funnelshift_r(v0, v1, 24) & kLtuKeyMask, prm);
+            uint32_t cur[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) q[j] = __shfl_xor_sync(kFull, w[j], 1);
-            // validity (only the last batch of a segment has invalid positions, and they follow all valid ones)
-            uint32_t vw = 0, vq = 0;
-            {
-                const unsigned long long left = ck.npos > pos0 ? ck.npos - pos0 : 0ull;
-                vw = left >= 4 ? 0xFu : (1u << (uint32_t)left) - 1u;
-                // the partner of an even lane covers pos0 + 4 .. pos0 + 7
-                const unsigned long long leftq = left > 4 ? left - 4 : 0ull;
-                vq = leftq >= 4 ? 0xFu : (1u << (uint32_t)leftq) - 1u;
+            for (int k = 0; k < 4; k++) cur[k] = nxt[k];
+            if (t + kProducers < nb) load(t + kProducers, nxt);
+            const uint32_t pos0 = t * kBatchPos + kWin * lane;   // chunk-relative
+            uint4 cmd[kWin];
+            if (pos0 + kWin <= chunk_valid) {   // (almost always; a lane-level branch only in the last batch of a segment)
+                count += produce_window<G, TOP, true>(cur, sh, kWin, prm, ck.part, table_addr, dummy_addr, sink_addr, cmd);
+            } else {
+                const uint32_t nvalid = chunk_valid > pos0 ? chunk_valid - pos0 : 0u;
+                count += produce_window<G, TOP, false>(cur, sh, nvalid, prm, ck.part, table_addr, dummy_addr, sink_addr, cmd);
             }
-            uint32_t flags = 0;
+            // wait for the slot (the table warp has read batch t - kRing), then the commands: position i of lane l goes to
+            // chunk 4 i + (l & 3) of row l >> 2, so the eight lanes of a store phase cover 128 consecutive bytes (rows are
+            // skewed by 64 B) and table-warp lane c finds its command at chunk c
+            if (t >= (uint32_t)kRing) wait_at_least(consumed, t - kRing + 1);
+            uint4* sw = reinterpret_cast<uint4*>(ring + (size_t)(t % kRing) * kSlotBytes + (lane >> 2) * kRowPitch) + (lane & 3);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t me = w[i];
-                bool has_pred = false;
-                uint32_t predw = 0;
-                // latest earlier position of the window that lies in an earlier group and has my bucket
-                if (G == 1) {
-#pragma unroll
-                    for (int j = 3; j >= 0; j--)
-                        if (j < i) {
-                            const bool sbm = ((me ^ w[j]) >> prm.sb) == 0;
-                            if (!has_pred && sbm) has_pred = true, predw = w[j];
-                        }
-                }
-#pragma unroll
-                for (int j = 3; j >= 0; j--) {
-                    const bool sbm = odd && ((me ^ q[j]) >> prm.sb) == 0;
-                    if (!has_pred && sbm) has_pred = true, predw = q[j];
-                }
-                // any later position of the window with my bucket overwrites me
-                bool later = false;
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (j > i) later |= ((vw >> j) & 1u) && ((me ^ w[j]) >> prm.sb) == 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++) later |= !odd && ((vq >> j) & 1u) && ((me ^ q[j]) >> prm.sb) == 0;
-                const bool act = ((vw >> i) & 1u) && ((me >> prm.part_shift) & prm.part_mask) == ck.part;
-                if (act && !has_pred) flags |= 1u << i;          // head: reads the table
-                if (act && !later) flags |= 16u << i;            // tail: writes the table
-                count += act && has_pred && me == predw;         // same packet <=> same key
-            }
-            const uint32_t slot = t % kRing, use = t / kRing;
-            if (use) mbar_wait(empty + slot, (use - 1) & 1u);
-            uint32_t* sw = ring + slot * kSlotWords + (lane >> 3) * kRowWords;
-            *reinterpret_cast<uint4*>(sw + 4 * (lane & 7)) =
-                make_uint4(w[0] & prm.keep_mask, w[1] & prm.keep_mask, w[2] & prm.keep_mask, w[3] & prm.keep_mask);
-            sw[32 + (lane & 7)] = flags;
+            for (int i = 0; i < kWin; i++) sw[4 * i] = cmd[i];
             __syncwarp();
-            if (lane == 0) mbar_arrive(full + slot);
+            if (lane == 0) st_release_shared(ready + t % kRing, t + 1);
         }
     } else {
-        // =============================== the table warp ===============================
-        // round k of a row = window k = lanes 8k .. 8k+7; flags of my position: bit (lane & 3) of the quad's word
-        uint32_t rm[4], wm[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) rm[k] = (lane >> 3) == (unsigned)k ? 1u << (lane & 3) : 0u, wm[k] = rm[k] << 4;
-        const bool unknown = ck.first_seen != nullptr;
-        uint16_t* fs = ck.first_seen + (lane & 3);
-        if (nb) mbar_wait(full + 0, 0);
-        for (uint32_t t = 0; t < nb; t++) {
-            const uint32_t slot = t % kRing;
-            // probe the next slot now, use the answer after this batch (the probe's latency hides behind the rows)
-            bool next_ready = true;
-            if (t + 1 < nb) next_ready = mbar_test_wait(full + (t + 1) % kRing, ((t + 1) / kRing) & 1u);
-            const uint32_t* sw = ring + slot * kSlotWords;
-#pragma unroll
-            for (int row = 0; row < 4; row++) {
-                const uint32_t pkt = sw[row * kRowWords + lane];
-                const uint32_t f = sw[row * kRowWords + 32 + (lane >> 2)];
-                const uint32_t idx = pkt >> prm.sb;
-                volatile uint16_t* e = reinterpret_cast<volatile uint16_t*>(table) + idx;
-                uint32_t seen = kNoRead;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (f & rm[k]) seen = *e;
-                    if (f & wm[k]) *e = (uint16_t)pkt;
-                }
-                count += seen == (pkt & 0xFFFFu);
-                if (unknown && seen == kUntouched) fs[(size_t)idx * 4] = (uint16_t)pkt;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + slot);
-            if (!next_ready) mbar_wait(full + (t + 1) % kRing, ((t + 1) / kRing) & 1u);
-        }
+        count = ck.first_seen ? table_warp<true>(ck, nb, table, ring, ready, consumed) : table_warp<false>(ck, nb, table, ring, ready, consumed);
     }
     for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(kFull, count, o);
     if (lane == 0 && count) atomicAdd(&matches[ck.slot], (unsigned long long)count);
@@ -313,11 +341,13 @@ __global__ void __launch_bounds__(256) ltu_resolve_kernel(const SeqResolve* __re
             const uint2 f = __ldg(reinterpret_cast<const uint2*>(r.first_base + ((size_t)(c - 1) * entries + b) * 4));
             uint32_t o = kUntouched;
             if (c + 1 < r.nchunks) o = r.out_base[(size_t)c * entries + b];
-            // a recorded tag is never 0xFFFF, an untouched `cur` (0xFFFF) therefore matches nothing
-            count += (f.x & 0xFFFFu) == cur;
-            count += (f.x >> 16) == cur;
-            count += (f.y & 0xFFFFu) == cur;
-            count += (f.y >> 16) == cur;
+            // an empty slot holds 0xFFFF and a recorded tag never does: nothing may match while `cur` is still untouched
+            if (cur != kUntouched) {
+                count += (f.x & 0xFFFFu) == cur;
+                count += (f.x >> 16) == cur;
+                count += (f.y & 0xFFFFu) == cur;
+                count += (f.y >> 16) == cur;
+            }
             if (o != kUntouched) cur = o;
         }
     }
@@ -357,7 +387,7 @@ Geometry geometry(const LtuParams& p) {
     g.prm.part_mask = g.parts - 1u;
     g.prm.keep_mask = part_bits ? ((g.entries - 1u) << g.prm.sb) | g.prm.tag_mask : ~0u;
     g.prm.table_bytes = g.entries * 2u;
-    g.smem_bytes = g.prm.table_bytes + (size_t)kRing * kSlotWords * 4 + 2 * kRing * sizeof(uint64_t);
+    g.smem_bytes = g.prm.table_bytes + kDummyBytes + (size_t)kRing * kSlotBytes + (kRing + 1) * sizeof(uint32_t) + 12;
     return g;
 }
 
@@ -468,25 +498,28 @@ LtuParams ltu_params() {
 
 uint64_t estimator_launch_count() { return g_est_launches.load(std::memory_order_relaxed); }
 
+// Scratch for `nseg` segments with `batches` batches in total: an upper bound of what any plan of such a call needs,
+// monotone in both arguments (callers size the scratch from a worst-case segment list and then estimate a subset).
+//   chunks          <= nseg * parts + kTargetChunks      (chunk_batches keeps the cut near one wave; rounding adds one per segment)
+//   chunks with hand-over state <= min(kTargetChunks, batches * parts / kMinChunkBatches): 10 bytes per table entry each
+static size_t scratch_bound(size_t nseg, size_t batches, const Geometry& g) {
+    nseg = std::max<size_t>(nseg, 1);
+    const size_t max_chunks = nseg * g.parts + (size_t)kTargetChunks;
+    const size_t cut = std::min<size_t>((size_t)kTargetChunks, batches * g.parts / kMinChunkBatches + g.parts);
+    return result_bytes((int)std::min<size_t>(nseg, 0x7FFFFFFF)) + align_up(max_chunks * sizeof(SeqChunk), 256) +
+           align_up(nseg * g.parts * sizeof(SeqResolve), 256) + align_up(cut * (size_t)g.entries * 10, 256);
+}
+
 void LtuScratchMeter::add(size_t len) {
     nseg_++;
     batches_ += (len + kBatchPos - 1) / kBatchPos;   // >= the batches of ltu_positions(len) for any group size
 }
-size_t LtuScratchMeter::bytes() const {
-    // chunks <= segments + one wave (chunk_batches keeps the total near kTargetChunks); only chunks of segments that
-    // were cut need hand-over state, and there are at most 2 * (batches / kMinChunkBatches) of those
-    const Geometry g = geometry(ltu_params());
-    const size_t nseg = nseg_ > 0 ? nseg_ : 1;
-    const size_t max_chunks = nseg * g.parts + 4 * (size_t)kTargetChunks * g.parts;
-    const size_t cut = std::min<size_t>(4 * (size_t)kTargetChunks, 2 * (batches_ / kMinChunkBatches)) * g.parts;
-    return result_bytes((int)std::min<size_t>(nseg, 0x7FFFFFFF)) + align_up(max_chunks * sizeof(SeqChunk), 256) +
-           align_up(std::max<size_t>(nseg * g.parts, 1) * sizeof(SeqResolve), 256) + align_up(cut * (size_t)g.entries * 10, 256);
-}
+size_t LtuScratchMeter::bytes() const { return scratch_bound(nseg_, batches_, geometry(ltu_params())); }
 
 size_t ltu_scratch_bytes(const LtuSegment* segs, int nseg) {
-    const LtuParams p = ltu_params();
-    const Geometry g = geometry(p);
-    return result_bytes(nseg) + make_plan(segs, nseg, p, g, false, nullptr).total();
+    size_t batches = 0;
+    for (int i = 0; i < nseg; i++) batches += (segs[i].len + kBatchPos - 1) / kBatchPos;
+    return scratch_bound((size_t)std::max(nseg, 0), batches, geometry(ltu_params()));
 }
 
 // One launch of the table machine over all chunks of all segments, one resolve launch if any segment was cut, one

@@ -9,6 +9,9 @@
 #include <algorithm>
 #include <utility>
 #include <vector>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
 
 #include <cuda.h>   // types of cuPointerGetAttributes only; the entry point comes from cudaGetDriverEntryPoint
 
@@ -36,22 +39,59 @@ thread_local char t_error[256] = "";
         }                                                      \
     } while (0)
 
-// Staging copies for pageable caller memory: a few worker threads split each large memcpy so the
-// host side of the pipeline keeps up with the link (one thread tops out well below PCIe Gen5).
+// Copy with non-temporal stores: neither side of a staging copy is read again by this core (the pinned slot is read by
+// the DMA engine, the caller's buffer by whoever comes after the call), so the destination lines need not be fetched
+// first (a plain store reads the line it is about to overwrite: 3 bytes of DRAM traffic per byte copied instead of 2)
+// and must not evict the caches.  glibc only switches to such stores for copies far larger than the 2 MiB parts here.
+inline void stream_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+#if defined(__x86_64__) || defined(_M_X64)
+    if (n < 4096) {
+        std::memcpy(dst, src, n);
+        return;
+    }
+    const size_t head = (64 - (reinterpret_cast<uintptr_t>(dst) & 63)) & 63;
+    std::memcpy(dst, src, head);
+    dst += head, src += head, n -= head;
+    const size_t lines = n / 64;
+    for (size_t i = 0; i < lines; i++) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 32));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 48), d);
+    }
+    _mm_sfence();
+    std::memcpy(dst + 64 * lines, src + 64 * lines, n - 64 * lines);
+#else
+    std::memcpy(dst, src, n);
+#endif
+}
+
+// Staging copies for pageable caller memory: a few worker threads split each large copy so the host side of the
+// pipeline keeps up with the link (one thread tops out well below PCIe Gen5).  Two pools: one FILLS the pinned input
+// slots (driven by the submitting thread), one DRAINS the pinned output slots (driven by the pipeline's drain thread),
+// so uploads and downloads of a pageable call overlap on the host as they do on the link.
 class CopyPool {
 public:
-    static CopyPool& instance() {
+    static CopyPool& fill() {
         static CopyPool* pool = new CopyPool;  // leaked on purpose: workers outlive static destruction
+        return *pool;
+    }
+    static CopyPool& drain() {
+        static CopyPool* pool = new CopyPool;
         return *pool;
     }
     void copy(uint8_t* dst, const uint8_t* src, size_t n) {
         constexpr size_t kMinPart = 512u << 10;
         const size_t parts = std::min<size_t>(workers_.size() + 1, n / kMinPart);
         if (parts <= 1) {
-            std::memcpy(dst, src, n);
+            stream_copy(dst, src, n);
             return;
         }
-        std::lock_guard<std::mutex> serial(call_mutex_);  // one parallel copy at a time
+        std::lock_guard<std::mutex> serial(call_mutex_);  // one parallel copy at a time per pool
         const size_t per = (n / parts + 63) & ~(size_t)63;
         {
             std::lock_guard<std::mutex> lk(m_);
@@ -59,15 +99,16 @@ public:
             ++generation_;
         }
         cv_.notify_all();
-        std::memcpy(dst, src, std::min(per, n));
+        stream_copy(dst, src, std::min(per, n));
         std::unique_lock<std::mutex> lk(m_);
         done_cv_.wait(lk, [&] { return pending_ == 0; });
     }
 
 private:
     CopyPool() {
+        // each pool gets a bit under half of the cores: the two run at the same time
         unsigned hw = std::thread::hardware_concurrency();
-        unsigned n = hw >= 16 ? 7 : hw >= 8 ? 3 : hw >= 4 ? 1 : 0;
+        unsigned n = hw >= 32 ? 7 : hw >= 16 ? 5 : hw >= 8 ? 3 : hw >= 4 ? 1 : 0;
         if (const char* v = std::getenv("DLTCUDA_COPY_THREADS")) {
             const long t = std::atol(v);
             if (t >= 1 && t <= 64) n = (unsigned)t - 1;
@@ -85,7 +126,7 @@ private:
                 if (next_ >= total_parts_) seen = generation_;
             }
             const size_t off = part * per_;
-            if (off < n_) std::memcpy(dst_ + off, src_ + off, std::min(per_, n_ - off));
+            if (off < n_) stream_copy(dst_ + off, src_ + off, std::min(per_, n_ - off));
             {
                 std::lock_guard<std::mutex> lk(m_);
                 if (--pending_ == 0) done_cv_.notify_all();
@@ -101,7 +142,7 @@ private:
     uint64_t generation_ = 0;
 };
 
-inline void staged_copy(uint8_t* dst, const uint8_t* src, size_t n) { CopyPool::instance().copy(dst, src, n); }
+inline void staged_copy(uint8_t* dst, const uint8_t* src, size_t n) { CopyPool::fill().copy(dst, src, n); }
 
 Status create_context(int device, Context** out) {
     Context* c = new Context();
@@ -409,6 +450,7 @@ namespace {
 class HostPipeline {
 public:
     explicit HostPipeline(Context* ctx) : ctx_(ctx), cfg_(host_path_config()) {}
+    ~HostPipeline() { stop_drainer(); }
 
     // What prepare() learns about a job: where its buffers live and the largest chunk it will use.
     struct JobInfo {
@@ -568,6 +610,8 @@ public:
             k += r;
         }
 
+        // a pageable destination of more than a few chunks: downloads are copied out by the drain thread
+        if (!out_pinned && chunks.size() > 2) start_drainer();
         for (const auto& chunk : chunks) {
             const int slot = (int)(seq_++ % cfg_.stages);
             Status f = finish(slot);
@@ -623,6 +667,7 @@ public:
             // The host has to wait for this chunk only if it must touch the slot's staging memory again.
             pend.host_wait = !in_pinned || !out_pinned;
             if (pend.host_wait) DLT_CUDA(cudaEventRecord(ctx_->done[slot], s));
+            if (pend.ncopy && drainer_.joinable()) queue_drain(slot);
         }
         return Status::kOk;
     }
@@ -709,12 +754,14 @@ public:
             const cudaError_t e = cudaStreamSynchronize(ctx_->stream[i]);
             if (e != cudaSuccess && result == Status::kOk) note_cuda_error(e), result = Status::kCudaError;
         }
+        stop_drainer();   // idle by now: every slot has been finished
         return result;
     }
 
 private:
     struct Pending {
         bool host_wait = false;
+        bool queued = false;   // the drain thread owns the copies (guarded by dm_)
         int ncopy = 0;
         struct {
             uint8_t* dst;
@@ -723,14 +770,75 @@ private:
         } copy[kMaxStreams] = {};
     };
 
+    // The host is done with a slot once the chunk that used it has left the device AND its staged output has been
+    // copied to the caller's buffer.  Small calls do that copy right here; a large pageable call hands it to a drain
+    // thread (start_drainer), so that this thread can already fill the next chunk's input slot: uploads and downloads
+    // then overlap on the host side too, instead of taking turns on one thread.
     Status finish(int slot) {
         Pending& p = pending_[slot];
         if (!p.host_wait) return Status::kOk;
         p.host_wait = false;
+        if (drainer_.joinable()) {
+            std::unique_lock<std::mutex> lk(dm_);
+            if (p.queued) {
+                dcv_done_.wait(lk, [&] { return !pending_[slot].queued; });
+                return drain_status_;
+            }
+        }
         DLT_CUDA(cudaEventSynchronize(ctx_->done[slot]));
         for (int i = 0; i < p.ncopy; i++) staged_copy(p.copy[i].dst, p.copy[i].src, p.copy[i].n);
         p.ncopy = 0;
         return Status::kOk;
+    }
+
+    void start_drainer() {
+        if (drainer_.joinable()) return;
+        try {
+            drainer_ = std::thread([this] {
+                cudaSetDevice(ctx_->device);
+                for (;;) {
+                    int slot;
+                    {
+                        std::unique_lock<std::mutex> lk(dm_);
+                        dcv_work_.wait(lk, [&] { return dstop_ || dhead_ != dtail_; });
+                        if (dhead_ == dtail_) return;   // stop requested and nothing left
+                        slot = dqueue_[dhead_ % kDrainQueue];
+                    }
+                    Pending& p = pending_[slot];
+                    Status st = Status::kOk;
+                    const cudaError_t e = cudaEventSynchronize(ctx_->done[slot]);
+                    if (e != cudaSuccess) note_cuda_error(e), st = Status::kCudaError;
+                    else
+                        for (int i = 0; i < p.ncopy; i++) CopyPool::drain().copy(p.copy[i].dst, p.copy[i].src, p.copy[i].n);
+                    {
+                        std::lock_guard<std::mutex> lk(dm_);
+                        p.ncopy = 0, p.queued = false, dhead_++;
+                        if (st != Status::kOk) drain_status_ = st;
+                    }
+                    dcv_done_.notify_all();
+                }
+            });
+        } catch (...) {
+            // no thread: the copies stay on the submitting thread (finish)
+        }
+    }
+    void stop_drainer() {
+        if (!drainer_.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(dm_);
+            dstop_ = true;
+        }
+        dcv_work_.notify_all();
+        drainer_.join();
+    }
+    // queue the staged output of `slot` for the drain thread (the slot's event has been recorded)
+    void queue_drain(int slot) {
+        {
+            std::lock_guard<std::mutex> lk(dm_);
+            pending_[slot].queued = true;
+            dqueue_[dtail_ % kDrainQueue] = slot, dtail_++;
+        }
+        dcv_work_.notify_all();
     }
 
     struct ZeroCopyGroup {
@@ -752,6 +860,15 @@ private:
     const HostPathConfig& cfg_;
     Slots slots_{};
     Pending pending_[kStages];
+    // drain thread (large pageable calls only)
+    static constexpr int kDrainQueue = 2 * kStages;
+    std::thread drainer_;
+    std::mutex dm_;
+    std::condition_variable dcv_work_, dcv_done_;
+    int dqueue_[kDrainQueue] = {};
+    size_t dhead_ = 0, dtail_ = 0;
+    bool dstop_ = false;
+    Status drain_status_ = Status::kOk;
     size_t seq_ = 0;
     PinnedRanges pinned_;
     std::vector<JobInfo> info_;
