@@ -113,10 +113,16 @@ __device__ __forceinline__ void st_volatile_shared(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 // Blocking wait with a guard: a protocol bug must end in a CUDA error, never in a hung GPU.
+// SLEEP: back off between polls.  The producers run ahead of the table warp and spend most of their time waiting for a
+// free slot; polling flat out they issued 280 M shared-memory loads per launch (ncu, r02_seq_v2) into the same LSU the
+// table warp's loads and stores go through.
+template <bool SLEEP>
 __device__ __forceinline__ void wait_at_least(const uint32_t* p, uint32_t want) {
     uint32_t spins = 0;
-    while ((int32_t)(ld_acquire_shared(p) - want) < 0)
-        if (++spins > (1u << 26)) __trap();
+    while ((int32_t)(ld_acquire_shared(p) - want) < 0) {
+        if (SLEEP) __nanosleep(256);
+        if (++spins > (1u << 24)) __trap();
+    }
 }
 
 template <bool TOP>
@@ -208,8 +214,10 @@ __device__ __forceinline__ uint32_t table_warp(const SeqChunk& ck, const uint32_
     const uint32_t table_addr = smem_u32(table);
     uint16_t* fs = ck.first_seen + ((lane >> 2) & 3);   // position & 3
     uint32_t count = 0;
+    uint32_t flag = nb ? ld_acquire_shared(ready) : 0u;   // ready[slot of batch t], fetched one batch ahead
     for (uint32_t t = 0; t < nb; t++) {
-        wait_at_least(ready + t % kRing, t + 1);
+        if ((int32_t)(flag - (t + 1)) < 0) wait_at_least<false>(ready + t % kRing, t + 1);
+        if (t + 1 < nb) flag = ld_acquire_shared(ready + (t + 1) % kRing);
         const uint4* sw = reinterpret_cast<const uint4*>(ring + (size_t)(t % kRing) * kSlotBytes) + lane;
         uint4 c[kRows];
 #pragma unroll
@@ -308,7 +316,7 @@ ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restri
             // wait for the slot (the table warp has read batch t - kRing), then the commands: position i of lane l goes to
             // chunk 4 i + (l & 3) of row l >> 2, so the eight lanes of a store phase cover 128 consecutive bytes (rows are
             // skewed by 64 B) and table-warp lane c finds its command at chunk c
-            if (t >= (uint32_t)kRing) wait_at_least(consumed, t - kRing + 1);
+            if (t >= (uint32_t)kRing) wait_at_least<true>(consumed, t - kRing + 1);
             uint4* sw = reinterpret_cast<uint4*>(ring + (size_t)(t % kRing) * kSlotBytes + (lane >> 2) * kRowPitch) + (lane & 3);
 #pragma unroll
             for (int i = 0; i < kWin; i++) sw[4 * i] = cmd[i];
