@@ -45,15 +45,18 @@ constexpr uint32_t kUntouched = 0xFFFFu;   // table entry: no position of this b
 constexpr uint32_t kAlias = 0xFFFEu;       // stored instead of a tag of 0xFFFF
 constexpr uint32_t kNoRead = 0x10000u;     // "value seen" of a position that did not read the table: equals no tag
 
-constexpr int kWin = 8;                                // positions per producer lane = one WINDOW = one round of the table warp
-constexpr int kBatchPos = 32 * kWin;                   // positions per batch (one producer warp iteration)
-constexpr int kRows = kBatchPos / 32;                  // rows of 32 commands per batch
-constexpr int kRowPitch = 512 + 64;                    // bytes: 32 commands of 16 B; the skew keeps the producers' stores conflict-free
-constexpr int kSlotBytes = kRows * kRowPitch;          // one batch of commands
-constexpr int kRing = 16;                              // ring slots
+constexpr int kRows = 8;                                // rows of 32 consecutive positions per batch: one row = one WINDOW = one round of the table warp
+constexpr int kBatchPos = 32 * kRows;                  // positions per batch (one producer warp iteration)
+constexpr int kRowBytes = 32 * 16;                     // 32 commands of 16 B
+constexpr int kSlotBytes = kRows * kRowBytes;          // one batch of commands
+constexpr int kRing = 12;                              // ring slots
 constexpr int kDummyBytes = 128;                       // 64 B that always read "untouched" + 64 B of write sink
-constexpr int kProducers = 15;
-constexpr int kSeqThreads = (kProducers + 1) * 32;     // the table warp is the last one (highest issue priority)
+// Warp w runs on scheduler w & 3.  The table warp (warp 0) is the serial part of the machine: it gets its scheduler to
+// itself (warps 4, 8, 12 go straight to the final barrier), the 12 producers share the other three.  With a producer
+// on its scheduler the table warp issued one instruction every ~5 cycles (round-2 v2, ncu: r02_seq_v2).
+constexpr int kWarps = 16;
+constexpr int kProducers = 12;
+constexpr int kSeqThreads = kWarps * 32;
 constexpr int kMaxTableEntries = 1 << 16;              // per CTA: 128 KiB of 16-bit entries
 constexpr int kTargetChunks = 148;                     // one chunk per SM when there is enough work
 constexpr uint32_t kMinChunkBatches = 128;             // 32 Ki positions: below this a chunk's fixed costs dominate
@@ -113,14 +116,13 @@ __device__ __forceinline__ void st_volatile_shared(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 // Blocking wait with a guard: a protocol bug must end in a CUDA error, never in a hung GPU.
-// SLEEP: back off between polls.  The producers run ahead of the table warp and spend most of their time waiting for a
-// free slot; polling flat out they issued 280 M shared-memory loads per launch (ncu, r02_seq_v2) into the same LSU the
-// table warp's loads and stores go through.
+// SLEEP: back off between polls (the producers run ahead of the table warp; their polls go through the same LSU as
+// the table warp's loads and stores).
 template <bool SLEEP>
 __device__ __forceinline__ void wait_at_least(const uint32_t* p, uint32_t want) {
     uint32_t spins = 0;
     while ((int32_t)(ld_acquire_shared(p) - want) < 0) {
-        if (SLEEP) __nanosleep(256);
+        if (SLEEP) __nanosleep(128);
         if (++spins > (1u << 24)) __trap();
     }
 }
@@ -142,77 +144,153 @@ __device__ __forceinline__ uint32_t make_packet(uint32_t key, const SeqParams& p
 }
 
 // ---- producers --------------------------------------------------------------------------------------------------
-// One LANE = one window of kWin = 8 consecutive positions: everything that can be decided inside the window is decided
-// here, lane-locally (no shuffles, no ballots).  With pos = position inside the window and grp(pos) = pos / G:
-//   pred(i)  = the latest j < i with grp(j) < grp(i) and the bucket of i   -> i does not read the table: it is a match iff
-//              the packets are equal (same packet <=> same key); no such j -> i is a HEAD and reads the table
-//   later(i) = some j > i has the bucket of i                              -> i never writes; otherwise it is a TAIL
-// The lane then writes one 16-byte command per position: {address to load, address to store, tag, is head}.  A
-// position that is not a head loads the "always untouched" dummy (it matches nothing), one that is not a tail stores
-// into a sink: the table warp needs no data-dependent predicate.
-// FULL: every position of the batch is valid (all batches but the last one of a segment).
-template <int G, bool TOP, bool FULL>
-__device__ __forceinline__ uint32_t produce_window(const uint32_t (&wd)[4], const uint32_t sh, const uint32_t nvalid,
-                                                   const SeqParams& prm, const uint32_t part, const uint32_t table_addr,
-                                                   const uint32_t dummy_addr, const uint32_t sink_addr, uint4 (&cmd)[kWin]) {
-    // bytes 0 .. 11 of the window, then the eight 3-byte keys
-    const uint32_t v0 = __funnelshift_r(wd[0], wd[1], 8 * sh), v1 = __funnelshift_r(wd[1], wd[2], 8 * sh),
-                   v2 = __funnelshift_r(wd[2], wd[3], 8 * sh);
-    uint32_t w[kWin];
-    w[0] = make_packet<TOP>(v0 & kLtuKeyMask, prm);
-    w[1] = make_packet<TOP>(__funnelshift_r(v0, v1, 8) & kLtuKeyMask, prm);
-    w[2] = make_packet<TOP>(__funnelshift_r(v0, v1, 16) & kLtuKeyMask, prm);
-    w[3] = make_packet<TOP>(__funnelshift_r(v0, v1, 24) & kLtuKeyMask, prm);
-    w[4] = make_packet<TOP>(v1 & kLtuKeyMask, prm);
-    w[5] = make_packet<TOP>(__funnelshift_r(v1, v2, 8) & kLtuKeyMask, prm);
-    w[6] = make_packet<TOP>(__funnelshift_r(v1, v2, 16) & kLtuKeyMask, prm);
-    w[7] = make_packet<TOP>(__funnelshift_r(v1, v2, 24) & kLtuKeyMask, prm);
+// A batch = 8 rows of 32 consecutive positions, lane = position inside the row.  A ROW is a window: everything that can be
+// decided inside it is decided here.  With grp(i) = i / G:
+//   pred(i)  = the highest lane j with grp(j) < grp(i) and the bucket of i -> i does not read the table: it is a match iff the
+//              packets are equal (same packet <=> same key); no such j -> i is a HEAD and reads the table
+//   later(i) = some lane j > i has the bucket of i                        -> i never writes; otherwise it is a TAIL
+// Two heads of one bucket lie in the same group (else the later one has a pred), a tail is the last position of its bucket:
+// the table warp may perform all loads of a row, then all stores of the row.  The lane writes one 16-byte command:
+// {address to load, address to store, tag, is head}.  A position that is not a head loads the "always untouched" dummy (it
+// matches nothing), one that is not a tail stores into a sink: the table warp needs no data-dependent predicate.
+//
+// Finding the lanes of one bucket is a MATCH.ANY, and MATCH.ANY is one unit per SM that spends 2 cycles per DISTINCT value:
+// 64 cycles for a row of 32 different buckets (tools/microbench/match_bench.cu), which made the whole kernel run at exactly
+// 8 x 64 cycles per batch.  But a row of 32 different buckets needs no resolution at all — every lane is head and tail — and
+// that is the common case wherever MATCH.ANY is slow.  So each row is first screened through a per-warp scratch of 4096 byte
+// slots: every lane stores its lane id at slot (bucket mod 4096) and loads it back; two lanes of one bucket share a slot, so at
+// least one of them reads a foreign id (no false negatives, whatever else hits the slot).  Only rows with such a lane take
+// the MATCH.ANY path (random buckets: 11 % of the rows, through slot collisions of different buckets), and there the lanes that are alone in
+// their slot enter with one common value: MATCH.ANY only pays for the contested buckets.
+constexpr int kScratchSlots = 4096;
+
+template <bool FAST16, bool TOP>
+__device__ __forceinline__ uint32_t packet_of(uint32_t key, const SeqParams& prm) {
+    if (FAST16) {   // H = 16, index from the top bits: the packet is the product itself
+        uint32_t pkt = key * kLtuGoldenRatio;
+        if ((pkt & 0xFFFFu) == kUntouched) pkt ^= (kUntouched ^ kAlias);
+        return pkt;
+    }
+    return make_packet<TOP>(key, prm);
+}
+
+// FULL: every position of the batch is valid and the table is not split (all batches but the last one of a segment).
+template <int G, bool TOP, bool FAST16, bool FULL>
+__device__ __forceinline__ uint32_t produce_batch(const uint32_t (&wa)[kRows], const uint32_t (&wb)[kRows], const uint32_t fsh,
+                                                  const uint32_t pos0, const uint32_t chunk_valid, const SeqParams& prm,
+                                                  const uint32_t part, const uint32_t table_addr, const uint32_t dummy_addr,
+                                                  const uint32_t sink_addr, const uint32_t scratch_addr, uint4* sw) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t below = (1u << (lane & ~(unsigned)(G - 1))) - 1u;   // the lanes of earlier groups
     uint32_t count = 0;
 #pragma unroll
-    for (int i = 0; i < kWin; i++) {
-        bool has_pred = false, match = false, later = false;
+    for (int r = 0; r < kRows; r++) {
+        const uint32_t pkt = packet_of<FAST16, TOP>(__funnelshift_r(wa[r], wb[r], fsh) & kLtuKeyMask, prm);
+        bool act = true;
+        if (!FULL) {
+            act = pos0 + 32u * r < chunk_valid;
+            if (prm.part_mask) act = act && ((pkt >> prm.part_shift) & prm.part_mask) == part;
+        }
+        const uint32_t bucket = FAST16 ? pkt >> 16 : pkt >> prm.sb;
+        const uint32_t entry = FAST16 ? table_addr + ((pkt >> 15) & 0x1FFFEu) : table_addr + (((pkt & prm.keep_mask) >> prm.sb) << 1);
+        // screen: does any lane share its scratch slot with another lane of this row?
+        const uint32_t slot = scratch_addr + (bucket & (kScratchSlots - 1));
+        uint32_t winner = lane;
+        if (act) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(slot), "r"(lane) : "memory");
+        __syncwarp();
+        if (act) asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(winner) : "r"(slot) : "memory");
+        const bool loser = winner != lane;
+        bool head = act, tail = act;
+        if (__any_sync(kFull, loser)) {
+            // second pass: the losers mark their slot, so that the lane that won it learns that it is contested too
+            if (loser) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(slot), "r"(0xFFu) : "memory");
+            __syncwarp();
+            if (act && !loser) asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(winner) : "r"(slot) : "memory");
+            const bool contested = winner != lane;   // the lanes that may share their bucket with another lane of the row
+            // every other lane is alone in its slot, hence in its bucket: head and tail.  They all enter MATCH.ANY with one common
+            // value (a real bucket has at most 17 bits), so that it sees few distinct values.
+            const uint32_t same = __match_any_sync(kFull, contested ? bucket : 0xFFFFFFFFu);
+            if (contested) {
+                const uint32_t lower = same & below;
+                head = lower == 0u;
+                tail = (same >> lane) == 1u;
+            }
+            const uint32_t lower = contested ? same & below : 0u;
+            const uint32_t ppkt = __shfl_sync(kFull, pkt, lower ? 31u - (uint32_t)__clz(lower) : lane);
+            count += lower != 0u && ppkt == pkt;
+        }
+        sw[r * 32] = make_uint4(head ? entry : dummy_addr, tail ? entry : sink_addr, pkt & 0xFFFFu, head);
+    }
+    return count;
+}
+
+template <int G, bool TOP, bool FAST16>
+__device__ __forceinline__ uint32_t producer_warp(const SeqChunk& ck, const uint32_t nb, const uint32_t pi, const SeqParams& prm,
+                                                  const uint32_t table_addr, const uint32_t dummy_addr, const uint32_t scratch_addr,
+                                                  uint8_t* ring, uint32_t* ready, const uint32_t* consumed) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(ck.data) & 3u);
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(ck.data - sh) + (ck.first_pos >> 2);   // chunk-relative words
+    // positions of the segment still ahead at the start of the chunk (clamped: batches are 32-bit quantities)
+    const unsigned long long ahead = ck.npos - ck.first_pos;
+    const uint32_t chunk_valid = ahead > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)ahead;
+    const uint32_t maxw = (sh + chunk_valid + 1) >> 2;   // chunk-relative word of the last byte any valid position reads
+    const uint32_t sink_addr = dummy_addr + 64u + 2u * lane;
+    // the key of position (row base + lane) starts at byte lane + sh of the row's first word
+    const uint32_t wofs = (lane + sh) >> 2, fsh = ((lane + sh) & 3u) * 8u;
+    auto load = [&](uint32_t t, uint32_t (&a)[kRows], uint32_t (&b)[kRows]) {
+        const uint32_t w0 = t * (kBatchPos / 4) + wofs;
+        if (w0 + 8u * (kRows - 1) + 1 <= maxw) {   // (a lane-level branch only in the last batch of a segment)
 #pragma unroll
-        for (int j = 0; j < kWin; j++) {
-            if (j == i) continue;
-            const uint32_t x = w[i] ^ w[j];
-            const bool same_bucket = x <= prm.tag_mask;
-            if (j < i) {
-                if (j / G < i / G) {   // ascending j: the last one wins
-                    match = same_bucket ? x == 0 : match;
-                    has_pred |= same_bucket;
-                }
-            } else {
-                later |= same_bucket && (FULL || (uint32_t)j < nvalid);
+            for (int r = 0; r < kRows; r++) {
+                a[r] = __ldg(base + w0 + 8 * r);
+                b[r] = __ldg(base + w0 + 8 * r + 1);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kRows; r++) {
+                const uint32_t w = w0 + 8u * r;
+                a[r] = w <= maxw ? __ldg(base + w) : 0u;
+                b[r] = w + 1 <= maxw ? __ldg(base + w + 1) : 0u;
             }
         }
-        bool act = FULL || (uint32_t)i < nvalid;
-        if (prm.part_mask) act = act && ((w[i] >> prm.part_shift) & prm.part_mask) == part;
-        const bool head = act && !has_pred, tail = act && !later;
-        count += act && has_pred && match;
-        const uint32_t entry = table_addr + (((w[i] & prm.keep_mask) >> prm.sb) << 1);
-        cmd[i].x = head ? entry : dummy_addr;
-        cmd[i].y = tail ? entry : sink_addr;
-        cmd[i].z = w[i] & 0xFFFFu;
-        cmd[i].w = head;
+    };
+    uint32_t count = 0;
+    uint32_t na[kRows], nbw[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; r++) na[r] = nbw[r] = 0u;
+    if (pi < nb) load(pi, na, nbw);
+    for (uint32_t t = pi; t < nb; t += kProducers) {
+        uint32_t ca[kRows], cb[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; r++) ca[r] = na[r], cb[r] = nbw[r];
+        if (t + kProducers < nb) load(t + kProducers, na, nbw);
+        // wait for the slot: the table warp has read batch t - kRing
+        if (t >= (uint32_t)kRing) wait_at_least<true>(consumed, t - kRing + 1);
+        uint4* sw = reinterpret_cast<uint4*>(ring + (size_t)(t % kRing) * kSlotBytes) + lane;
+        const uint32_t pos0 = t * kBatchPos + lane;   // chunk-relative
+        if (prm.part_mask == 0u && (t + 1) * (uint32_t)kBatchPos <= chunk_valid)
+            count += produce_batch<G, TOP, FAST16, true>(ca, cb, fsh, pos0, chunk_valid, prm, ck.part, table_addr, dummy_addr, sink_addr, scratch_addr, sw);
+        else
+            count += produce_batch<G, TOP, FAST16, false>(ca, cb, fsh, pos0, chunk_valid, prm, ck.part, table_addr, dummy_addr, sink_addr, scratch_addr, sw);
+        __syncwarp();
+        if (lane == 0) st_release_shared(ready + t % kRing, t + 1);
     }
     return count;
 }
 
 // ---- the table warp ---------------------------------------------------------------------------------------------
-// Lane c handles chunk c of every row: position i = c >> 2 of window (producer lane) c & 3 of the row; round k of a row =
-// window k = the lanes with (c & 3) == k: STATIC predicates.  Per row: load / store for each of the four rounds in
-// program order (a warp's shared-memory instructions are performed in order: this IS the reference's sequential loop).
-// The loads of the four rounds go to four registers (a shared destination would serialise them on the scoreboard), and
-// nothing waits for them before the next row's instructions have been issued: the commands of a whole batch are
-// fetched first, the compares come after the eight rows.
+// Lane c handles position c of every row; per row ONE load and ONE store of all 32 lanes, in program order (a warp's
+// shared-memory instructions are performed in order: this IS the reference's sequential loop).  Nothing waits for the
+// loaded values before the next rows' instructions have been issued: the commands of a whole batch are fetched first, the
+// compares come after the eight rows.
 // UNKNOWN: the chunk does not start its segment; a head that finds its entry untouched records its tag for the resolve.
 template <bool UNKNOWN>
 __device__ __forceinline__ uint32_t table_warp(const SeqChunk& ck, const uint32_t nb, uint16_t* table, const uint8_t* ring,
                                                const uint32_t* ready, uint32_t* consumed) {
     const unsigned lane = threadIdx.x & 31;
-    const uint32_t my_round = lane & 3;
     const uint32_t table_addr = smem_u32(table);
-    uint16_t* fs = ck.first_seen + ((lane >> 2) & 3);   // position & 3
+    uint16_t* fs = ck.first_seen + (lane & 3);   // position & 3
     uint32_t count = 0;
     uint32_t flag = nb ? ld_acquire_shared(ready) : 0u;   // ready[slot of batch t], fetched one batch ahead
     for (uint32_t t = 0; t < nb; t++) {
@@ -221,25 +299,12 @@ __device__ __forceinline__ uint32_t table_warp(const SeqChunk& ck, const uint32_
         const uint4* sw = reinterpret_cast<const uint4*>(ring + (size_t)(t % kRing) * kSlotBytes) + lane;
         uint4 c[kRows];
 #pragma unroll
-        for (int r = 0; r < kRows; r++) c[r] = sw[r * (kRowPitch / 16)];
+        for (int r = 0; r < kRows; r++) c[r] = sw[r * 32];
         uint32_t seen[kRows];
 #pragma unroll
-        for (int r = 0; r < kRows; r++) {
-            uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            asm volatile(
-                "{\n"
-                " .reg .pred p0, p1, p2, p3;\n"
-                " setp.eq.u32 p0, %4, 0;\n setp.eq.u32 p1, %4, 1;\n setp.eq.u32 p2, %4, 2;\n setp.eq.u32 p3, %4, 3;\n"
-                " @p0 ld.volatile.shared.u16 %0, [%5];\n @p0 st.volatile.shared.u16 [%6], %7;\n"
-                " @p1 ld.volatile.shared.u16 %1, [%5];\n @p1 st.volatile.shared.u16 [%6], %7;\n"
-                " @p2 ld.volatile.shared.u16 %2, [%5];\n @p2 st.volatile.shared.u16 [%6], %7;\n"
-                " @p3 ld.volatile.shared.u16 %3, [%5];\n @p3 st.volatile.shared.u16 [%6], %7;\n"
-                "}\n"
-                : "+r"(s0), "+r"(s1), "+r"(s2), "+r"(s3)
-                : "r"(my_round), "r"(c[r].x), "r"(c[r].y), "r"(c[r].z)
-                : "memory");
-            seen[r] = s0 | s1 | s2 | s3;   // exactly one of them was loaded
-        }
+        for (int r = 0; r < kRows; r++)
+            asm volatile("ld.volatile.shared.u16 %0, [%1];\n st.volatile.shared.u16 [%2], %3;"
+                         : "=r"(seen[r]) : "r"(c[r].x), "r"(c[r].y), "r"(c[r].z) : "memory");
         // the commands have been used as addresses: their loads are complete and the slot may be refilled
         if (lane == 0) st_volatile_shared(consumed, t + 1);
 #pragma unroll
@@ -252,14 +317,15 @@ __device__ __forceinline__ uint32_t table_warp(const SeqChunk& ck, const uint32_
 }
 
 // G: positions per group of the reference loop.  TOP: index from the top bits of the product (else: low bits).
-template <int G, bool TOP>
+template <int G, bool TOP, bool FAST16>
 __global__ void __launch_bounds__(kSeqThreads, 1)
 ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restrict__ matches, const SeqParams prm) {
     extern __shared__ __align__(16) uint8_t seq_smem[];
     uint16_t* table = reinterpret_cast<uint16_t*>(seq_smem);
     uint8_t* dummy = seq_smem + prm.table_bytes;          // [0, 64): never written, reads 0xFFFF; [64, 128): write sink
     uint8_t* ring = dummy + kDummyBytes;
-    uint32_t* ready = reinterpret_cast<uint32_t*>(ring + (size_t)kRing * kSlotBytes);
+    uint8_t* scratch = ring + (size_t)kRing * kSlotBytes;   // kProducers x kScratchSlots bytes (contents never matter)
+    uint32_t* ready = reinterpret_cast<uint32_t*>(scratch + (size_t)kProducers * kScratchSlots);
     uint32_t* consumed = ready + kRing;
 
     const SeqChunk ck = chunks[blockIdx.x];
@@ -283,48 +349,12 @@ ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restri
     __syncthreads();
 
     uint32_t count = 0;
-    if (warp < (unsigned)kProducers) {
-        // =============================== producers ===============================
-        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(ck.data) & 3u);
-        const uint32_t* base = reinterpret_cast<const uint32_t*>(ck.data - sh) + (ck.first_pos >> 2);   // chunk-relative words
-        // positions of the segment still ahead at the start of the chunk (clamped: batches are 32-bit quantities)
-        const unsigned long long ahead = ck.npos - ck.first_pos;
-        const uint32_t chunk_valid = ahead > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)ahead;
-        const uint32_t maxw = (sh + chunk_valid + 1) >> 2;   // chunk-relative word of the last byte any valid position reads
-        const uint32_t table_addr = smem_u32(table), dummy_addr = smem_u32(dummy);
-        const uint32_t sink_addr = dummy_addr + 64u + 2u * lane;
-        auto load = [&](uint32_t t, uint32_t (&wd)[4]) {
-            const uint32_t widx = t * (kBatchPos / 4) + 2u * lane;   // the window's first byte is 8 * lane into the batch
-#pragma unroll
-            for (int k = 0; k < 4; k++) wd[k] = widx + k <= maxw ? __ldg(base + widx + k) : 0u;
-        };
-        uint32_t nxt[4] = {0, 0, 0, 0};
-        if (warp < nb) load(warp, nxt);
-        for (uint32_t t = warp; t < nb; t += kProducers) {
-            uint32_t cur[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) cur[k] = nxt[k];
-            if (t + kProducers < nb) load(t + kProducers, nxt);
-            const uint32_t pos0 = t * kBatchPos + kWin * lane;   // chunk-relative
-            uint4 cmd[kWin];
-            if (pos0 + kWin <= chunk_valid) {   // (almost always; a lane-level branch only in the last batch of a segment)
-                count += produce_window<G, TOP, true>(cur, sh, kWin, prm, ck.part, table_addr, dummy_addr, sink_addr, cmd);
-            } else {
-                const uint32_t nvalid = chunk_valid > pos0 ? chunk_valid - pos0 : 0u;
-                count += produce_window<G, TOP, false>(cur, sh, nvalid, prm, ck.part, table_addr, dummy_addr, sink_addr, cmd);
-            }
-            // wait for the slot (the table warp has read batch t - kRing), then the commands: position i of lane l goes to
-            // chunk 4 i + (l & 3) of row l >> 2, so the eight lanes of a store phase cover 128 consecutive bytes (rows are
-            // skewed by 64 B) and table-warp lane c finds its command at chunk c
-            if (t >= (uint32_t)kRing) wait_at_least<true>(consumed, t - kRing + 1);
-            uint4* sw = reinterpret_cast<uint4*>(ring + (size_t)(t % kRing) * kSlotBytes + (lane >> 2) * kRowPitch) + (lane & 3);
-#pragma unroll
-            for (int i = 0; i < kWin; i++) sw[4 * i] = cmd[i];
-            __syncwarp();
-            if (lane == 0) st_release_shared(ready + t % kRing, t + 1);
-        }
-    } else {
+    if (warp == 0) {
         count = ck.first_seen ? table_warp<true>(ck, nb, table, ring, ready, consumed) : table_warp<false>(ck, nb, table, ring, ready, consumed);
+    } else if (warp & 3) {
+        const uint32_t pi = warp - 1 - (warp >> 2);
+        count = producer_warp<G, TOP, FAST16>(ck, nb, pi, prm, smem_u32(table), smem_u32(dummy), smem_u32(scratch) + pi * kScratchSlots, ring,
+                                              ready, consumed);
     }
     for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(kFull, count, o);
     if (lane == 0 && count) atomicAdd(&matches[ck.slot], (unsigned long long)count);
@@ -395,7 +425,7 @@ Geometry geometry(const LtuParams& p) {
     g.prm.part_mask = g.parts - 1u;
     g.prm.keep_mask = part_bits ? ((g.entries - 1u) << g.prm.sb) | g.prm.tag_mask : ~0u;
     g.prm.table_bytes = g.entries * 2u;
-    g.smem_bytes = g.prm.table_bytes + kDummyBytes + (size_t)kRing * kSlotBytes + (kRing + 1) * sizeof(uint32_t) + 12;
+    g.smem_bytes = g.prm.table_bytes + kDummyBytes + (size_t)kRing * kSlotBytes + (size_t)kProducers * kScratchSlots + (kRing + 1) * sizeof(uint32_t) + 12;
     return g;
 }
 
@@ -479,12 +509,12 @@ Plan make_plan(const LtuSegment* segs, int nseg, const LtuParams& p, const Geome
     return pl;
 }
 
-template <int G, bool TOP>
+template <int G, bool TOP, bool FAST16>
 cudaError_t launch_seq(const SeqChunk* d_chunks, int n, unsigned long long* d_matches, const Geometry& g, cudaStream_t stream) {
     // function attributes are per device: set it on every call (microseconds), a process may drive several GPUs
-    cudaError_t e = cudaFuncSetAttribute(ltu_seq_kernel<G, TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(ltu_seq_kernel<G, TOP, FAST16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
     if (e != cudaSuccess) return e;
-    ltu_seq_kernel<G, TOP><<<n, kSeqThreads, g.smem_bytes, stream>>>(d_chunks, d_matches, g.prm);
+    ltu_seq_kernel<G, TOP, FAST16><<<n, kSeqThreads, g.smem_bytes, stream>>>(d_chunks, d_matches, g.prm);
     return cudaGetLastError();
 }
 
@@ -560,8 +590,9 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
         if (e != cudaSuccess) return fail(e);
         const SeqChunk* dc = reinterpret_cast<const SeqChunk*>(d_chunk_desc);
         const int n = (int)pl.chunks.size();
-        if (p.group == 4) e = p.index_top ? launch_seq<4, true>(dc, n, d_matches, g, stream) : launch_seq<4, false>(dc, n, d_matches, g, stream);
-        else e = p.index_top ? launch_seq<1, true>(dc, n, d_matches, g, stream) : launch_seq<1, false>(dc, n, d_matches, g, stream);
+        if (p.group == 4 && p.index_top && p.hash_bits == 16) e = launch_seq<4, true, true>(dc, n, d_matches, g, stream);   // the restated crate
+        else if (p.group == 4) e = p.index_top ? launch_seq<4, true, false>(dc, n, d_matches, g, stream) : launch_seq<4, false, false>(dc, n, d_matches, g, stream);
+        else e = p.index_top ? launch_seq<1, true, false>(dc, n, d_matches, g, stream) : launch_seq<1, false, false>(dc, n, d_matches, g, stream);
         if (e != cudaSuccess) return fail(e);
         g_est_launches.fetch_add(1, std::memory_order_relaxed);
         if (!pl.resolves.empty()) {
