@@ -43,24 +43,24 @@ LtuParams g_params;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kUntouched = 0xFFFFu;   // table entry: no position of this bucket seen yet
 constexpr uint32_t kAlias = 0xFFFEu;       // stored instead of a tag of 0xFFFF
-constexpr uint32_t kNoRead = 0x10000u;     // "value seen" of a position that did not read the table: equals no tag
 
 constexpr int kRows = 8;                                // rows of 32 consecutive positions per batch: one row = one WINDOW = one round of the table warp
 constexpr int kBatchPos = 32 * kRows;                  // positions per batch (one producer warp iteration)
-constexpr int kRowBytes = 32 * 16;                     // 32 commands of 16 B
-constexpr int kSlotBytes = kRows * kRowBytes;          // one batch of commands
-constexpr int kRing = 12;                              // ring slots
-constexpr int kDummyBytes = 128;                       // 64 B that always read "untouched" + 64 B of write sink
-// Warp w runs on scheduler w & 3.  The table warp (warp 0) is the serial part of the machine: it gets its scheduler to
-// itself (warps 4, 8, 12 go straight to the final barrier), the 12 producers share the other three.  With a producer
-// on its scheduler the table warp issued one instruction every ~5 cycles (round-2 v2, ncu: r02_seq_v2).
+constexpr int kSlotBytes = kRows * 32 * 8;             // one batch of commands: 8 bytes per position
+constexpr int kSeenBytes = kRows * 32 * 2;             // one batch of answers: what every position found in the table (16 bits)
+constexpr int kRing = 16;                              // ring slots (a power of two)
+constexpr int kSinkBytes = 64;                         // where positions that do not exist load and store: one 16-bit word per lane
+constexpr int kScratchSlots = 2048;                    // per producer warp: byte slots of the row screen (a power of two)
+// 16 warps: the table warp and 15 producers.  (Keeping the table warp's scheduler to itself — producers only on the other
+// three — did not make it faster: its pace is the LSU's dispatch rate of one instruction per 4 cycles and per warp, with
+// or without neighbours; ncu r02_seq_v3 .. v5.)
 constexpr int kWarps = 16;
-constexpr int kProducers = 12;
+constexpr int kProducers = kWarps - 1;
 constexpr int kSeqThreads = kWarps * 32;
 constexpr int kMaxTableEntries = 1 << 16;              // per CTA: 128 KiB of 16-bit entries
 constexpr int kTargetChunks = 148;                     // one chunk per SM when there is enough work
 constexpr uint32_t kMinChunkBatches = 128;             // 32 Ki positions: below this a chunk's fixed costs dominate
-static_assert(kRing >= kProducers, "every producer must be able to hold one batch in the ring");
+static_assert(kRing >= kProducers && (kRing & (kRing - 1)) == 0, "every producer holds one batch in the ring");
 
 // Number of positions the reference loop visits: groups starting at i = 0, G, 2G, .. while i < len - 7.
 inline size_t ltu_positions(size_t len, int group) {
@@ -100,10 +100,10 @@ struct SeqResolve {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Ring hand-over by sequence numbers in shared memory.  ready[slot] = t + 1 once batch t sits in its slot (a release
-// store by lane 0 after __syncwarp: MEMBAR.CTA + STS); consumed = t + 1 once the table warp has READ batch t (a plain
-// store: it is issued after instructions that used the loaded registers, so the loads have been performed).  Readers
-// poll with acquire loads, which are plain LDS on sm_100: ~30 cycles instead of the 90-150 of an mbarrier wait —
-// the table warp is a single warp and every cycle of its loop is on the critical path.
+// store by lane 0 after __syncwarp: MEMBAR.CTA + STS); consumed = t + 1 once the table warp has answered batch t (a plain
+// store after the stores of the answers: a warp's shared-memory instructions are performed in order).  Readers poll with
+// acquire loads, which are plain LDS on sm_100: ~30 cycles instead of the 90-150 of an mbarrier wait — the table warp is a
+// single warp and every cycle of its loop is on the critical path.
 __device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
@@ -116,118 +116,146 @@ __device__ __forceinline__ void st_volatile_shared(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 // Blocking wait with a guard: a protocol bug must end in a CUDA error, never in a hung GPU.
-// SLEEP: back off between polls (the producers run ahead of the table warp; their polls go through the same LSU as
-// the table warp's loads and stores).
+// SLEEP: back off between polls, longer the further away the awaited value is (the producers run ahead of the table warp;
+// their polls go through the same LSU as the table warp's loads and stores: v3 issued ~200 polls per batch).
 template <bool SLEEP>
 __device__ __forceinline__ void wait_at_least(const uint32_t* p, uint32_t want) {
     uint32_t spins = 0;
-    while ((int32_t)(ld_acquire_shared(p) - want) < 0) {
-        if (SLEEP) __nanosleep(128);
+    for (;;) {
+        const int32_t behind = (int32_t)(want - ld_acquire_shared(p));
+        if (behind <= 0) break;
+        if (SLEEP) __nanosleep(64u * (uint32_t)behind);
         if (++spins > (1u << 24)) __trap();
     }
 }
 
-template <bool TOP>
-__device__ __forceinline__ uint32_t make_packet(uint32_t key, const SeqParams& prm) {
+// packet = bucket << sb | tag.  key -> key * GOLDEN is a bijection, so equal packets <=> equal keys.
+template <bool FAST16, bool TOP>
+__device__ __forceinline__ uint32_t packet_of(uint32_t key, const SeqParams& prm) {
     const uint32_t p = key * kLtuGoldenRatio;
-    uint32_t bucket, tag;
-    if (TOP) {
-        bucket = p >> (32 - prm.hash_bits);
-        tag = p & prm.tag_mask;
-    } else {
-        bucket = p & ((1u << prm.hash_bits) - 1u);
-        tag = (p >> prm.hash_bits) & prm.tag_mask;
+    uint32_t pkt = p;   // FAST16 (H = 16, index from the top bits): the packet is the product itself
+    if (!FAST16) {
+        uint32_t bucket, tag;
+        if (TOP) {
+            bucket = p >> (32 - prm.hash_bits);
+            tag = p & prm.tag_mask;
+        } else {
+            bucket = p & ((1u << prm.hash_bits) - 1u);
+            tag = (p >> prm.hash_bits) & prm.tag_mask;
+        }
+        pkt = (bucket << prm.sb) | tag;
     }
-    uint32_t pkt = (bucket << prm.sb) | tag;
-    if ((pkt & 0xFFFFu) == kUntouched) pkt ^= (kUntouched ^ kAlias);   // low 16 bits 0xFFFF -> 0xFFFE
+    if ((~pkt & 0xFFFFu) == 0u) pkt ^= 1u;   // low 16 bits 0xFFFF ("untouched") -> 0xFFFE (kAlias)
     return pkt;
 }
 
 // ---- producers --------------------------------------------------------------------------------------------------
 // A batch = 8 rows of 32 consecutive positions, lane = position inside the row.  A ROW is a window: everything that can be
 // decided inside it is decided here.  With grp(i) = i / G:
-//   pred(i)  = the highest lane j with grp(j) < grp(i) and the bucket of i -> i does not read the table: it is a match iff the
-//              packets are equal (same packet <=> same key); no such j -> i is a HEAD and reads the table
-//   later(i) = some lane j > i has the bucket of i                        -> i never writes; otherwise it is a TAIL
-// Two heads of one bucket lie in the same group (else the later one has a pred), a tail is the last position of its bucket:
-// the table warp may perform all loads of a row, then all stores of the row.  The lane writes one 16-byte command:
-// {address to load, address to store, tag, is head}.  A position that is not a head loads the "always untouched" dummy (it
-// matches nothing), one that is not a tail stores into a sink: the table warp needs no data-dependent predicate.
+//   pred(i) = the highest lane j with grp(j) < grp(i) and the bucket of i -> i is a match iff the packets are equal (same packet
+//             <=> same key) and what the table holds is irrelevant; no such j -> i is a HEAD: it is a match iff the table holds its tag
+//   tail    = the highest lane of a bucket: the bucket's entry holds its tag after the row
+// Two heads of one bucket lie in the same group (else the later one has a pred): the table warp may perform all loads of a
+// row, then all stores of the row.  The lane writes one 8-byte command {entry address, tag to store}: EVERY lane loads its
+// entry (the answer of a lane that is not a head is ignored) and every lane stores the tag of its bucket's tail (the lanes
+// of one bucket store the same value to the same address): the table warp needs no predicate and no second address.
 //
 // Finding the lanes of one bucket is a MATCH.ANY, and MATCH.ANY is one unit per SM that spends 2 cycles per DISTINCT value:
 // 64 cycles for a row of 32 different buckets (tools/microbench/match_bench.cu), which made the whole kernel run at exactly
-// 8 x 64 cycles per batch.  But a row of 32 different buckets needs no resolution at all — every lane is head and tail — and
-// that is the common case wherever MATCH.ANY is slow.  So each row is first screened through a per-warp scratch of 4096 byte
-// slots: every lane stores its lane id at slot (bucket mod 4096) and loads it back; two lanes of one bucket share a slot, so at
-// least one of them reads a foreign id (no false negatives, whatever else hits the slot).  Only rows with such a lane take
-// the MATCH.ANY path (random buckets: 11 % of the rows, through slot collisions of different buckets), and there the lanes that are alone in
-// their slot enter with one common value: MATCH.ANY only pays for the contested buckets.
-constexpr int kScratchSlots = 4096;
+// 8 x 64 cycles per batch.  But a lane whose bucket no other lane of the row has needs no resolution — it is head and tail —
+// and that is the common case wherever MATCH.ANY is slow.  So each row is first screened through a per-warp scratch of 2048
+// byte slots: every lane stores its lane id at slot (bucket mod 2048) and loads it back.  Two lanes of one bucket share a
+// slot, so at least one of them reads a foreign id (a "loser"; no false negatives, whatever else hits the slot); every loser
+// names the lane it read (one REDUX.OR), which tells the winners of contested slots.  The lanes of uncontested slots enter
+// MATCH.ANY with one common value: it only pays for the contested buckets, and rows without a loser skip it.
 
-template <bool FAST16, bool TOP>
-__device__ __forceinline__ uint32_t packet_of(uint32_t key, const SeqParams& prm) {
-    if (FAST16) {   // H = 16, index from the top bits: the packet is the product itself
-        uint32_t pkt = key * kLtuGoldenRatio;
-        if ((pkt & 0xFFFFu) == kUntouched) pkt ^= (kUntouched ^ kAlias);
-        return pkt;
-    }
-    return make_packet<TOP>(key, prm);
-}
+// What a producer remembers of a batch until the table warp has answered it.
+struct Pending {
+    uint32_t pkt[kRows];   // packet of this lane's position in every row
+    uint32_t heads;        // bit r: the position of row r is a head (its answer counts)
+};
 
 // FULL: every position of the batch is valid and the table is not split (all batches but the last one of a segment).
+// Returns the number of matches decided inside the rows; cmd_a / cmd_b = the commands.
 template <int G, bool TOP, bool FAST16, bool FULL>
 __device__ __forceinline__ uint32_t produce_batch(const uint32_t (&wa)[kRows], const uint32_t (&wb)[kRows], const uint32_t fsh,
                                                   const uint32_t pos0, const uint32_t chunk_valid, const SeqParams& prm,
-                                                  const uint32_t part, const uint32_t table_addr, const uint32_t dummy_addr,
-                                                  const uint32_t sink_addr, const uint32_t scratch_addr, uint4* sw) {
+                                                  const uint32_t part, const uint32_t table_addr, const uint32_t sink_addr,
+                                                  const uint32_t scratch_addr, uint32_t (&cmd_a)[kRows], uint32_t (&cmd_b)[kRows],
+                                                  Pending& pend) {
     const unsigned lane = threadIdx.x & 31;
     const uint32_t below = (1u << (lane & ~(unsigned)(G - 1))) - 1u;   // the lanes of earlier groups
     uint32_t count = 0;
+    pend.heads = 0;
 #pragma unroll
     for (int r = 0; r < kRows; r++) {
         const uint32_t pkt = packet_of<FAST16, TOP>(__funnelshift_r(wa[r], wb[r], fsh) & kLtuKeyMask, prm);
+        pend.pkt[r] = pkt;
         bool act = true;
         if (!FULL) {
             act = pos0 + 32u * r < chunk_valid;
             if (prm.part_mask) act = act && ((pkt >> prm.part_shift) & prm.part_mask) == part;
         }
         const uint32_t bucket = FAST16 ? pkt >> 16 : pkt >> prm.sb;
-        const uint32_t entry = FAST16 ? table_addr + ((pkt >> 15) & 0x1FFFEu) : table_addr + (((pkt & prm.keep_mask) >> prm.sb) << 1);
-        // screen: does any lane share its scratch slot with another lane of this row?
-        const uint32_t slot = scratch_addr + (bucket & (kScratchSlots - 1));
+        const uint32_t entry = FAST16 ? table_addr + 2u * bucket : table_addr + (((pkt & prm.keep_mask) >> prm.sb) << 1);
+        // screen: which lanes share their scratch slot with another lane of this row?  (scratch_addr is 2 KiB aligned;
+        // store then load of one warp: performed in order)
+        const uint32_t slot = scratch_addr | (bucket & (kScratchSlots - 1));
         uint32_t winner = lane;
-        if (act) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(slot), "r"(lane) : "memory");
-        __syncwarp();
-        if (act) asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(winner) : "r"(slot) : "memory");
-        const bool loser = winner != lane;
-        bool head = act, tail = act;
-        if (__any_sync(kFull, loser)) {
-            // second pass: the losers mark their slot, so that the lane that won it learns that it is contested too
-            if (loser) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(slot), "r"(0xFFu) : "memory");
+        if (FULL) {
+            asm volatile("st.volatile.shared.u8 [%1], %2;\n ld.volatile.shared.u8 %0, [%1];" : "=r"(winner) : "r"(slot), "r"(lane) : "memory");
+        } else {
+            if (act) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(slot), "r"(lane) : "memory");
             __syncwarp();
-            if (act && !loser) asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(winner) : "r"(slot) : "memory");
-            const bool contested = winner != lane;   // the lanes that may share their bucket with another lane of the row
-            // every other lane is alone in its slot, hence in its bucket: head and tail.  They all enter MATCH.ANY with one common
-            // value (a real bucket has at most 17 bits), so that it sees few distinct values.
-            const uint32_t same = __match_any_sync(kFull, contested ? bucket : 0xFFFFFFFFu);
-            if (contested) {
-                const uint32_t lower = same & below;
-                head = lower == 0u;
-                tail = (same >> lane) == 1u;
-            }
-            const uint32_t lower = contested ? same & below : 0u;
-            const uint32_t ppkt = __shfl_sync(kFull, pkt, lower ? 31u - (uint32_t)__clz(lower) : lane);
-            count += lower != 0u && ppkt == pkt;
+            if (act) asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(winner) : "r"(slot) : "memory");
         }
-        sw[r * 32] = make_uint4(head ? entry : dummy_addr, tail ? entry : sink_addr, pkt & 0xFFFFu, head);
+        const bool loser = winner != lane;
+        bool head = act;
+        uint32_t store_tag = pkt;
+        if (__any_sync(kFull, loser)) {
+            // the lane that won a contested slot must learn it too: every loser names its winner
+            const uint32_t named = __reduce_or_sync(kFull, loser ? 1u << winner : 0u);
+            const bool contested = loser || ((named >> lane) & 1u);   // may share its bucket with another lane of the row
+            // (a real bucket has at most 17 bits)
+            const uint32_t same = __match_any_sync(kFull, contested ? bucket : 0xFFFFFFFFu);
+            const uint32_t lower = contested ? same & below : 0u;
+            const uint32_t tail_lane = contested ? 31u - (uint32_t)__clz(same) : lane;
+            const uint32_t pred_pkt = __shfl_sync(kFull, pkt, lower ? 31u - (uint32_t)__clz(lower) : lane);
+            store_tag = __shfl_sync(kFull, pkt, tail_lane);
+            head = act && lower == 0u;
+            count += lower != 0u && pred_pkt == pkt;
+        }
+        cmd_a[r] = act ? entry : sink_addr;
+        cmd_b[r] = store_tag;   // the table warp stores the low 16 bits
+        pend.heads |= (uint32_t)head << r;
+    }
+    return count;
+}
+
+// The table warp has answered a batch: count the heads that found their own tag; UNKNOWN (the chunk does not start its
+// segment): a head that found its entry untouched records its tag for the resolve kernel.
+template <bool FAST16>
+__device__ __forceinline__ uint32_t collect_batch(const Pending& pend, const uint4 seen4, const SeqParams& prm, uint16_t* first_seen) {
+    const uint32_t packed[4] = {seen4.x, seen4.y, seen4.z, seen4.w};
+    uint32_t count = 0;
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        const uint32_t seen = (r & 1) ? packed[r >> 1] >> 16 : packed[r >> 1] & 0xFFFFu;
+        const uint32_t tag = pend.pkt[r] & 0xFFFFu;
+        const bool head = (pend.heads >> r) & 1u;
+        count += head && seen == tag;
+        if (first_seen && head && seen == kUntouched) {
+            const uint32_t idx = FAST16 ? pend.pkt[r] >> 16 : (pend.pkt[r] & prm.keep_mask) >> prm.sb;
+            first_seen[(size_t)idx * 4] = (uint16_t)tag;   // first_seen is already advanced by position & 3
+        }
     }
     return count;
 }
 
 template <int G, bool TOP, bool FAST16>
 __device__ __forceinline__ uint32_t producer_warp(const SeqChunk& ck, const uint32_t nb, const uint32_t pi, const SeqParams& prm,
-                                                  const uint32_t table_addr, const uint32_t dummy_addr, const uint32_t scratch_addr,
-                                                  uint8_t* ring, uint32_t* ready, const uint32_t* consumed) {
+                                                  const uint32_t table_addr, const uint32_t sink_base, const uint32_t scratch_addr,
+                                                  uint8_t* ring, const uint8_t* seen_base, uint32_t* ready, const uint32_t* consumed) {
     const unsigned lane = threadIdx.x & 31;
     const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(ck.data) & 3u);
     const uint32_t* base = reinterpret_cast<const uint32_t*>(ck.data - sh) + (ck.first_pos >> 2);   // chunk-relative words
@@ -235,7 +263,8 @@ __device__ __forceinline__ uint32_t producer_warp(const SeqChunk& ck, const uint
     const unsigned long long ahead = ck.npos - ck.first_pos;
     const uint32_t chunk_valid = ahead > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)ahead;
     const uint32_t maxw = (sh + chunk_valid + 1) >> 2;   // chunk-relative word of the last byte any valid position reads
-    const uint32_t sink_addr = dummy_addr + 64u + 2u * lane;
+    const uint32_t sink_addr = sink_base + 2u * lane;
+    uint16_t* first_seen = ck.first_seen ? ck.first_seen + (lane & 3) : nullptr;   // position & 3 == lane & 3
     // the key of position (row base + lane) starts at byte lane + sh of the row's first word
     const uint32_t wofs = (lane + sh) >> 2, fsh = ((lane + sh) & 3u) * 8u;
     auto load = [&](uint32_t t, uint32_t (&a)[kRows], uint32_t (&b)[kRows]) {
@@ -255,77 +284,96 @@ __device__ __forceinline__ uint32_t producer_warp(const SeqChunk& ck, const uint
             }
         }
     };
+    auto answers = [&](uint32_t t) { return reinterpret_cast<const uint4*>(seen_base + (size_t)(t % kRing) * kSeenBytes)[lane]; };
     uint32_t count = 0;
     uint32_t na[kRows], nbw[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; r++) na[r] = nbw[r] = 0u;
     if (pi < nb) load(pi, na, nbw);
-    for (uint32_t t = pi; t < nb; t += kProducers) {
+    Pending pend;        // the batch this warp produced last (t - kProducers), not yet collected
+    bool have_pending = false;
+    uint32_t t = pi;
+    for (; t < nb; t += kProducers) {
         uint32_t ca[kRows], cb[kRows];
 #pragma unroll
         for (int r = 0; r < kRows; r++) ca[r] = na[r], cb[r] = nbw[r];
         if (t + kProducers < nb) load(t + kProducers, na, nbw);
-        // wait for the slot: the table warp has read batch t - kRing
-        if (t >= (uint32_t)kRing) wait_at_least<true>(consumed, t - kRing + 1);
-        uint4* sw = reinterpret_cast<uint4*>(ring + (size_t)(t % kRing) * kSlotBytes) + lane;
+        // the table warp's answers to this warp's previous batch (this also frees the slot: t - kProducers >= t - kRing)
+        if (have_pending) {
+            wait_at_least<true>(consumed, t - kProducers + 1);
+            count += collect_batch<FAST16>(pend, answers(t - kProducers), prm, first_seen);
+        }
         const uint32_t pos0 = t * kBatchPos + lane;   // chunk-relative
+        uint32_t cmd_a[kRows], cmd_b[kRows];
         if (prm.part_mask == 0u && (t + 1) * (uint32_t)kBatchPos <= chunk_valid)
-            count += produce_batch<G, TOP, FAST16, true>(ca, cb, fsh, pos0, chunk_valid, prm, ck.part, table_addr, dummy_addr, sink_addr, scratch_addr, sw);
+            count += produce_batch<G, TOP, FAST16, true>(ca, cb, fsh, pos0, chunk_valid, prm, ck.part, table_addr, sink_addr, scratch_addr, cmd_a, cmd_b, pend);
         else
-            count += produce_batch<G, TOP, FAST16, false>(ca, cb, fsh, pos0, chunk_valid, prm, ck.part, table_addr, dummy_addr, sink_addr, scratch_addr, sw);
+            count += produce_batch<G, TOP, FAST16, false>(ca, cb, fsh, pos0, chunk_valid, prm, ck.part, table_addr, sink_addr, scratch_addr, cmd_a, cmd_b, pend);
+        have_pending = true;
+        // the commands of rows 2k and 2k + 1 of a lane travel together (one 128-bit load of the table warp)
+        uint4* sw = reinterpret_cast<uint4*>(ring + (size_t)(t % kRing) * kSlotBytes) + lane;
+#pragma unroll
+        for (int k = 0; k < kRows / 2; k++) sw[k * 32] = make_uint4(cmd_a[2 * k], cmd_b[2 * k], cmd_a[2 * k + 1], cmd_b[2 * k + 1]);
         __syncwarp();
         if (lane == 0) st_release_shared(ready + t % kRing, t + 1);
+    }
+    if (have_pending) {
+        wait_at_least<true>(consumed, t - kProducers + 1);
+        count += collect_batch<FAST16>(pend, answers(t - kProducers), prm, first_seen);
     }
     return count;
 }
 
 // ---- the table warp ---------------------------------------------------------------------------------------------
-// Lane c handles position c of every row; per row ONE load and ONE store of all 32 lanes, in program order (a warp's
-// shared-memory instructions are performed in order: this IS the reference's sequential loop).  Nothing waits for the
-// loaded values before the next rows' instructions have been issued: the commands of a whole batch are fetched first, the
-// compares come after the eight rows.
-// UNKNOWN: the chunk does not start its segment; a head that finds its entry untouched records its tag for the resolve.
-template <bool UNKNOWN>
-__device__ __forceinline__ uint32_t table_warp(const SeqChunk& ck, const uint32_t nb, uint16_t* table, const uint8_t* ring,
-                                               const uint32_t* ready, uint32_t* consumed) {
+// Lane c handles position c of every row; per row ONE load and ONE store of all 32 lanes at the same addresses, in program
+// order (a warp's shared-memory instructions are performed in order: this IS the reference's sequential loop).  The warp
+// does nothing else: what the loads found goes back to the producer of the batch (16 bits per position), which counts the
+// matches and keeps the books of the hand-over between chunks.  Every instruction of this loop is on the critical path of
+// the kernel, and the LSU takes one instruction per 4 cycles from a warp: 4 command loads + 16 + 1 answer store per batch.
+__device__ __forceinline__ void table_warp(const uint32_t nb, const uint8_t* ring, uint8_t* seen_base, const uint32_t* ready, uint32_t* consumed) {
     const unsigned lane = threadIdx.x & 31;
-    const uint32_t table_addr = smem_u32(table);
-    uint16_t* fs = ck.first_seen + (lane & 3);   // position & 3
-    uint32_t count = 0;
     uint32_t flag = nb ? ld_acquire_shared(ready) : 0u;   // ready[slot of batch t], fetched one batch ahead
     for (uint32_t t = 0; t < nb; t++) {
         if ((int32_t)(flag - (t + 1)) < 0) wait_at_least<false>(ready + t % kRing, t + 1);
         if (t + 1 < nb) flag = ld_acquire_shared(ready + (t + 1) % kRing);
         const uint4* sw = reinterpret_cast<const uint4*>(ring + (size_t)(t % kRing) * kSlotBytes) + lane;
-        uint4 c[kRows];
+        uint4 c[kRows / 2];
 #pragma unroll
-        for (int r = 0; r < kRows; r++) c[r] = sw[r * 32];
+        for (int k = 0; k < kRows / 2; k++) c[k] = sw[k * 32];
         uint32_t seen[kRows];
 #pragma unroll
-        for (int r = 0; r < kRows; r++)
-            asm volatile("ld.volatile.shared.u16 %0, [%1];\n st.volatile.shared.u16 [%2], %3;"
-                         : "=r"(seen[r]) : "r"(c[r].x), "r"(c[r].y), "r"(c[r].z) : "memory");
-        // the commands have been used as addresses: their loads are complete and the slot may be refilled
+        for (int k = 0; k < kRows / 2; k++)
+            asm volatile(
+                "ld.volatile.shared.u16 %0, [%2];\n st.volatile.shared.u16 [%2], %3;\n"
+                "ld.volatile.shared.u16 %1, [%4];\n st.volatile.shared.u16 [%4], %5;"
+                : "=&r"(seen[2 * k]), "=&r"(seen[2 * k + 1])
+                : "r"(c[k].x), "r"(c[k].y), "r"(c[k].z), "r"(c[k].w)
+                : "memory");
+        uint4 packed;
+        packed.x = seen[0] | (seen[1] << 16), packed.y = seen[2] | (seen[3] << 16);
+        packed.z = seen[4] | (seen[5] << 16), packed.w = seen[6] | (seen[7] << 16);
+        asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(seen_base + (size_t)(t % kRing) * kSeenBytes) + 16u * lane),
+                     "r"(packed.x), "r"(packed.y), "r"(packed.z), "r"(packed.w)
+                     : "memory");
+        // the answers are in place (and the commands have been read): the producer may collect them and refill the slot
+        __syncwarp();
         if (lane == 0) st_volatile_shared(consumed, t + 1);
-#pragma unroll
-        for (int r = 0; r < kRows; r++) {
-            count += seen[r] == c[r].z;
-            if (UNKNOWN && seen[r] == kUntouched && c[r].w) fs[(size_t)((c[r].x - table_addr) >> 1) * 4] = (uint16_t)c[r].z;
-        }
     }
-    return count;
 }
 
 // G: positions per group of the reference loop.  TOP: index from the top bits of the product (else: low bits).
+// FAST16: H = 16 and TOP (the restated crate's parameters): the packet is the product itself.
 template <int G, bool TOP, bool FAST16>
 __global__ void __launch_bounds__(kSeqThreads, 1)
 ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restrict__ matches, const SeqParams prm) {
     extern __shared__ __align__(16) uint8_t seq_smem[];
+    // table | pad to 2 KiB | scratch (kProducers x 2 KiB) | ring | answers | sink | ready[kRing], consumed
     uint16_t* table = reinterpret_cast<uint16_t*>(seq_smem);
-    uint8_t* dummy = seq_smem + prm.table_bytes;          // [0, 64): never written, reads 0xFFFF; [64, 128): write sink
-    uint8_t* ring = dummy + kDummyBytes;
-    uint8_t* scratch = ring + (size_t)kRing * kSlotBytes;   // kProducers x kScratchSlots bytes (contents never matter)
-    uint32_t* ready = reinterpret_cast<uint32_t*>(scratch + (size_t)kProducers * kScratchSlots);
+    const uint32_t scratch0 = (smem_u32(seq_smem) + prm.table_bytes + (kScratchSlots - 1)) & ~(uint32_t)(kScratchSlots - 1);
+    uint8_t* ring = seq_smem + (scratch0 - smem_u32(seq_smem)) + (size_t)kProducers * kScratchSlots;
+    uint8_t* seen = ring + (size_t)kRing * kSlotBytes;
+    uint8_t* sink = seen + (size_t)kRing * kSeenBytes;
+    uint32_t* ready = reinterpret_cast<uint32_t*>(sink + kSinkBytes);
     uint32_t* consumed = ready + kRing;
 
     const SeqChunk ck = chunks[blockIdx.x];
@@ -337,7 +385,7 @@ ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restri
     {
         uint4* t4 = reinterpret_cast<uint4*>(table);
         const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
-        for (uint32_t i = tid; i < (prm.table_bytes + kDummyBytes) / 16; i += kSeqThreads) t4[i] = ones;
+        for (uint32_t i = tid; i < prm.table_bytes / 16; i += kSeqThreads) t4[i] = ones;
         if (ck.first_seen) {
             uint4* f4 = reinterpret_cast<uint4*>(ck.first_seen);
             for (uint32_t i = tid; i < prm.table_bytes / 4; i += kSeqThreads) f4[i] = ones;   // entries * 8 bytes
@@ -350,11 +398,11 @@ ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restri
 
     uint32_t count = 0;
     if (warp == 0) {
-        count = ck.first_seen ? table_warp<true>(ck, nb, table, ring, ready, consumed) : table_warp<false>(ck, nb, table, ring, ready, consumed);
-    } else if (warp & 3) {
-        const uint32_t pi = warp - 1 - (warp >> 2);
-        count = producer_warp<G, TOP, FAST16>(ck, nb, pi, prm, smem_u32(table), smem_u32(dummy), smem_u32(scratch) + pi * kScratchSlots, ring,
-                                              ready, consumed);
+        table_warp(nb, ring, seen, ready, consumed);
+    } else {
+        const uint32_t pi = warp - 1;
+        count = producer_warp<G, TOP, FAST16>(ck, nb, pi, prm, smem_u32(table), smem_u32(sink), scratch0 + pi * kScratchSlots, ring, seen, ready,
+                                              consumed);
     }
     for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(kFull, count, o);
     if (lane == 0 && count) atomicAdd(&matches[ck.slot], (unsigned long long)count);
@@ -425,7 +473,8 @@ Geometry geometry(const LtuParams& p) {
     g.prm.part_mask = g.parts - 1u;
     g.prm.keep_mask = part_bits ? ((g.entries - 1u) << g.prm.sb) | g.prm.tag_mask : ~0u;
     g.prm.table_bytes = g.entries * 2u;
-    g.smem_bytes = g.prm.table_bytes + kDummyBytes + (size_t)kRing * kSlotBytes + (size_t)kProducers * kScratchSlots + (kRing + 1) * sizeof(uint32_t) + 12;
+    g.smem_bytes = g.prm.table_bytes + (size_t)kScratchSlots + (size_t)kProducers * kScratchSlots + (size_t)kRing * (kSlotBytes + kSeenBytes) + kSinkBytes +
+                   (kRing + 1) * sizeof(uint32_t) + 12;   // table, alignment pad, scratch, ring, answers, sink, flags
     return g;
 }
 
