@@ -124,7 +124,7 @@ __device__ __forceinline__ void wait_at_least(const uint32_t* p, uint32_t want) 
     for (;;) {
         const int32_t behind = (int32_t)(want - ld_acquire_shared(p));
         if (behind <= 0) break;
-        if (SLEEP) __nanosleep(64u * (uint32_t)behind);
+        if (SLEEP) __nanosleep(96u * (uint32_t)behind);
         if (++spins > (1u << 24)) __trap();
     }
 }
@@ -298,17 +298,19 @@ __device__ __forceinline__ uint32_t producer_warp(const SeqChunk& ck, const uint
 #pragma unroll
         for (int r = 0; r < kRows; r++) ca[r] = na[r], cb[r] = nbw[r];
         if (t + kProducers < nb) load(t + kProducers, na, nbw);
+        const uint32_t pos0 = t * kBatchPos + lane;   // chunk-relative
+        uint32_t cmd_a[kRows], cmd_b[kRows];
+        Pending fresh;
+        if (prm.part_mask == 0u && (t + 1) * (uint32_t)kBatchPos <= chunk_valid)
+            count += produce_batch<G, TOP, FAST16, true>(ca, cb, fsh, pos0, chunk_valid, prm, ck.part, table_addr, sink_addr, scratch_addr, cmd_a, cmd_b, fresh);
+        else
+            count += produce_batch<G, TOP, FAST16, false>(ca, cb, fsh, pos0, chunk_valid, prm, ck.part, table_addr, sink_addr, scratch_addr, cmd_a, cmd_b, fresh);
         // the table warp's answers to this warp's previous batch (this also frees the slot: t - kProducers >= t - kRing)
         if (have_pending) {
             wait_at_least<true>(consumed, t - kProducers + 1);
             count += collect_batch<FAST16>(pend, answers(t - kProducers), prm, first_seen);
         }
-        const uint32_t pos0 = t * kBatchPos + lane;   // chunk-relative
-        uint32_t cmd_a[kRows], cmd_b[kRows];
-        if (prm.part_mask == 0u && (t + 1) * (uint32_t)kBatchPos <= chunk_valid)
-            count += produce_batch<G, TOP, FAST16, true>(ca, cb, fsh, pos0, chunk_valid, prm, ck.part, table_addr, sink_addr, scratch_addr, cmd_a, cmd_b, pend);
-        else
-            count += produce_batch<G, TOP, FAST16, false>(ca, cb, fsh, pos0, chunk_valid, prm, ck.part, table_addr, sink_addr, scratch_addr, cmd_a, cmd_b, pend);
+        pend = fresh;
         have_pending = true;
         // the commands of rows 2k and 2k + 1 of a lane travel together (one 128-bit load of the table warp)
         uint4* sw = reinterpret_cast<uint4*>(ring + (size_t)(t % kRing) * kSlotBytes) + lane;
@@ -330,35 +332,62 @@ __device__ __forceinline__ uint32_t producer_warp(const SeqChunk& ck, const uint
 // does nothing else: what the loads found goes back to the producer of the batch (16 bits per position), which counts the
 // matches and keeps the books of the hand-over between chunks.  Every instruction of this loop is on the critical path of
 // the kernel, and the LSU takes one instruction per 4 cycles from a warp: 4 command loads + 16 + 1 answer store per batch.
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void table_load_commands(const uint8_t* ring, uint32_t t, unsigned lane, uint4 (&c)[kRows / 2]) {
+    const uint32_t a = smem_u32(ring + (size_t)(t % kRing) * kSlotBytes) + 16u * lane;
+#pragma unroll
+    for (int k = 0; k < kRows / 2; k++)   // volatile: after the flag has been seen, never hoisted above it
+        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c[k].x), "=r"(c[k].y), "=r"(c[k].z), "=r"(c[k].w) : "r"(a + 512u * k) : "memory");
+}
+__device__ __forceinline__ void table_store_answers(uint8_t* seen_base, uint32_t t, unsigned lane, const uint32_t (&seen)[kRows], uint32_t* consumed) {
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(seen_base + (size_t)(t % kRing) * kSeenBytes) + 16u * lane),
+                 "r"(seen[0] | (seen[1] << 16)), "r"(seen[2] | (seen[3] << 16)), "r"(seen[4] | (seen[5] << 16)), "r"(seen[6] | (seen[7] << 16))
+                 : "memory");
+    // the answers of batch t are in place (and its commands have been read long ago): the producer may collect them and
+    // refill the slot
+    __syncwarp();
+    if (lane == 0) st_volatile_shared(consumed, t + 1);
+}
+// Software pipeline: while batch t goes through the table, the commands of batch t + 1 are already on their way from the
+// ring and the answers of batch t - 1 (whose loads have long completed) are packed and stored: no instruction of the loop
+// waits for a load it has just issued.
 __device__ __forceinline__ void table_warp(const uint32_t nb, const uint8_t* ring, uint8_t* seen_base, const uint32_t* ready, uint32_t* consumed) {
     const unsigned lane = threadIdx.x & 31;
-    uint32_t flag = nb ? ld_acquire_shared(ready) : 0u;   // ready[slot of batch t], fetched one batch ahead
+    if (nb == 0) return;
+    uint4 cur[kRows / 2], nxt[kRows / 2];
+    uint32_t seen[kRows], prev[kRows];
+    wait_at_least<false>(ready, 1);
+    table_load_commands(ring, 0, lane, cur);
+    uint32_t flag = nb > 1 ? ld_volatile_shared(ready + 1) : 0u;   // ready[slot of batch t + 1]
+#pragma unroll 2
     for (uint32_t t = 0; t < nb; t++) {
-        if ((int32_t)(flag - (t + 1)) < 0) wait_at_least<false>(ready + t % kRing, t + 1);
-        if (t + 1 < nb) flag = ld_acquire_shared(ready + (t + 1) % kRing);
-        const uint4* sw = reinterpret_cast<const uint4*>(ring + (size_t)(t % kRing) * kSlotBytes) + lane;
-        uint4 c[kRows / 2];
-#pragma unroll
-        for (int k = 0; k < kRows / 2; k++) c[k] = sw[k * 32];
-        uint32_t seen[kRows];
+        const bool more = t + 1 < nb;
+        const bool early = more && (int32_t)(flag - (t + 2)) >= 0;   // batch t + 1 is in the ring already (the usual case)
+        if (early) table_load_commands(ring, t + 1, lane, nxt);
+        if (t + 2 < nb) flag = ld_volatile_shared(ready + (t + 2) % kRing);
 #pragma unroll
         for (int k = 0; k < kRows / 2; k++)
             asm volatile(
                 "ld.volatile.shared.u16 %0, [%2];\n st.volatile.shared.u16 [%2], %3;\n"
                 "ld.volatile.shared.u16 %1, [%4];\n st.volatile.shared.u16 [%4], %5;"
                 : "=&r"(seen[2 * k]), "=&r"(seen[2 * k + 1])
-                : "r"(c[k].x), "r"(c[k].y), "r"(c[k].z), "r"(c[k].w)
+                : "r"(cur[k].x), "r"(cur[k].y), "r"(cur[k].z), "r"(cur[k].w)
                 : "memory");
-        uint4 packed;
-        packed.x = seen[0] | (seen[1] << 16), packed.y = seen[2] | (seen[3] << 16);
-        packed.z = seen[4] | (seen[5] << 16), packed.w = seen[6] | (seen[7] << 16);
-        asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(seen_base + (size_t)(t % kRing) * kSeenBytes) + 16u * lane),
-                     "r"(packed.x), "r"(packed.y), "r"(packed.z), "r"(packed.w)
-                     : "memory");
-        // the answers are in place (and the commands have been read): the producer may collect them and refill the slot
-        __syncwarp();
-        if (lane == 0) st_volatile_shared(consumed, t + 1);
+        if (t > 0) table_store_answers(seen_base, t - 1, lane, prev, consumed);
+        if (more && !early) {
+            wait_at_least<false>(ready + (t + 1) % kRing, t + 2);
+            table_load_commands(ring, t + 1, lane, nxt);
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; r++) prev[r] = seen[r];
+#pragma unroll
+        for (int k = 0; k < kRows / 2; k++) cur[k] = nxt[k];
     }
+    table_store_answers(seen_base, nb - 1, lane, prev, consumed);
 }
 
 // G: positions per group of the reference loop.  TOP: index from the top bits of the product (else: low bits).
