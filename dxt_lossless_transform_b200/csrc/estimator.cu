@@ -124,7 +124,7 @@ __device__ __forceinline__ void wait_at_least(const uint32_t* p, uint32_t want) 
     for (;;) {
         const int32_t behind = (int32_t)(want - ld_acquire_shared(p));
         if (behind <= 0) break;
-        if (SLEEP) __nanosleep(96u * (uint32_t)behind);
+        if (SLEEP) __nanosleep(32u * (uint32_t)behind);
         if (++spins > (1u << 24)) __trap();
     }
 }
@@ -317,7 +317,7 @@ __device__ __forceinline__ uint32_t producer_warp(const SeqChunk& ck, const uint
 #pragma unroll
         for (int k = 0; k < kRows / 2; k++) sw[k * 32] = make_uint4(cmd_a[2 * k], cmd_b[2 * k], cmd_a[2 * k + 1], cmd_b[2 * k + 1]);
         __syncwarp();
-        if (lane == 0) st_release_shared(ready + t % kRing, t + 1);
+        if (lane == 0) st_volatile_shared(ready + t % kRing, t + 1);   // (a release store is a MEMBAR: it would wait for the prefetch loads)
     }
     if (have_pending) {
         wait_at_least<true>(consumed, t - kProducers + 1);
@@ -337,38 +337,60 @@ __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) {
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
     return v;
 }
-__device__ __forceinline__ void table_load_commands(const uint8_t* ring, uint32_t t, unsigned lane, uint4 (&c)[kRows / 2]) {
-    const uint32_t a = smem_u32(ring + (size_t)(t % kRing) * kSlotBytes) + 16u * lane;
-#pragma unroll
-    for (int k = 0; k < kRows / 2; k++)   // volatile: after the flag has been seen, never hoisted above it
-        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c[k].x), "=r"(c[k].y), "=r"(c[k].z), "=r"(c[k].w) : "r"(a + 512u * k) : "memory");
-}
-__device__ __forceinline__ void table_store_answers(uint8_t* seen_base, uint32_t t, unsigned lane, const uint32_t (&seen)[kRows], uint32_t* consumed) {
-    asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(seen_base + (size_t)(t % kRing) * kSeenBytes) + 16u * lane),
-                 "r"(seen[0] | (seen[1] << 16)), "r"(seen[2] | (seen[3] << 16)), "r"(seen[4] | (seen[5] << 16)), "r"(seen[6] | (seen[7] << 16))
-                 : "memory");
-    // the answers of batch t are in place (and its commands have been read long ago): the producer may collect them and
-    // refill the slot
-    __syncwarp();
-    if (lane == 0) st_volatile_shared(consumed, t + 1);
-}
 // Software pipeline: while batch t goes through the table, the commands of batch t + 1 are already on their way from the
 // ring and the answers of batch t - 1 (whose loads have long completed) are packed and stored: no instruction of the loop
-// waits for a load it has just issued.
-__device__ __forceinline__ void table_warp(const uint32_t nb, const uint8_t* ring, uint8_t* seen_base, const uint32_t* ready, uint32_t* consumed) {
-    const unsigned lane = threadIdx.x & 31;
-    if (nb == 0) return;
-    uint4 cur[kRows / 2], nxt[kRows / 2];
-    uint32_t seen[kRows], prev[kRows];
-    wait_at_least<false>(ready, 1);
-    table_load_commands(ring, 0, lane, cur);
-    uint32_t flag = nb > 1 ? ld_volatile_shared(ready + 1) : 0u;   // ready[slot of batch t + 1]
-#pragma unroll 2
-    for (uint32_t t = 0; t < nb; t++) {
-        const bool more = t + 1 < nb;
-        const bool early = more && (int32_t)(flag - (t + 2)) >= 0;   // batch t + 1 is in the ring already (the usual case)
-        if (early) table_load_commands(ring, t + 1, lane, nxt);
-        if (t + 2 < nb) flag = ld_volatile_shared(ready + (t + 2) % kRing);
+// waits for a load it has just issued.  The loop is unrolled over the 16 ring slots, so every ring address is an immediate:
+// a single warp issues a dependent instruction every ~4.5 cycles, so the pace of the table warp — of the whole kernel — is
+// its instruction count (ncu r02_seq_exp5: with the table accesses themselves removed the loop still took 260 cycles per
+// batch, for ~55 instructions of slot arithmetic, flag handling and packing).
+struct TableWarp {
+    uint32_t ring_lane, seen_lane, ready_addr, consumed_addr;   // shared-memory addresses (this lane's 16 bytes of slot 0)
+    uint32_t nb;
+    unsigned lane;
+
+    template <int SLOT>
+    __device__ __forceinline__ void load_commands(uint4 (&c)[kRows / 2]) const {
+#pragma unroll
+        for (int k = 0; k < kRows / 2; k++)   // volatile: after the flag has been seen, never hoisted above it
+            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(c[k].x), "=r"(c[k].y), "=r"(c[k].z), "=r"(c[k].w)
+                         : "r"(ring_lane + (uint32_t)(SLOT * kSlotBytes + 512 * k))
+                         : "memory");
+    }
+    template <int SLOT>
+    __device__ __forceinline__ uint32_t load_flag() const {
+        uint32_t v;
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(ready_addr + (uint32_t)(SLOT * 4)) : "memory");
+        return v;
+    }
+    template <int SLOT>
+    __device__ __forceinline__ void wait_flag(uint32_t flag, uint32_t want) const {
+        uint32_t spins = 0;
+        while (flag < want) {   // (sequence numbers start at 1 and a chunk has far fewer than 2^32 batches)
+            flag = load_flag<SLOT>();
+            if (++spins > (1u << 26)) __trap();
+        }
+    }
+    // answers of batch t (slot SLOT) and the signal that they are there: the producer may collect them and refill the slot
+    template <int SLOT>
+    __device__ __forceinline__ void store_answers(const uint32_t (&seen)[kRows], uint32_t t) const {
+        asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(seen_lane + (uint32_t)(SLOT * kSeenBytes)), "r"(__byte_perm(seen[0], seen[1], 0x5410)),
+                     "r"(__byte_perm(seen[2], seen[3], 0x5410)), "r"(__byte_perm(seen[4], seen[5], 0x5410)), "r"(__byte_perm(seen[6], seen[7], 0x5410))
+                     : "memory");
+        if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(consumed_addr), "r"(t + 1) : "memory");
+    }
+    // batch t = base + SLOT: `cur` holds its commands, `flag` = ready[slot of t + 1] as loaded one step ago.
+    // INNER: 0 < t and t + 1 < nb are known (all steps of a ring round that is neither the first nor the last).
+    template <int SLOT, bool INNER>
+    __device__ __forceinline__ void step(uint32_t base, uint4 (&cur)[kRows / 2], uint4 (&nxt)[kRows / 2], uint32_t (&seen)[kRows],
+                                         const uint32_t (&prev)[kRows], uint32_t& flag) const {
+        constexpr int S1 = (SLOT + 1) % kRing, S2 = (SLOT + 2) % kRing, SP = (SLOT + kRing - 1) % kRing;
+        const uint32_t t = base + SLOT;
+        if (INNER || t + 1 < nb) {
+            wait_flag<S1>(flag, t + 2);
+            load_commands<S1>(nxt);
+        }
+        flag = load_flag<S2>();   // (a stale value of a slot that is never filled is never looked at)
 #pragma unroll
         for (int k = 0; k < kRows / 2; k++)
             asm volatile(
@@ -377,18 +399,46 @@ __device__ __forceinline__ void table_warp(const uint32_t nb, const uint8_t* rin
                 : "=&r"(seen[2 * k]), "=&r"(seen[2 * k + 1])
                 : "r"(cur[k].x), "r"(cur[k].y), "r"(cur[k].z), "r"(cur[k].w)
                 : "memory");
-        if (t > 0) table_store_answers(seen_base, t - 1, lane, prev, consumed);
-        if (more && !early) {
-            wait_at_least<false>(ready + (t + 1) % kRing, t + 2);
-            table_load_commands(ring, t + 1, lane, nxt);
-        }
-#pragma unroll
-        for (int r = 0; r < kRows; r++) prev[r] = seen[r];
-#pragma unroll
-        for (int k = 0; k < kRows / 2; k++) cur[k] = nxt[k];
+        if (INNER || t > 0) store_answers<SP>(prev, t - 1);
     }
-    table_store_answers(seen_base, nb - 1, lane, prev, consumed);
-}
+    template <int SLOT, bool INNER>
+    __device__ __forceinline__ bool steps(uint32_t base, uint4 (&a)[kRows / 2], uint4 (&b)[kRows / 2], uint32_t (&sa)[kRows],
+                                          uint32_t (&sb)[kRows], uint32_t& flag) const {
+        if constexpr (SLOT < kRing) {
+            if (!INNER && base + SLOT >= nb) return false;
+            step<SLOT, INNER>(base, a, b, sa, sb, flag);
+            if (!INNER && base + SLOT + 1 >= nb) return false;
+            step<SLOT + 1, INNER>(base, b, a, sb, sa, flag);
+            return steps<SLOT + 2, INNER>(base, a, b, sa, sb, flag);
+        } else {
+            return true;
+        }
+    }
+    __device__ __forceinline__ void run() const {
+        if (nb == 0) return;
+        uint4 a[kRows / 2], b[kRows / 2];
+        uint32_t sa[kRows], sb[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; r++) sa[r] = sb[r] = 0u;
+        wait_flag<0>(0u, 1u);
+        load_commands<0>(a);
+        uint32_t flag = load_flag<1>();
+        uint32_t base = 0;
+        if (steps<0, false>(base, a, b, sa, sb, flag)) {   // the first round of the ring (t = 0 has no previous answers)
+            for (base = kRing; base + kRing < nb; base += kRing) steps<0, true>(base, a, b, sa, sb, flag);
+            steps<0, false>(base, a, b, sa, sb, flag);     // the last round (it may be empty: nb a multiple of the ring)
+        }
+        // the answers of the last batch: in sa if nb is odd, else in sb
+        const uint32_t last = nb - 1;
+        uint32_t fin[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; r++) fin[r] = (last & 1u) ? sb[r] : sa[r];
+        asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(seen_lane + (last % kRing) * kSeenBytes), "r"(__byte_perm(fin[0], fin[1], 0x5410)),
+                     "r"(__byte_perm(fin[2], fin[3], 0x5410)), "r"(__byte_perm(fin[4], fin[5], 0x5410)), "r"(__byte_perm(fin[6], fin[7], 0x5410))
+                     : "memory");
+        if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(consumed_addr), "r"(nb) : "memory");
+    }
+};
 
 // G: positions per group of the reference loop.  TOP: index from the top bits of the product (else: low bits).
 // FAST16: H = 16 and TOP (the restated crate's parameters): the packet is the product itself.
@@ -427,7 +477,7 @@ ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restri
 
     uint32_t count = 0;
     if (warp == 0) {
-        table_warp(nb, ring, seen, ready, consumed);
+        TableWarp{smem_u32(ring) + 16u * lane, smem_u32(seen) + 16u * lane, smem_u32(ready), smem_u32(consumed), nb, lane}.run();
     } else {
         const uint32_t pi = warp - 1;
         count = producer_warp<G, TOP, FAST16>(ck, nb, pi, prm, smem_u32(table), smem_u32(sink), scratch0 + pi * kScratchSlots, ring, seen, ready,
