@@ -11,20 +11,24 @@
 //     bits of P identify the key among the keys of that bucket (checked exhaustively for every supported parameter
 //     set: tests/test_ltu_params.py).  0xFFFF means "untouched"; the one key per bucket whose 16 bits are 0xFFFF is
 //     stored as 0xFFFE, which no key of such a bucket uses (same exhaustive check).  2^16 entries = 128 KiB.
-//   * 15 PRODUCER warps turn 128 consecutive positions at a time into packets (bucket << 16 | tag) and resolve, with
-//     two shuffles per word and no ballots, everything that can be decided inside a WINDOW of two groups (8
-//     positions): a position whose predecessor of the same bucket lies in the window is counted (or not) on the spot
-//     and never touches the table ("not a head"); a position that is overwritten inside the window never writes
-//     ("not a tail").  Packets travel through a ring in shared memory (mbarrier full / empty per slot).
-//   * ONE TABLE warp consumes the ring in stream order.  Per row of 32 positions it runs four rounds (one per
-//     window): heads of the window load their entry, then tails of the window store theirs.  A warp's shared-memory
-//     instructions are performed in order, so the reference's sequential semantics hold exactly, for any data: a
-//     flat texture (every position in one bucket) and random bytes cost the same.
+//   * 15 PRODUCER warps turn 256 consecutive positions at a time (a batch = 8 rows of 32, lane = position in the row)
+//     into 8-byte commands {entry address, tag to store}.  A ROW is one window: a position whose predecessor of the
+//     same bucket lies in an earlier group of the row is decided on the spot (equal packets <=> a match) and the
+//     answer of the table is ignored for it; the last position of a bucket in the row decides what the entry holds
+//     afterwards.  Rows are screened through a per-warp byte scratch (which lanes could share a bucket at all?) and only
+//     those lanes pay for a MATCH.ANY.  Commands travel through a ring of 16 slots in shared memory.
+//   * ONE TABLE warp consumes the ring in stream order: per row one load and one store of all 32 lanes at the same
+//     addresses.  A warp's shared-memory instructions are performed in order, so the reference's sequential semantics
+//     hold exactly, for any data: a flat texture (every position in one bucket) and random bytes cost the same.  What the
+//     loads found goes back to the producer (16 bits per position), which counts the matches one ring cycle later.
+//     The table warp is ~30 instructions per batch, unrolled over the ring: it is the serial part of the machine.
 //   * Chunks of one stream run concurrently.  A chunk that does not start its segment does not know the table it
-//     inherits: a head that finds its entry untouched records its tag in first_seen[bucket][position & 3] (global),
+//     inherits: a position that finds its entry untouched records its tag in first_seen[bucket][position & 3] (global),
 //     the chunk publishes its final table, and one small RESOLVE kernel walks the chunks of a segment in order, one
 //     thread per bucket, fully coalesced, and adds the matches of those first touches.
 // DRAM traffic: the stream is read once (1 byte per position); hand-over state is 640 KiB per chunk.
+// Measured (B200, 4 x 32 Mi positions): 1.30 ms for the first version of this design (one producer lane per 8-position
+// window, four table rounds per row), 0.47 ms now; the steps are in DESIGN.md.
 #include "estimator.h"
 
 #include <algorithm>
@@ -50,6 +54,7 @@ constexpr int kSlotBytes = kRows * 32 * 8;             // one batch of commands:
 constexpr int kSeenBytes = kRows * 32 * 2;             // one batch of answers: what every position found in the table (16 bits)
 constexpr int kRing = 16;                              // ring slots (a power of two)
 constexpr int kSinkBytes = 64;                         // where positions that do not exist load and store: one 16-bit word per lane
+constexpr int kRowGroup = 2;                            // rows a producer resolves side by side (measured: 1: 0.77, 2: 0.69, 4: 0.70, 8: 0.73 ms)
 constexpr int kScratchSlots = 2048;                    // per producer warp: byte slots of the row screen (a power of two)
 // 16 warps: the table warp and 15 producers.  (Keeping the table warp's scheduler to itself — producers only on the other
 // three — did not make it faster: its pace is the LSU's dispatch rate of one instruction per 4 cycles and per warp, with
@@ -187,47 +192,80 @@ __device__ __forceinline__ uint32_t produce_batch(const uint32_t (&wa)[kRows], c
     const uint32_t below = (1u << (lane & ~(unsigned)(G - 1))) - 1u;   // the lanes of earlier groups
     uint32_t count = 0;
     pend.heads = 0;
+    // kRowGroup rows at a time, every step for all rows of the group before the next step: the chain store -> load -> vote ->
+    // REDUX -> MATCH -> shuffle of ONE row is ~400 cycles of latency, and a producer that walks its rows one by one spends
+    // 4700 cycles per batch (ncu r02_seq_v8: with the table warp at ~30 instructions per batch the producers set the pace).
 #pragma unroll
-    for (int r = 0; r < kRows; r++) {
-        const uint32_t pkt = packet_of<FAST16, TOP>(__funnelshift_r(wa[r], wb[r], fsh) & kLtuKeyMask, prm);
-        pend.pkt[r] = pkt;
-        bool act = true;
-        if (!FULL) {
-            act = pos0 + 32u * r < chunk_valid;
-            if (prm.part_mask) act = act && ((pkt >> prm.part_shift) & prm.part_mask) == part;
+    for (int r0 = 0; r0 < kRows; r0 += kRowGroup) {
+        uint32_t pkt[kRowGroup], bucket[kRowGroup], slot[kRowGroup], winner[kRowGroup];
+        bool act[kRowGroup];
+#pragma unroll
+        for (int i = 0; i < kRowGroup; i++) {
+            const int r = r0 + i;
+            pkt[i] = packet_of<FAST16, TOP>(__funnelshift_r(wa[r], wb[r], fsh) & kLtuKeyMask, prm);
+            pend.pkt[r] = pkt[i];
+            act[i] = true;
+            if (!FULL) {
+                act[i] = pos0 + 32u * r < chunk_valid;
+                if (prm.part_mask) act[i] = act[i] && ((pkt[i] >> prm.part_shift) & prm.part_mask) == part;
+            }
+            bucket[i] = FAST16 ? pkt[i] >> 16 : pkt[i] >> prm.sb;
+            // screen: which lanes share their scratch slot with another lane?  (scratch_addr is 2 KiB aligned.)  A slot may
+            // also be overwritten by a lane of another row of the group: that only adds false alarms.
+            slot[i] = scratch_addr | (bucket[i] & (kScratchSlots - 1));
+            if (FULL || act[i]) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(slot[i]), "r"(lane) : "memory");
         }
-        const uint32_t bucket = FAST16 ? pkt >> 16 : pkt >> prm.sb;
-        const uint32_t entry = FAST16 ? table_addr + 2u * bucket : table_addr + (((pkt & prm.keep_mask) >> prm.sb) << 1);
-        // screen: which lanes share their scratch slot with another lane of this row?  (scratch_addr is 2 KiB aligned;
-        // store then load of one warp: performed in order)
-        const uint32_t slot = scratch_addr | (bucket & (kScratchSlots - 1));
-        uint32_t winner = lane;
-        if (FULL) {
-            asm volatile("st.volatile.shared.u8 [%1], %2;\n ld.volatile.shared.u8 %0, [%1];" : "=r"(winner) : "r"(slot), "r"(lane) : "memory");
-        } else {
-            if (act) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(slot), "r"(lane) : "memory");
-            __syncwarp();
-            if (act) asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(winner) : "r"(slot) : "memory");
+        if (!FULL) __syncwarp();   // (store then load of one converged warp: performed in order)
+#pragma unroll
+        for (int i = 0; i < kRowGroup; i++) {
+            winner[i] = lane;
+            if (FULL || act[i]) asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(winner[i]) : "r"(slot[i]) : "memory");
         }
-        const bool loser = winner != lane;
-        bool head = act;
-        uint32_t store_tag = pkt;
-        if (__any_sync(kFull, loser)) {
+        bool any_loser = false;
+#pragma unroll
+        for (int i = 0; i < kRowGroup; i++) any_loser |= winner[i] != lane;
+        const bool resolve = __any_sync(kFull, any_loser);
+        bool head[kRowGroup];
+        uint32_t store_tag[kRowGroup];
+#pragma unroll
+        for (int i = 0; i < kRowGroup; i++) head[i] = act[i], store_tag[i] = pkt[i];
+        if (resolve) {
+            // phase by phase over the rows of the group (warp-level operations are issued in program order: a row's chain
+            // written out on its own would be waited for link by link)
+            uint32_t named[kRowGroup], same[kRowGroup], lower[kRowGroup], pred_pkt[kRowGroup];
+            bool contested[kRowGroup];
             // the lane that won a contested slot must learn it too: every loser names its winner
-            const uint32_t named = __reduce_or_sync(kFull, loser ? 1u << winner : 0u);
-            const bool contested = loser || ((named >> lane) & 1u);   // may share its bucket with another lane of the row
-            // (a real bucket has at most 17 bits)
-            const uint32_t same = __match_any_sync(kFull, contested ? bucket : 0xFFFFFFFFu);
-            const uint32_t lower = contested ? same & below : 0u;
-            const uint32_t tail_lane = contested ? 31u - (uint32_t)__clz(same) : lane;
-            const uint32_t pred_pkt = __shfl_sync(kFull, pkt, lower ? 31u - (uint32_t)__clz(lower) : lane);
-            store_tag = __shfl_sync(kFull, pkt, tail_lane);
-            head = act && lower == 0u;
-            count += lower != 0u && pred_pkt == pkt;
+#pragma unroll
+            for (int i = 0; i < kRowGroup; i++) named[i] = __reduce_or_sync(kFull, winner[i] != lane ? 1u << winner[i] : 0u);
+#pragma unroll
+            for (int i = 0; i < kRowGroup; i++) {
+                // may share its bucket with another lane of the row.  (A loser may name a lane of the OTHER row of the group: a
+                // false alarm for that lane here, and nothing at all if the position does not exist in this row.)
+                contested[i] = act[i] && (winner[i] != lane || ((named[i] >> lane) & 1u));
+                // the others all enter with one common value (a real bucket has at most 17 bits)
+                same[i] = __match_any_sync(kFull, contested[i] ? bucket[i] : 0xFFFFFFFFu);
+            }
+#pragma unroll
+            for (int i = 0; i < kRowGroup; i++) {
+                lower[i] = contested[i] ? same[i] & below : 0u;
+                pred_pkt[i] = __shfl_sync(kFull, pkt[i], lower[i] ? 31u - (uint32_t)__clz(lower[i]) : lane);
+            }
+#pragma unroll
+            for (int i = 0; i < kRowGroup; i++) store_tag[i] = __shfl_sync(kFull, pkt[i], contested[i] ? 31u - (uint32_t)__clz(same[i]) : lane);
+#pragma unroll
+            for (int i = 0; i < kRowGroup; i++) {
+                head[i] = act[i] && lower[i] == 0u;
+                count += lower[i] != 0u && pred_pkt[i] == pkt[i];
+            }
         }
-        cmd_a[r] = act ? entry : sink_addr;
-        cmd_b[r] = store_tag;   // the table warp stores the low 16 bits
-        pend.heads |= (uint32_t)head << r;
+#pragma unroll
+        for (int i = 0; i < kRowGroup; i++) {
+            const int r = r0 + i;
+            const uint32_t entry = FAST16 ? table_addr + 2u * bucket[i] : table_addr + (((pkt[i] & prm.keep_mask) >> prm.sb) << 1);
+            cmd_a[r] = act[i] ? entry : sink_addr;
+            cmd_b[r] = store_tag[i];   // the table warp stores the low 16 bits
+            pend.heads |= (uint32_t)head[i] << r;
+        }
     }
     return count;
 }
