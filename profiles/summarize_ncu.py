@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Turns an ncu report (gpurun_out/*.ncu-rep) into the small text/JSON summaries kept under profiles/.
 
-    python profiles/summarize_ncu.py gpurun_out/prof_r01.ncu-rep r01
+    python profiles/summarize_ncu.py gpurun_out/prof_r01.ncu-rep r01 [outdir=profiles/]
+(run it on the GPU box with outdir=gpurun_out when the .ncu-rep is too big to bring back)
 """
 import csv
 import io
@@ -27,7 +28,7 @@ def to_bytes(value: str, unit: str) -> float:
     return float(value.replace(",", "")) * scale.get(unit, 1)
 
 
-def main(rep: str, tag: str) -> None:
+def main(rep: str, tag: str, outdir: Path = HERE) -> None:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -43,10 +44,10 @@ def main(rep: str, tag: str) -> None:
         wr = to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
         traffic[name] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "dram_total_bytes": rd + wr}
         lines.append(f"    {'dram read+write bytes per launch':70s} {rd + wr:.0f}")
-    (HERE / f"{tag}_ncu_full_summary.txt").write_text("\n".join(lines) + "\n")
-    (HERE / f"{tag}_dram_traffic_per_kernel.json").write_text(json.dumps(traffic, indent=1) + "\n")
+    (outdir / f"{tag}_ncu_full_summary.txt").write_text("\n".join(lines) + "\n")
+    (outdir / f"{tag}_dram_traffic_per_kernel.json").write_text(json.dumps(traffic, indent=1) + "\n")
     print("\n".join(lines))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], Path(sys.argv[3]) if len(sys.argv) > 3 else HERE)
