@@ -13,6 +13,8 @@
 #include <emmintrin.h>
 #endif
 
+#include <atomic>
+
 #include <cuda.h>   // types of cuPointerGetAttributes only; the entry point comes from cudaGetDriverEntryPoint
 
 #include "bcn_kernels.h"
@@ -74,6 +76,10 @@ inline void stream_copy(uint8_t* dst, const uint8_t* src, size_t n) {
 // pipeline keeps up with the link (one thread tops out well below PCIe Gen5).  Two pools: one FILLS the pinned input
 // slots (driven by the submitting thread), one DRAINS the pinned output slots (driven by the pipeline's drain thread),
 // so uploads and downloads of a pageable call overlap on the host as they do on the link.
+// A part is 0.5-3 MiB — 50-300 us of copying — so how fast a worker STARTS matters as much as how fast it copies: waking
+// a thread that sleeps on a condition variable costs 50-100 us in a VM.  Workers therefore keep polling for ~200 us after
+// their last part (the next chunk of a running pipeline arrives sooner than that) before they go to sleep, and parts are
+// handed out through one atomic ticket {generation, parts of the job, next part}: no lock on the copy path.
 class CopyPool {
 public:
     static CopyPool& fill() {
@@ -86,25 +92,32 @@ public:
     }
     void copy(uint8_t* dst, const uint8_t* src, size_t n) {
         constexpr size_t kMinPart = 512u << 10;
-        const size_t parts = std::min<size_t>(workers_.size() + 1, n / kMinPart);
+        const size_t parts = std::min<size_t>({workers_ + 1, n / kMinPart, kFieldMask});
         if (parts <= 1) {
             stream_copy(dst, src, n);
             return;
         }
         std::lock_guard<std::mutex> serial(call_mutex_);  // one parallel copy at a time per pool
-        const size_t per = (n / parts + 63) & ~(size_t)63;
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            dst_ = dst, src_ = src, n_ = n, per_ = per, next_ = 1, pending_ = parts - 1, total_parts_ = parts;
-            ++generation_;
+        dst_ = dst, src_ = src, n_ = n, per_ = (n / parts + 63) & ~(size_t)63;
+        pending_.store(parts, std::memory_order_relaxed);
+        const uint64_t gen = (ticket_.load(std::memory_order_relaxed) >> (2 * kFieldBits)) + 1;
+        ticket_.store(gen << (2 * kFieldBits) | (uint64_t)parts << kFieldBits, std::memory_order_seq_cst);   // publishes the job
+        if (sleepers_.load(std::memory_order_seq_cst) > 0) {
+            { std::lock_guard<std::mutex> lk(m_); }
+            cv_.notify_all();
         }
-        cv_.notify_all();
-        stream_copy(dst, src, std::min(per, n));
-        std::unique_lock<std::mutex> lk(m_);
-        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        work();   // the caller copies parts too
+        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
     }
 
 private:
+    static constexpr int kFieldBits = 20;
+    static constexpr uint64_t kFieldMask = (1u << kFieldBits) - 1;
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(_M_X64)
+        _mm_pause();
+#endif
+    }
     CopyPool() {
         // each pool gets a bit under half of the cores: the two run at the same time
         unsigned hw = std::thread::hardware_concurrency();
@@ -113,36 +126,57 @@ private:
             const long t = std::atol(v);
             if (t >= 1 && t <= 64) n = (unsigned)t - 1;
         }
-        for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { run(); }), workers_.back().detach();
+        workers_ = n;
+        for (unsigned i = 0; i < n; i++) std::thread([this] { run(); }).detach();
+    }
+    // claims and copies parts of the current job until none is left; returns the generation it worked on
+    uint64_t work() {
+        for (;;) {
+            const uint64_t t = ticket_.fetch_add(1, std::memory_order_acq_rel);
+            const uint64_t next = t & kFieldMask, total = (t >> kFieldBits) & kFieldMask;
+            if (next >= total) {
+                // nothing left: undo the overshoot's effect on nobody (the field only counts up until the next job resets it;
+                // at most one overshoot per thread and job, far from the 2^20 that would carry)
+                return t >> (2 * kFieldBits);
+            }
+            // a valid part: the job is unfinished, so its parameters are the ones published with this ticket
+            const size_t off = next * per_;
+            if (off < n_) stream_copy(dst_ + off, src_ + off, std::min(per_, n_ - off));
+            pending_.fetch_sub(1, std::memory_order_acq_rel);
+        }
     }
     void run() {
         uint64_t seen = 0;
         for (;;) {
-            size_t part;
-            {
+            // wait for a job of a generation this thread has not finished yet: poll first, then sleep
+            uint32_t spins = 0;
+            while ((ticket_.load(std::memory_order_acquire) >> (2 * kFieldBits)) == seen) {
+                if (++spins < 40000) {   // ~200 us
+                    cpu_relax();
+                    continue;
+                }
                 std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return generation_ != seen && next_ < total_parts_; });
-                part = next_++;
-                if (next_ >= total_parts_) seen = generation_;
+                sleepers_.fetch_add(1, std::memory_order_seq_cst);
+                cv_.wait(lk, [&] { return (ticket_.load(std::memory_order_seq_cst) >> (2 * kFieldBits)) != seen; });
+                sleepers_.fetch_sub(1, std::memory_order_seq_cst);
+                spins = 0;
             }
-            const size_t off = part * per_;
-            if (off < n_) stream_copy(dst_ + off, src_ + off, std::min(per_, n_ - off));
-            {
-                std::lock_guard<std::mutex> lk(m_);
-                if (--pending_ == 0) done_cv_.notify_all();
-            }
+            seen = work();
         }
     }
-    std::vector<std::thread> workers_;
+    size_t workers_ = 0;
     std::mutex m_, call_mutex_;
-    std::condition_variable cv_, done_cv_;
+    std::condition_variable cv_;
+    std::atomic<uint64_t> ticket_{0};   // generation << 40 | parts << 20 | next part
+    std::atomic<size_t> pending_{0};
+    std::atomic<int> sleepers_{0};
     uint8_t* dst_ = nullptr;
     const uint8_t* src_ = nullptr;
-    size_t n_ = 0, per_ = 0, next_ = 0, pending_ = 0, total_parts_ = 0;
-    uint64_t generation_ = 0;
+    size_t n_ = 0, per_ = 0;
 };
 
 inline void staged_copy(uint8_t* dst, const uint8_t* src, size_t n) { CopyPool::fill().copy(dst, src, n); }
+
 
 Status create_context(int device, Context** out) {
     Context* c = new Context();
