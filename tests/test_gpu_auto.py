@@ -79,9 +79,9 @@ def test_estimator_device_pointer_any_alignment(dlt, torch):
 
 
 def adversarial_streams():
-    """Inputs aimed at the partition + per-piece compare path: everything in one bucket, rare outliers in a flat
-    stream (long look-backs in the resolve pass), same-group bucket collisions across piece boundaries, sizes on
-    both sides of every piece-length threshold."""
+    """Inputs aimed at the worst cases of any parallel formulation of the sequential table: everything in one bucket, rare
+    outliers in a flat stream (long look-backs in the hand-over between chunks), same-group bucket collisions across
+    window / batch / chunk boundaries, short periods, low-entropy streams of many sizes."""
     rng = np.random.default_rng(77)
     yield "zeros_1M", np.zeros(1 << 20, np.uint8)
     yield "ff_3M+5", np.full((3 << 20) + 5, 0xFF, np.uint8)
@@ -109,6 +109,29 @@ def test_estimator_large_path_adversarial(dlt, torch):
         assert dlt.ltu_estimate_device(d.data_ptr(), data.size) == oracle.ltu_estimate(data), name
         if data.size > 100_000:  # an unaligned view of the same stream
             assert dlt.ltu_estimate_device(d.data_ptr() + 3, data.size - 3) == oracle.ltu_estimate(data[3:]), name
+
+
+def test_estimator_batch_row_and_ring_boundaries(dlt, torch):
+    """Sizes around every boundary of the table machine (csrc/estimator.cu): a row is 32 positions, a batch 256, the ring has
+    16 slots, a chunk starts at 128 batches, a call aims at one chunk per SM; the loop visits len - 7 positions rounded up to
+    the group.  Three kinds of data: almost every row contested (two symbols), almost none (random), one bucket (flat);
+    several segments per call go through the batched search tests."""
+    rng = np.random.default_rng(2026)
+    sizes = set()
+    for positions in (1, 4, 31, 32, 33, 255, 256, 257, 511, 512, 513, 15 * 256, 16 * 256, 17 * 256, 32 * 256 + 4, 127 * 256, 128 * 256,
+                      128 * 256 + 4, 129 * 256, 2 * 128 * 256, 2 * 128 * 256 + 260, 148 * 128 * 256 - 256, 148 * 128 * 256, 148 * 128 * 256 + 512):
+        for delta in (-4, -1, 0, 3):
+            if positions + 7 + delta > 7:
+                sizes.add(positions + 7 + delta)
+    for n in sorted(sizes):
+        kinds = {"two": rng.integers(0, 2, n, dtype=np.uint8), "flat": np.full(n, 9, np.uint8)}
+        if n < 2_000_000:
+            kinds["random"] = rng.integers(0, 256, n, dtype=np.uint8)
+        for name, data in kinds.items():
+            d = torch.from_numpy(data).cuda()
+            assert dlt.ltu_estimate_device(d.data_ptr(), n) == oracle.ltu_estimate(data), (name, n)
+            if n > 64:   # the same stream from an odd address
+                assert dlt.ltu_estimate_device(d.data_ptr() + 1, n - 1) == oracle.ltu_estimate(data[1:]), (name, n, "+1")
 
 
 @pytest.mark.parametrize("fmt", [1, 2, 3])
