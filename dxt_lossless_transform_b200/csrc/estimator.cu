@@ -33,6 +33,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -726,8 +727,32 @@ size_t ltu_scratch_bytes(const LtuSegment* segs, int nseg) {
     return scratch_bound((size_t)std::max(nseg, 0), batches, geometry(ltu_params()));
 }
 
-// One launch of the table machine over all chunks of all segments, one resolve launch if any segment was cut, one
-// copy back and one synchronize.  A directory of small textures is one chunk per endpoint stream.
+// Page-locked staging for the descriptors and the results of a call, one per host thread (a call synchronises its stream
+// before it returns, so the buffer is free again).  Grown on demand, never freed: a few KiB for one texture, 64 bytes per
+// chunk for a directory.  nullptr if page-locked memory cannot be had: the copies then go through pageable memory.
+static uint8_t* call_staging(size_t bytes) {
+    struct Buf {
+        uint8_t* p = nullptr;
+        size_t cap = 0;
+    };
+    thread_local Buf buf;
+    if (buf.cap < bytes) {
+        if (buf.p) cudaFreeHost(buf.p);
+        buf.p = nullptr, buf.cap = 0;
+        const size_t want = std::max<size_t>(align_up(bytes, 4096), 64u << 10);
+        void* q = nullptr;
+        if (cudaHostAlloc(&q, want, cudaHostAllocDefault) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        buf.p = static_cast<uint8_t*>(q), buf.cap = want;
+    }
+    return buf.p;
+}
+
+// One launch of the table machine over all chunks of all segments, one resolve launch if any segment was cut; the zeroed
+// result slots and both descriptor tables go up in ONE copy from page-locked memory, the results come back in one, and the
+// call synchronises once.  A directory of small textures is one chunk per endpoint stream.
 Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, cudaStream_t stream, uint8_t* scratch,
                           size_t scratch_bytes) {
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
@@ -740,20 +765,34 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
     };
     const Plan sizes = make_plan(segs, nseg, p, g, false, nullptr);
     if (scratch_bytes < result_bytes(nseg) + sizes.total()) return Status::kOutOfMemory;
+    const size_t res_bytes = result_bytes(nseg);
     unsigned long long* d_matches = reinterpret_cast<unsigned long long*>(scratch);
-    uint8_t* d_chunk_desc = scratch + result_bytes(nseg);
+    uint8_t* d_chunk_desc = scratch + res_bytes;
     uint8_t* d_resolve_desc = d_chunk_desc + sizes.chunk_desc_bytes;
     uint8_t* d_state = d_resolve_desc + sizes.resolve_desc_bytes;
     const Plan pl = make_plan(segs, nseg, p, g, true, d_state);
 
-    cudaError_t e = cudaMemsetAsync(d_matches, 0, result_bytes(nseg), stream);
-    if (e != cudaSuccess) return fail(e);
-    if (!pl.chunks.empty()) {
-        // pageable source: the driver stages the bytes before the call returns, the vectors may die afterwards
-        e = cudaMemcpyAsync(d_chunk_desc, pl.chunks.data(), pl.chunks.size() * sizeof(SeqChunk), cudaMemcpyHostToDevice, stream);
+    // [results = 0 | chunk descriptors | resolve descriptors] is contiguous on the device: one upload
+    const size_t head_bytes = res_bytes + sizes.chunk_desc_bytes + sizes.resolve_desc_bytes;
+    uint8_t* staging = call_staging(head_bytes);
+    cudaError_t e;
+    if (staging) {
+        std::memset(staging, 0, res_bytes);
+        std::memcpy(staging + res_bytes, pl.chunks.data(), pl.chunks.size() * sizeof(SeqChunk));
+        std::memcpy(staging + res_bytes + sizes.chunk_desc_bytes, pl.resolves.data(), pl.resolves.size() * sizeof(SeqResolve));
+        const size_t used = pl.resolves.empty() ? res_bytes + pl.chunks.size() * sizeof(SeqChunk)
+                                                : res_bytes + sizes.chunk_desc_bytes + pl.resolves.size() * sizeof(SeqResolve);
+        e = cudaMemcpyAsync(scratch, staging, used, cudaMemcpyHostToDevice, stream);
+    } else {
+        // pageable sources: the driver stages the bytes before the call returns, the vectors may die afterwards
+        e = cudaMemsetAsync(d_matches, 0, res_bytes, stream);
+        if (e == cudaSuccess && !pl.chunks.empty())
+            e = cudaMemcpyAsync(d_chunk_desc, pl.chunks.data(), pl.chunks.size() * sizeof(SeqChunk), cudaMemcpyHostToDevice, stream);
         if (e == cudaSuccess && !pl.resolves.empty())
             e = cudaMemcpyAsync(d_resolve_desc, pl.resolves.data(), pl.resolves.size() * sizeof(SeqResolve), cudaMemcpyHostToDevice, stream);
-        if (e != cudaSuccess) return fail(e);
+    }
+    if (e != cudaSuccess) return fail(e);
+    if (!pl.chunks.empty()) {
         const SeqChunk* dc = reinterpret_cast<const SeqChunk*>(d_chunk_desc);
         const int n = (int)pl.chunks.size();
         if (p.group == 4 && p.index_top && p.hash_bits == 16) e = launch_seq<4, true, true>(dc, n, d_matches, g, stream);   // the restated crate
@@ -768,9 +807,11 @@ Status ltu_matches_device(const LtuSegment* segs, int nseg, uint64_t* matches, c
             g_est_launches.fetch_add(1, std::memory_order_relaxed);
         }
     }
-    if ((e = cudaMemcpyAsync(matches, d_matches, sizeof(uint64_t) * (size_t)nseg, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+    void* back = staging ? static_cast<void*>(staging) : static_cast<void*>(matches);
+    if ((e = cudaMemcpyAsync(back, d_matches, sizeof(uint64_t) * (size_t)nseg, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(stream)) != cudaSuccess)
         return fail(e);
+    if (staging) std::memcpy(matches, staging, sizeof(uint64_t) * (size_t)nseg);
     return Status::kOk;
 }
 
