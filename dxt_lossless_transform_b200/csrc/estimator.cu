@@ -248,11 +248,13 @@ __device__ __forceinline__ uint32_t produce_batch(const uint32_t (&wa)[kRows], c
             }
 #pragma unroll
             for (int i = 0; i < kRowGroup; i++) {
-                lower[i] = contested[i] ? same[i] & below : 0u;
-                pred_pkt[i] = __shfl_sync(kFull, pkt[i], lower[i] ? 31u - (uint32_t)__clz(lower[i]) : lane);
+                if (!contested[i]) same[i] = 1u << lane;   // alone in its bucket (the common value's class means nothing)
+                lower[i] = same[i] & below;
+                // (no predecessor: lane -1 = lane 31 of the shuffle, and the value is not looked at)
+                pred_pkt[i] = __shfl_sync(kFull, pkt[i], 31u - (uint32_t)__clz(lower[i]));
             }
 #pragma unroll
-            for (int i = 0; i < kRowGroup; i++) store_tag[i] = __shfl_sync(kFull, pkt[i], contested[i] ? 31u - (uint32_t)__clz(same[i]) : lane);
+            for (int i = 0; i < kRowGroup; i++) store_tag[i] = __shfl_sync(kFull, pkt[i], 31u - (uint32_t)__clz(same[i]));
 #pragma unroll
             for (int i = 0; i < kRowGroup; i++) {
                 head[i] = act[i] && lower[i] == 0u;

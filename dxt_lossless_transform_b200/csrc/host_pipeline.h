@@ -40,6 +40,8 @@ struct HostPathConfig {
     size_t zero_copy_max_bytes;
     bool ramp;
     bool strided;
+    size_t split;             // a single-payload call is cut into about this many chunks ...
+    size_t min_chunk_bytes;   // ... but not into chunks smaller than this
 };
 const HostPathConfig& host_path_config();
 
