@@ -53,20 +53,21 @@ constexpr int kRows = 8;                                // rows of 32 consecutiv
 constexpr int kBatchPos = 32 * kRows;                  // positions per batch (one producer warp iteration)
 constexpr int kSlotBytes = kRows * 32 * 8;             // one batch of commands: 8 bytes per position
 constexpr int kSeenBytes = kRows * 32 * 2;             // one batch of answers: what every position found in the table (16 bits)
-constexpr int kRing = 16;                              // ring slots (a power of two)
+constexpr int kWarps = 20;                             // the table warp and 19 producers (16 / 18 / 20 warps: 0.688 / 0.679 / 0.664 ms for the 64 MiB search;
+                                                       // 96 registers x 640 threads and 223 KiB of shared memory: the SM is full)
+constexpr int kRing = kWarps;                          // ring slots (even: the table warp's loop is unrolled over them in pairs)
 constexpr int kSinkBytes = 64;                         // where positions that do not exist load and store: one 16-bit word per lane
 constexpr int kRowGroup = 2;                            // rows a producer resolves side by side (measured: 1: 0.77, 2: 0.69, 4: 0.70, 8: 0.73 ms)
 constexpr int kScratchSlots = 2048;                    // per producer warp: byte slots of the row screen (a power of two)
-// 16 warps: the table warp and 15 producers.  (Keeping the table warp's scheduler to itself — producers only on the other
+// The table warp and kWarps - 1 producers.  (Keeping the table warp's scheduler to itself — producers only on the other
 // three — did not make it faster: its pace is the LSU's dispatch rate of one instruction per 4 cycles and per warp, with
 // or without neighbours; ncu r02_seq_v3 .. v5.)
-constexpr int kWarps = 16;
 constexpr int kProducers = kWarps - 1;
 constexpr int kSeqThreads = kWarps * 32;
 constexpr int kMaxTableEntries = 1 << 16;              // per CTA: 128 KiB of 16-bit entries
 constexpr int kTargetChunks = 148;                     // one chunk per SM when there is enough work
 constexpr uint32_t kMinChunkBatches = 128;             // 32 Ki positions: below this a chunk's fixed costs dominate
-static_assert(kRing >= kProducers && (kRing & (kRing - 1)) == 0, "every producer holds one batch in the ring");
+static_assert(kRing >= kProducers && kRing % 2 == 0, "every producer holds one batch in the ring");
 
 // Number of positions the reference loop visits: groups starting at i = 0, G, 2G, .. while i < len - 7.
 inline size_t ltu_positions(size_t len, int group) {
@@ -278,17 +279,23 @@ __device__ __forceinline__ uint32_t produce_batch(const uint32_t (&wa)[kRows], c
 template <bool FAST16>
 __device__ __forceinline__ uint32_t collect_batch(const Pending& pend, const uint4 seen4, const SeqParams& prm, uint16_t* first_seen) {
     const uint32_t packed[4] = {seen4.x, seen4.y, seen4.z, seen4.w};
-    uint32_t count = 0;
+    uint32_t count = 0, untouched = 0;
 #pragma unroll
     for (int r = 0; r < kRows; r++) {
         const uint32_t seen = (r & 1) ? packed[r >> 1] >> 16 : packed[r >> 1] & 0xFFFFu;
         const uint32_t tag = pend.pkt[r] & 0xFFFFu;
-        const bool head = (pend.heads >> r) & 1u;
-        count += head && seen == tag;
-        if (first_seen && head && seen == kUntouched) {
-            const uint32_t idx = FAST16 ? pend.pkt[r] >> 16 : (pend.pkt[r] & prm.keep_mask) >> prm.sb;
-            first_seen[(size_t)idx * 4] = (uint16_t)tag;   // first_seen is already advanced by position & 3
-        }
+        count += ((pend.heads >> r) & 1u) && seen == tag;
+        untouched |= (uint32_t)(seen == kUntouched) << r;
+    }
+    // heads that found their entry untouched: common in the first batches of a chunk, rare afterwards (a lane-level branch)
+    untouched &= pend.heads;
+    if (first_seen && untouched) {
+#pragma unroll
+        for (int r = 0; r < kRows; r++)
+            if ((untouched >> r) & 1u) {
+                const uint32_t idx = FAST16 ? pend.pkt[r] >> 16 : (pend.pkt[r] & prm.keep_mask) >> prm.sb;
+                first_seen[(size_t)idx * 4] = (uint16_t)pend.pkt[r];   // first_seen is already advanced by position & 3
+            }
     }
     return count;
 }
@@ -334,6 +341,8 @@ __device__ __forceinline__ uint32_t producer_warp(const SeqChunk& ck, const uint
     Pending pend;        // the batch this warp produced last (t - kProducers), not yet collected
     bool have_pending = false;
     uint32_t t = pi;
+    // (Writing the loop out in pairs with two register sets that change roles — no copies of the 16 prefetched words and the
+    // 9 remembered ones — made ptxas spill: 0.66 -> 0.72 ms.)
     for (; t < nb; t += kProducers) {
         uint32_t ca[kRows], cb[kRows];
 #pragma unroll
@@ -358,7 +367,7 @@ __device__ __forceinline__ uint32_t producer_warp(const SeqChunk& ck, const uint
 #pragma unroll
         for (int k = 0; k < kRows / 2; k++) sw[k * 32] = make_uint4(cmd_a[2 * k], cmd_b[2 * k], cmd_a[2 * k + 1], cmd_b[2 * k + 1]);
         __syncwarp();
-        if (lane == 0) st_volatile_shared(ready + t % kRing, t + 1);   // (a release store is a MEMBAR: it would wait for the prefetch loads)
+        if (lane == 0) st_release_shared(ready + t % kRing, t + 1);   // (MEMBAR.CTA + STS; measured: free on this side of the ring)
     }
     if (have_pending) {
         wait_at_least<true>(consumed, t - kProducers + 1);
