@@ -510,14 +510,19 @@ __device__ __forceinline__ void transform_tile(const uint8_t* __restrict__ in, c
     }
 }
 
-// Resident CTAs per SM the transform kernels are compiled for.  The RAGGED kernel of the six-stream BC3 layouts waits
-// longer per tile (halo, more segment edges): at 8 CTAs / SM (32 registers, no spills) every BC3 settings combination
-// runs at 6.82-6.85 TB/s on 1 GiB - 3 blocks against 5.6-6.4 at 6 (profiles/r02_ragged_variants.jsonl); BC1 / BC2 and
-// the aligned kernels are best at 6.
-constexpr int transform_min_ctas(int fmt, bool ragged) { return ragged && fmt == 3 ? 8 : DLT_MIN_CTAS; }
+// Resident CTAs per SM the transform kernels are compiled for.  The RAGGED kernels with many streams wait longer per tile
+// (halo, more segment edges): compiled for 8 CTAs / SM (32 registers, no spills) every BC3 settings combination runs at
+// 6.82-6.86 TB/s on 1 GiB - 3 blocks against 5.6-6.4 at 6, and the BC2 split-colour layouts at 6.83-6.87 against 6.62-6.80;
+// the BC2 layouts with one colour stream (6.83 at 6, 6.27-6.67 at 8), BC1 (6.83-6.98 at 6) and the aligned kernels are
+// best at 6 (profiles/r02_ragged_ctas.jsonl: 6 / 7 / 8 for every settings combination).
+#ifdef DLT_RAGGED_CTAS
+constexpr int transform_min_ctas(int fmt, bool sc, bool ragged) { return ragged ? DLT_RAGGED_CTAS : DLT_MIN_CTAS; }
+#else
+constexpr int transform_min_ctas(int fmt, bool sc, bool ragged) { return ragged && (fmt == 3 || (fmt == 2 && sc)) ? 8 : DLT_MIN_CTAS; }
+#endif
 
 template <int FMT, bool SA, bool SC, int VAR, bool RAGGED, int NORM = kNormNone>
-__global__ void __launch_bounds__(kThreads, transform_min_ctas(FMT, RAGGED))
+__global__ void __launch_bounds__(kThreads, transform_min_ctas(FMT, SC, RAGGED))
     transform_tiled(const uint8_t* __restrict__ in, const StreamPtrs out, const uint64_t nblocks) {
     transform_tile<FMT, SA, SC, VAR, RAGGED, NORM>(in, out, nblocks);
 }
@@ -525,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, transform_min_ctas(FMT, RAGGED))
 // Many independent payloads with the same settings in ONE launch (the candidates of a batched best-settings search:
 // a directory of small textures is launch-bound otherwise): blockIdx.y picks the payload, blockIdx.x its tile.
 template <int FMT, bool SA, bool SC, int VAR, bool RAGGED>
-__global__ void __launch_bounds__(kThreads, transform_min_ctas(FMT, RAGGED)) transform_tiled_batch(const TransformBatchItem* __restrict__ items) {
+__global__ void __launch_bounds__(kThreads, transform_min_ctas(FMT, SC, RAGGED)) transform_tiled_batch(const TransformBatchItem* __restrict__ items) {
     const TransformBatchItem it = items[blockIdx.y];
     using L = Lay<FMT, SA, SC>;
     if ((uint64_t)blockIdx.x * L::T >= it.nblocks) return;

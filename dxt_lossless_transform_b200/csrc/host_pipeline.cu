@@ -18,6 +18,9 @@
 #include <cuda.h>   // types of cuPointerGetAttributes only; the entry point comes from cudaGetDriverEntryPoint
 
 #include "bcn_kernels.h"
+#include "copy_pool.h"
+
+static_assert(dlt::kCopyPoolMaxSegs >= dlt::kMaxStreams, "a copy job takes all streams of a chunk");
 
 namespace dlt {
 namespace {
@@ -40,140 +43,6 @@ thread_local char t_error[256] = "";
             return e__ == cudaErrorMemoryAllocation ? Status::kOutOfMemory : Status::kCudaError; \
         }                                                      \
     } while (0)
-
-// Copy with non-temporal stores: neither side of a staging copy is read again by this core (the pinned slot is read by
-// the DMA engine, the caller's buffer by whoever comes after the call), so the destination lines need not be fetched
-// first (a plain store reads the line it is about to overwrite: 3 bytes of DRAM traffic per byte copied instead of 2)
-// and must not evict the caches.  glibc only switches to such stores for copies far larger than the 2 MiB parts here.
-inline void stream_copy(uint8_t* dst, const uint8_t* src, size_t n) {
-#if defined(__x86_64__) || defined(_M_X64)
-    if (n < 4096) {
-        std::memcpy(dst, src, n);
-        return;
-    }
-    const size_t head = (64 - (reinterpret_cast<uintptr_t>(dst) & 63)) & 63;
-    std::memcpy(dst, src, head);
-    dst += head, src += head, n -= head;
-    const size_t lines = n / 64;
-    for (size_t i = 0; i < lines; i++) {
-        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i));
-        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 16));
-        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 32));
-        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 48));
-        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i), a);
-        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 16), b);
-        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 32), c);
-        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 48), d);
-    }
-    _mm_sfence();
-    std::memcpy(dst + 64 * lines, src + 64 * lines, n - 64 * lines);
-#else
-    std::memcpy(dst, src, n);
-#endif
-}
-
-// Staging copies for pageable caller memory: a few worker threads split each large copy so the host side of the
-// pipeline keeps up with the link (one thread tops out well below PCIe Gen5).  Two pools: one FILLS the pinned input
-// slots (driven by the submitting thread), one DRAINS the pinned output slots (driven by the pipeline's drain thread),
-// so uploads and downloads of a pageable call overlap on the host as they do on the link.
-// A part is 0.5-3 MiB — 50-300 us of copying — so how fast a worker STARTS matters as much as how fast it copies: waking
-// a thread that sleeps on a condition variable costs 50-100 us in a VM.  Workers therefore keep polling for ~200 us after
-// their last part (the next chunk of a running pipeline arrives sooner than that) before they go to sleep, and parts are
-// handed out through one atomic ticket {generation, parts of the job, next part}: no lock on the copy path.
-class CopyPool {
-public:
-    static CopyPool& fill() {
-        static CopyPool* pool = new CopyPool;  // leaked on purpose: workers outlive static destruction
-        return *pool;
-    }
-    static CopyPool& drain() {
-        static CopyPool* pool = new CopyPool;
-        return *pool;
-    }
-    void copy(uint8_t* dst, const uint8_t* src, size_t n) {
-        constexpr size_t kMinPart = 512u << 10;
-        const size_t parts = std::min<size_t>({workers_ + 1, n / kMinPart, kFieldMask});
-        if (parts <= 1) {
-            stream_copy(dst, src, n);
-            return;
-        }
-        std::lock_guard<std::mutex> serial(call_mutex_);  // one parallel copy at a time per pool
-        dst_ = dst, src_ = src, n_ = n, per_ = (n / parts + 63) & ~(size_t)63;
-        pending_.store(parts, std::memory_order_relaxed);
-        const uint64_t gen = (ticket_.load(std::memory_order_relaxed) >> (2 * kFieldBits)) + 1;
-        ticket_.store(gen << (2 * kFieldBits) | (uint64_t)parts << kFieldBits, std::memory_order_seq_cst);   // publishes the job
-        if (sleepers_.load(std::memory_order_seq_cst) > 0) {
-            { std::lock_guard<std::mutex> lk(m_); }
-            cv_.notify_all();
-        }
-        work();   // the caller copies parts too
-        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
-    }
-
-private:
-    static constexpr int kFieldBits = 20;
-    static constexpr uint64_t kFieldMask = (1u << kFieldBits) - 1;
-    static void cpu_relax() {
-#if defined(__x86_64__) || defined(_M_X64)
-        _mm_pause();
-#endif
-    }
-    CopyPool() {
-        // each pool gets a bit under half of the cores: the two run at the same time
-        unsigned hw = std::thread::hardware_concurrency();
-        unsigned n = hw >= 32 ? 7 : hw >= 16 ? 5 : hw >= 8 ? 3 : hw >= 4 ? 1 : 0;
-        if (const char* v = std::getenv("DLTCUDA_COPY_THREADS")) {
-            const long t = std::atol(v);
-            if (t >= 1 && t <= 64) n = (unsigned)t - 1;
-        }
-        workers_ = n;
-        for (unsigned i = 0; i < n; i++) std::thread([this] { run(); }).detach();
-    }
-    // claims and copies parts of the current job until none is left; returns the generation it worked on
-    uint64_t work() {
-        for (;;) {
-            const uint64_t t = ticket_.fetch_add(1, std::memory_order_acq_rel);
-            const uint64_t next = t & kFieldMask, total = (t >> kFieldBits) & kFieldMask;
-            if (next >= total) {
-                // nothing left: undo the overshoot's effect on nobody (the field only counts up until the next job resets it;
-                // at most one overshoot per thread and job, far from the 2^20 that would carry)
-                return t >> (2 * kFieldBits);
-            }
-            // a valid part: the job is unfinished, so its parameters are the ones published with this ticket
-            const size_t off = next * per_;
-            if (off < n_) stream_copy(dst_ + off, src_ + off, std::min(per_, n_ - off));
-            pending_.fetch_sub(1, std::memory_order_acq_rel);
-        }
-    }
-    void run() {
-        uint64_t seen = 0;
-        for (;;) {
-            // wait for a job of a generation this thread has not finished yet: poll first, then sleep
-            uint32_t spins = 0;
-            while ((ticket_.load(std::memory_order_acquire) >> (2 * kFieldBits)) == seen) {
-                if (++spins < 40000) {   // ~200 us
-                    cpu_relax();
-                    continue;
-                }
-                std::unique_lock<std::mutex> lk(m_);
-                sleepers_.fetch_add(1, std::memory_order_seq_cst);
-                cv_.wait(lk, [&] { return (ticket_.load(std::memory_order_seq_cst) >> (2 * kFieldBits)) != seen; });
-                sleepers_.fetch_sub(1, std::memory_order_seq_cst);
-                spins = 0;
-            }
-            seen = work();
-        }
-    }
-    size_t workers_ = 0;
-    std::mutex m_, call_mutex_;
-    std::condition_variable cv_;
-    std::atomic<uint64_t> ticket_{0};   // generation << 40 | parts << 20 | next part
-    std::atomic<size_t> pending_{0};
-    std::atomic<int> sleepers_{0};
-    uint8_t* dst_ = nullptr;
-    const uint8_t* src_ = nullptr;
-    size_t n_ = 0, per_ = 0;
-};
 
 inline void staged_copy(uint8_t* dst, const uint8_t* src, size_t n) { CopyPool::fill().copy(dst, src, n); }
 
@@ -681,7 +550,13 @@ public:
                 }
                 DLT_CUDA(cudaMemcpyAsync(slots_.blocks[slot], src, nb * bpb, cudaMemcpyHostToDevice, s));
                 DLT_CUDA(launch_transform(st, slots_.blocks[slot], sp, nb, s));
-                for (int k = 0; k < ns; k += run_of[k]) {
+                // a full chunk's streams are contiguous in the slot: a staged download is ONE copy (every DMA costs ~10 us)
+                const bool whole_slot = nb == chunk_blocks;
+                if (!out_pinned && whole_slot) {
+                    DLT_CUDA(cudaMemcpyAsync(ctx_->h_out[slot], slots_.streams[slot], nb * bpb, cudaMemcpyDeviceToHost, s));
+                    for (int j = 0; j < ns; j++) pend.copy[pend.ncopy++] = {job.out + host_off(j, b0), ctx_->h_out[slot] + slot_off(j), (size_t)w[j] * nb};
+                }
+                for (int k = 0; k < ns && !(!out_pinned && whole_slot); k += run_of[k]) {
                     if (out_pinned && run_of[k] > 1) {   // equal-width neighbours: one strided copy (rows = streams)
                         DLT_CUDA(cudaMemcpy2DAsync(job.out + host_off(k, b0), n * (size_t)w[k], sp.p[k], chunk_blocks * (size_t)w[k],
                                                    (size_t)w[k] * nb, (size_t)run_of[k], cudaMemcpyDeviceToHost, s));
@@ -694,20 +569,26 @@ public:
                     }
                 }
             } else {
-                for (int k = 0; k < ns; k += run_of[k]) {
+                const bool whole_slot = nb == chunk_blocks;
+                if (!in_pinned) {
+                    CopyPool::Seg segs[kMaxStreams];
+                    for (int j = 0; j < ns; j++) segs[j] = {ctx_->h_in[slot] + slot_off(j), job.in + host_off(j, b0), (size_t)w[j] * nb};
+                    CopyPool::fill().copy_many(segs, ns);
+                    if (whole_slot) {
+                        DLT_CUDA(cudaMemcpyAsync(slots_.streams[slot], ctx_->h_in[slot], nb * bpb, cudaMemcpyHostToDevice, s));
+                    } else {
+                        for (int j = 0; j < ns; j++)
+                            DLT_CUDA(cudaMemcpyAsync(sp.p[j], ctx_->h_in[slot] + slot_off(j), (size_t)w[j] * nb, cudaMemcpyHostToDevice, s));
+                    }
+                }
+                for (int k = 0; k < ns && in_pinned; k += run_of[k]) {
                     if (in_pinned && run_of[k] > 1) {
                         DLT_CUDA(cudaMemcpy2DAsync(sp.p[k], chunk_blocks * (size_t)w[k], job.in + host_off(k, b0), n * (size_t)w[k],
                                                    (size_t)w[k] * nb, (size_t)run_of[k], cudaMemcpyHostToDevice, s));
                         continue;
                     }
-                    for (int j = k; j < k + run_of[k]; j++) {
-                        const uint8_t* src = job.in + host_off(j, b0);
-                        if (!in_pinned) {
-                            staged_copy(ctx_->h_in[slot] + slot_off(j), src, (size_t)w[j] * nb);
-                            src = ctx_->h_in[slot] + slot_off(j);
-                        }
-                        DLT_CUDA(cudaMemcpyAsync(sp.p[j], src, (size_t)w[j] * nb, cudaMemcpyHostToDevice, s));
-                    }
+                    for (int j = k; j < k + run_of[k]; j++)
+                        DLT_CUDA(cudaMemcpyAsync(sp.p[j], job.in + host_off(j, b0), (size_t)w[j] * nb, cudaMemcpyHostToDevice, s));
                 }
                 DLT_CUDA(launch_untransform(st, sp, slots_.blocks[slot], nb, s));
                 uint8_t* dst = out_pinned ? job.out + b0 * bpb : ctx_->h_out[slot];
@@ -836,7 +717,11 @@ private:
             }
         }
         DLT_CUDA(cudaEventSynchronize(ctx_->done[slot]));
-        for (int i = 0; i < p.ncopy; i++) staged_copy(p.copy[i].dst, p.copy[i].src, p.copy[i].n);
+        {
+            CopyPool::Seg segs[kMaxStreams];
+            for (int i = 0; i < p.ncopy; i++) segs[i] = {p.copy[i].dst, p.copy[i].src, p.copy[i].n};
+            CopyPool::fill().copy_many(segs, p.ncopy);
+        }
         p.ncopy = 0;
         return Status::kOk;
     }
@@ -859,7 +744,11 @@ private:
                     const cudaError_t e = cudaEventSynchronize(ctx_->done[slot]);
                     if (e != cudaSuccess) note_cuda_error(e), st = Status::kCudaError;
                     else
-                        for (int i = 0; i < p.ncopy; i++) CopyPool::drain().copy(p.copy[i].dst, p.copy[i].src, p.copy[i].n);
+                    {
+                        CopyPool::Seg segs[kMaxStreams];
+                        for (int i = 0; i < p.ncopy; i++) segs[i] = {p.copy[i].dst, p.copy[i].src, p.copy[i].n};
+                        CopyPool::drain().copy_many(segs, p.ncopy);
+                    }
                     {
                         std::lock_guard<std::mutex> lk(dm_);
                         p.ncopy = 0, p.queued = false, dhead_++;
