@@ -37,6 +37,16 @@
 #include <mutex>
 #include <vector>
 
+// -DDLT_EST_CHECK=1: every shared-memory address the table machine computes is range-checked and a violation traps (a build
+// for the tests: compute-sanitizer is not available on the GPU pool).  Off in the product build.
+#ifndef DLT_EST_CHECK
+#define DLT_EST_CHECK 0
+#endif
+#define DLT_EST_ASSERT(cond)                 \
+    do {                                     \
+        if (DLT_EST_CHECK && !(cond)) __trap(); \
+    } while (0)
+
 namespace dlt {
 namespace {
 
@@ -215,6 +225,7 @@ __device__ __forceinline__ uint32_t produce_batch(const uint32_t (&wa)[kRows], c
             // screen: which lanes share their scratch slot with another lane?  (scratch_addr is 2 KiB aligned.)  A slot may
             // also be overwritten by a lane of another row of the group: that only adds false alarms.
             slot[i] = scratch_addr | (bucket[i] & (kScratchSlots - 1));
+            DLT_EST_ASSERT((scratch_addr & (kScratchSlots - 1)) == 0 && slot[i] - scratch_addr < (uint32_t)kScratchSlots);
             if (FULL || act[i]) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(slot[i]), "r"(lane) : "memory");
         }
         if (!FULL) __syncwarp();   // (store then load of one converged warp: performed in order)
@@ -294,6 +305,7 @@ __device__ __forceinline__ uint32_t collect_batch(const Pending& pend, const uin
         for (int r = 0; r < kRows; r++)
             if ((untouched >> r) & 1u) {
                 const uint32_t idx = FAST16 ? pend.pkt[r] >> 16 : (pend.pkt[r] & prm.keep_mask) >> prm.sb;
+                DLT_EST_ASSERT(idx * 2u < prm.table_bytes);
                 first_seen[(size_t)idx * 4] = (uint16_t)pend.pkt[r];   // first_seen is already advanced by position & 3
             }
     }
@@ -397,6 +409,10 @@ struct TableWarp {
     uint32_t ring_lane, seen_lane, ready_addr, consumed_addr;   // shared-memory addresses (this lane's 16 bytes of slot 0)
     uint32_t nb;
     unsigned lane;
+    uint32_t table_lo, table_hi, sink_lo;   // DLT_EST_CHECK: what a command may address
+    __device__ __forceinline__ bool valid_target(uint32_t a) const {
+        return (a & 1u) == 0 && ((a >= table_lo && a < table_hi) || (a >= sink_lo && a < sink_lo + kSinkBytes));
+    }
 
     template <int SLOT>
     __device__ __forceinline__ void load_commands(uint4 (&c)[kRows / 2]) const {
@@ -442,13 +458,15 @@ struct TableWarp {
         }
         flag = load_flag<S2>();   // (a stale value of a slot that is never filled is never looked at)
 #pragma unroll
-        for (int k = 0; k < kRows / 2; k++)
+        for (int k = 0; k < kRows / 2; k++) {
+            DLT_EST_ASSERT(valid_target(cur[k].x) && valid_target(cur[k].z));
             asm volatile(
                 "ld.volatile.shared.u16 %0, [%2];\n st.volatile.shared.u16 [%2], %3;\n"
                 "ld.volatile.shared.u16 %1, [%4];\n st.volatile.shared.u16 [%4], %5;"
                 : "=&r"(seen[2 * k]), "=&r"(seen[2 * k + 1])
                 : "r"(cur[k].x), "r"(cur[k].y), "r"(cur[k].z), "r"(cur[k].w)
                 : "memory");
+        }
         if (INNER || t > 0) store_answers<SP>(prev, t - 1);
     }
     template <int SLOT, bool INNER>
@@ -504,6 +522,11 @@ ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restri
     uint8_t* sink = seen + (size_t)kRing * kSeenBytes;
     uint32_t* ready = reinterpret_cast<uint32_t*>(sink + kSinkBytes);
     uint32_t* consumed = ready + kRing;
+    if (DLT_EST_CHECK) {
+        uint32_t dyn_bytes;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+        DLT_EST_ASSERT(smem_u32(consumed) + 4u <= smem_u32(seq_smem) + dyn_bytes);
+    }
 
     const SeqChunk ck = chunks[blockIdx.x];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -527,7 +550,8 @@ ltu_seq_kernel(const SeqChunk* __restrict__ chunks, unsigned long long* __restri
 
     uint32_t count = 0;
     if (warp == 0) {
-        TableWarp{smem_u32(ring) + 16u * lane, smem_u32(seen) + 16u * lane, smem_u32(ready), smem_u32(consumed), nb, lane}.run();
+        TableWarp{smem_u32(ring) + 16u * lane, smem_u32(seen) + 16u * lane, smem_u32(ready), smem_u32(consumed), nb, lane,
+                  smem_u32(table), smem_u32(table) + prm.table_bytes, smem_u32(sink)}.run();
     } else {
         const uint32_t pi = warp - 1;
         count = producer_warp<G, TOP, FAST16>(ck, nb, pi, prm, smem_u32(table), smem_u32(sink), scratch0 + pi * kScratchSlots, ring, seen, ready,
