@@ -84,6 +84,21 @@ DistinctPlan plan_distinct(int format, const Settings* order, int k, int nr) {
     return p;
 }
 
+// A candidate's image is only looked at in its estimated ranges: the colour-endpoint streams (and BC3's alpha-endpoint
+// streams).  The tiled kernels skip a stream whose pointer is null, so the candidates do not write their index streams
+// (half of a BC1 image, ten of BC3's sixteen bytes per block).  Only where the tiled kernels will run: the bytewise
+// fall-back for misaligned pointers writes every stream.
+static StreamPtrs estimated_streams_only(const Settings& st, const uint8_t* in, const StreamPtrs& all, uint64_t nblocks) {
+    bool ragged = false;
+    if (!transform_batch_item_ok(st, TransformBatchItem{in, all, nblocks}, &ragged)) return all;
+    StreamPtrs sp = all;
+    const int ns = num_streams(st.format, st.split_alpha, st.split_colour);
+    sp.p[ns - 1] = nullptr;                                        // the colour indices
+    if (st.format == 2) sp.p[0] = nullptr;                         // BC2: the explicit alpha
+    if (st.format == 3) sp.p[st.split_alpha ? 2 : 1] = nullptr;    // BC3: the alpha indices
+    return sp;
+}
+
 // Transforms the candidates of one device-resident payload that hold a distinct estimated range into scratch images and
 // estimates those ranges (in batches that fit the scratch budget): totals[i] = estimate of candidate i.
 static Status estimate_candidates(Context* ctx, int format, const uint8_t* d_in, size_t len, const Settings* order, int k,
@@ -121,7 +136,7 @@ static Status estimate_candidates(Context* ctx, int format, const uint8_t* d_in,
         for (int c = 0; c < mb; c++) {
             const int cand = plan.images[c0 + c];
             uint8_t* image = ctx->d_scratch + (size_t)c * img;
-            cudaError_t e = launch_transform(order[cand], d_in, reference_layout(image, n, 0, order[cand]), n, stream);
+            cudaError_t e = launch_transform(order[cand], d_in, estimated_streams_only(order[cand], d_in, reference_layout(image, n, 0, order[cand]), n), n, stream);
             if (e != cudaSuccess) {
                 note_cuda_error(e);
                 return Status::kCudaError;
@@ -223,6 +238,7 @@ struct BatchedTransform {
     const uint8_t* in;
     uint8_t* image;   // reference layout for `len` bytes
     size_t len;
+    bool estimate_only = false;   // a candidate: only its estimated streams are needed
 };
 static cudaError_t queue_transforms(const BatchedTransform* work, int n, TransformBatchItem* d_desc, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
@@ -239,6 +255,7 @@ static cudaError_t queue_transforms(const BatchedTransform* work, int n, Transfo
         const size_t nb = w.len / block_bytes(w.st.format);
         if (nb == 0) continue;
         TransformBatchItem item{w.in, reference_layout(w.image, nb, 0, w.st), nb};
+        if (w.estimate_only) item.out = estimated_streams_only(w.st, w.in, item.out, nb);
         bool ragged = false;
         if (!transform_batch_item_ok(w.st, item, &ragged)) {
             e = launch_transform(w.st, w.in, item.out, nb, stream);
@@ -344,7 +361,7 @@ Status auto_ltu_device_batch(Context* ctx, AutoJob* jobs, int njobs, bool use_al
             estimate_ranges(job.format, job.len, ranges);
             cd.image = next_image;
             next_image += (job.len + 255) / 256 * 256;
-            work.push_back(BatchedTransform{order[cd.index], job.d_in, cd.image, job.len});
+            work.push_back(BatchedTransform{order[cd.index], job.d_in, cd.image, job.len, /*estimate_only=*/true});
             for (size_t q = 0; q < js.plan.segs.size(); q++)
                 if (js.plan.segs[q].cand == cd.index) segs[(size_t)js.first_seg + q].d_ptr = cd.image + ranges[js.plan.segs[q].range].offset;
         }

@@ -456,6 +456,7 @@ __device__ __forceinline__ void transform_tile(const uint8_t* __restrict__ in, c
     // aligned address below the segment: the tile owns [lo_valid, hi_valid), has data up to `avail`.
 #pragma unroll
     for (int s = 0; s < L::NS; s++) {
+        if (out.p[s] == nullptr) continue;   // a stream nobody wants (the search only estimates the endpoint streams)
         const int w = L::w(s);
         const int lo_valid = sh[s], hi_valid = sh[s] + w * nb;
         uint8_t* gal = out.p[s] + (uint64_t)w * tile_first - sh[s];  // 128-byte aligned
@@ -491,6 +492,7 @@ __device__ __forceinline__ void transform_tile(const uint8_t* __restrict__ in, c
         if ((first_tile || last_tile) && tid < 32) {
 #pragma unroll
             for (int s = 0; s < L::NS; s++) {
+                if (out.p[s] == nullptr) continue;
                 const int w = L::w(s);
                 const int lo_valid = sh[s], hi_valid = sh[s] + w * nb, avail = sh[s] + w * nbs;
                 uint8_t* gal = out.p[s] + (uint64_t)w * tile_first - sh[s];
