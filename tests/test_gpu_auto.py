@@ -113,12 +113,13 @@ def test_estimator_large_path_adversarial(dlt, torch):
 
 def test_estimator_batch_row_and_ring_boundaries(dlt, torch):
     """Sizes around every boundary of the table machine (csrc/estimator.cu): a row is 32 positions, a batch 256, the ring has
-    16 slots, a chunk starts at 128 batches, a call aims at one chunk per SM; the loop visits len - 7 positions rounded up to
+    20 slots (16 in an earlier version), a chunk starts at 128 batches, a call aims at one chunk per SM; the loop visits len - 7 positions rounded up to
     the group.  Three kinds of data: almost every row contested (two symbols), almost none (random), one bucket (flat);
     several segments per call go through the batched search tests."""
     rng = np.random.default_rng(2026)
     sizes = set()
-    for positions in (1, 4, 31, 32, 33, 255, 256, 257, 511, 512, 513, 15 * 256, 16 * 256, 17 * 256, 32 * 256 + 4, 127 * 256, 128 * 256,
+    for positions in (1, 4, 31, 32, 33, 255, 256, 257, 511, 512, 513, 15 * 256, 16 * 256, 17 * 256, 19 * 256, 20 * 256, 21 * 256, 32 * 256 + 4,
+                      39 * 256, 40 * 256, 41 * 256, 60 * 256, 127 * 256, 128 * 256,
                       128 * 256 + 4, 129 * 256, 2 * 128 * 256, 2 * 128 * 256 + 260, 148 * 128 * 256 - 256, 148 * 128 * 256, 148 * 128 * 256 + 512):
         for delta in (-4, -1, 0, 3):
             if positions + 7 + delta > 7:
