@@ -42,6 +42,7 @@ struct HostPathConfig {
     bool strided;
     size_t split;             // a single-payload call is cut into about this many chunks ...
     size_t min_chunk_bytes;   // ... but not into chunks smaller than this
+    size_t zero_copy_pieces;  // a single mapped-memory payload is launched as up to this many block ranges on different streams
 };
 const HostPathConfig& host_path_config();
 

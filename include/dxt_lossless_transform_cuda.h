@@ -109,7 +109,7 @@ int dltcuda_split_color_endpoints(const uint8_t *colors, uint8_t *colors_out, si
  * payloads (any mix of formats and settings; host pointers, same rules as the with-settings calls)
  * goes through one pipeline per device: chunks of consecutive payloads overlap, one wait at the end.
  * untransform = false: transform_bcN_with_settings on every payload; true: untransform_...
- * Payloads of up to 4 MiB in page-locked memory (dltcuda_alloc_pinned, or anything cudaHostRegister-ed) are not
+ * Payloads of up to 4 MiB (8 MiB for a single-payload call) in page-locked memory (dltcuda_alloc_pinned, or anything cudaHostRegister-ed) are not
  * copied at all: all of them that share a settings combination are processed by ONE kernel launch over the mapped
  * host memory — a directory of thousands of small textures read into a pinned pool moves at ~30 GB/s. */
 typedef struct DltcudaPayload {
