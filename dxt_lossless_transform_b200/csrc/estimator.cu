@@ -776,7 +776,7 @@ static uint8_t* call_staging(size_t bytes) {
         buf.p = nullptr, buf.cap = 0;
         const size_t want = std::max<size_t>(align_up(bytes, 4096), 64u << 10);
         void* q = nullptr;
-        if (cudaHostAlloc(&q, want, cudaHostAllocDefault) != cudaSuccess) {
+        if (cudaHostAlloc(&q, want, cudaHostAllocPortable) != cudaSuccess) {   // one buffer per host thread, whichever device it drives
             (void)cudaGetLastError();
             return nullptr;
         }
