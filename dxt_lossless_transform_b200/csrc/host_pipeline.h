@@ -32,7 +32,11 @@ constexpr size_t kStagedChunkBytes = 16u << 20; // chunk when caller memory is p
 //   DLTCUDA_RAMP       1 (default): a large payload starts and ends with short chunks (1/8, 1/4, 1/2) so the
 //                      un-overlapped first upload / last download are short; 0: equal chunks
 //   DLTCUDA_STRIDED    1 (default): neighbouring streams of equal width travel as one strided (2D) copy; 0: one copy each
-//   DLTCUDA_COPY_THREADS      threads used for staging copies of pageable caller memory
+//   DLTCUDA_COPY_THREADS      threads used for staging copies of pageable caller memory (per pool; default by core count)
+//   DLTCUDA_SPLIT / DLTCUDA_MIN_CHUNK_KIB   a call with ONE payload is cut into about SPLIT chunks (default 6) of at least
+//                      MIN_CHUNK_KIB (default 4096) so that its own upload and download overlap
+//   DLTCUDA_ZEROCOPY_PIECES   a single mapped-memory payload of >= 1 MiB is launched as up to this many block ranges on
+//                      different streams (default 8; 1: one launch), and takes that path up to 8 MiB instead of 4
 struct HostPathConfig {
     size_t chunk_bytes;
     int stages;
