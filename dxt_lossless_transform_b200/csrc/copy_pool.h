@@ -13,6 +13,9 @@
 #if defined(__x86_64__) || defined(_M_X64)
 #include <emmintrin.h>
 #endif
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 namespace dlt {
 
@@ -119,6 +122,16 @@ private:
     CopyPool() {
         // each pool gets a bit under half of the cores: the two run at the same time
         unsigned hw = std::thread::hardware_concurrency();
+#if defined(__linux__)
+        {   // the cores this process may use, shared with the other ranks of a one-process-per-GPU job on the same box
+            cpu_set_t set;
+            if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = std::min<unsigned>(hw, (unsigned)CPU_COUNT(&set));
+            if (const char* v = std::getenv("LOCAL_WORLD_SIZE")) {
+                const long ranks = std::atol(v);
+                if (ranks > 1) hw = std::max(1u, hw / (unsigned)ranks);
+            }
+        }
+#endif
         // (16 cores, threads per pool incl. the caller: 4 / 6 / 8 / 12 -> 22.9 / 24.2 / 28.2 / 19.2 GB/s per direction for a pageable
         // 1 GiB transform: half of the cores each, never more — the workers poll)
         unsigned n = hw >= 16 ? 7 : hw >= 8 ? 3 : hw >= 4 ? 1 : 0;
