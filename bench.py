@@ -618,10 +618,11 @@ def run_gpu_arm(args) -> None:
         cpu_one = cpu_roundtrip(sample, 1, 1, 1)
         memcpy_gbs = host_memcpy_gbs(512 << 20, cores)
         # a pageable call moves every payload byte through host DRAM six times (staging copy in: read + write, DMA read, DMA
-        # write, staging copy out: read + write); an all-core memcpy moves two bytes per byte copied
-        e2e_pageable["host_dram_ceiling_gbs_per_direction"] = memcpy_gbs * 2 / 6
-        e2e_pageable["frac_of_host_dram_ceiling"] = (min(e2e_pageable["transform_gbs_per_direction"], e2e_pageable["untransform_gbs_per_direction"])
-                                                     / (memcpy_gbs * 2 / 6)) if world == 1 else None
+        # write, staging copy out: read + write); an all-core memcpy moves two bytes per byte copied — three if its stores
+        # allocate the destination lines first (numpy / glibc decide by size), hence a range for the ceiling
+        e2e_pageable["host_dram_ceiling_gbs_per_direction"] = [memcpy_gbs * 2 / 6, memcpy_gbs * 3 / 6]
+        e2e_pageable["frac_of_host_dram_ceiling"] = ([min(e2e_pageable["transform_gbs_per_direction"], e2e_pageable["untransform_gbs_per_direction"]) / c
+                                                      for c in (memcpy_gbs * 3 / 6, memcpy_gbs * 2 / 6)] if world == 1 else None)
         out = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
