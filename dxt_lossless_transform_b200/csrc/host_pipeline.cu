@@ -563,7 +563,11 @@ public:
                     DLT_CUDA(cudaMemcpyAsync(ctx_->h_out[slot], slots_.streams[slot], nb * bpb, cudaMemcpyDeviceToHost, s));
                     for (int j = 0; j < ns; j++) pend.copy[pend.ncopy++] = {job.out + host_off(j, b0), ctx_->h_out[slot] + slot_off(j), (size_t)w[j] * nb};
                 }
-                for (int k = 0; k < ns && !(!out_pinned && whole_slot); k += run_of[k]) {
+                // ... and a payload that is exactly one chunk has the same layout in the slot as in the caller's buffer: ONE
+                // copy whatever the number of streams (a BC3 payload of a batch: one download instead of four)
+                const bool whole_payload = out_pinned && whole_slot && nb == n;
+                if (whole_payload) DLT_CUDA(cudaMemcpyAsync(job.out, slots_.streams[slot], nb * bpb, cudaMemcpyDeviceToHost, s));
+                for (int k = 0; k < ns && !(!out_pinned && whole_slot) && !whole_payload; k += run_of[k]) {
                     if (out_pinned && run_of[k] > 1) {   // equal-width neighbours: one strided copy (rows = streams)
                         DLT_CUDA(cudaMemcpy2DAsync(job.out + host_off(k, b0), n * (size_t)w[k], sp.p[k], chunk_blocks * (size_t)w[k],
                                                    (size_t)w[k] * nb, (size_t)run_of[k], cudaMemcpyDeviceToHost, s));
@@ -588,7 +592,9 @@ public:
                             DLT_CUDA(cudaMemcpyAsync(sp.p[j], ctx_->h_in[slot] + slot_off(j), (size_t)w[j] * nb, cudaMemcpyHostToDevice, s));
                     }
                 }
-                for (int k = 0; k < ns && in_pinned; k += run_of[k]) {
+                const bool whole_payload = in_pinned && whole_slot && nb == n;
+                if (whole_payload) DLT_CUDA(cudaMemcpyAsync(slots_.streams[slot], job.in, nb * bpb, cudaMemcpyHostToDevice, s));
+                for (int k = 0; k < ns && in_pinned && !whole_payload; k += run_of[k]) {
                     if (in_pinned && run_of[k] > 1) {
                         DLT_CUDA(cudaMemcpy2DAsync(sp.p[k], chunk_blocks * (size_t)w[k], job.in + host_off(k, b0), n * (size_t)w[k],
                                                    (size_t)w[k] * nb, (size_t)run_of[k], cudaMemcpyHostToDevice, s));
