@@ -111,6 +111,20 @@ def test_estimator_large_path_adversarial(dlt, torch):
             assert dlt.ltu_estimate_device(d.data_ptr() + 3, data.size - 3) == oracle.ltu_estimate(data[3:]), name
 
 
+def test_estimator_is_deterministic_under_repetition(dlt, torch):
+    """The table machine hands batches over through flags in shared memory (no barriers on the hot path): the same stream must
+    give the same count every time, and the oracle's — 40 repetitions per kind, enough chunks to fill every SM."""
+    rng = np.random.default_rng(31)
+    n = 24_000_001
+    kinds = {"texture_like": np.repeat(rng.integers(0, 256, n // 3 + 1, dtype=np.uint8), rng.integers(1, 6, n // 3 + 1))[:n],
+             "random": rng.integers(0, 256, n, dtype=np.uint8), "two": rng.integers(0, 2, n, dtype=np.uint8)}
+    for name, data in kinds.items():
+        d = torch.from_numpy(data).cuda()
+        want = oracle.ltu_estimate(data)
+        got = {dlt.ltu_estimate_device(d.data_ptr(), data.size) for _ in range(40)}
+        assert got == {want}, (name, got, want)
+
+
 def test_estimator_batch_row_and_ring_boundaries(dlt, torch):
     """Sizes around every boundary of the table machine (csrc/estimator.cu): a row is 32 positions, a batch 256, the ring has
     20 slots (16 in an earlier version), a chunk starts at 128 batches, a call aims at one chunk per SM; the loop visits len - 7 positions rounded up to
