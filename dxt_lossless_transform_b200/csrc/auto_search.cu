@@ -133,13 +133,39 @@ static Status estimate_candidates(Context* ctx, int format, const uint8_t* d_in,
         const int mb = nimg - c0 < m ? nimg - c0 : m;
         segs.clear();
         std::vector<int> which;   // index into plan.segs of every segment of this batch
+        // The endpoint streams of all candidates of the batch from ONE read of the blocks (eight candidates per launch)
+        // where that kernel applies: no normalization, 16-byte aligned blocks.  Otherwise one transform per candidate.
+        bool fused = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
+        for (int c = 0; c < mb; c++) fused = fused && order[plan.images[c0 + c]].normalize == kNormNone;
+        if (fused) {
+            EndpointCandidate ec[kMaxEndpointCandidates];
+            int nec = 0;
+            for (int c = 0; c <= mb; c++) {
+                if (nec == kMaxEndpointCandidates || (c == mb && nec)) {
+                    const cudaError_t e = launch_endpoint_candidates(format, d_in, n, ec, nec, stream);
+                    if (e != cudaSuccess) {
+                        note_cuda_error(e);
+                        return Status::kCudaError;
+                    }
+                    nec = 0;
+                }
+                if (c == mb) break;
+                const Settings& st_c = order[plan.images[c0 + c]];
+                uint8_t* image = ctx->d_scratch + (size_t)c * img;
+                // the colour range is the last estimated range of every format; BC3's first one holds the alpha endpoints
+                ec[nec++] = EndpointCandidate{image + ranges[nr - 1].offset, format == 3 ? image + ranges[0].offset : nullptr, st_c.variant,
+                                              st_c.split_colour, st_c.split_alpha};
+            }
+        }
         for (int c = 0; c < mb; c++) {
             const int cand = plan.images[c0 + c];
             uint8_t* image = ctx->d_scratch + (size_t)c * img;
-            cudaError_t e = launch_transform(order[cand], d_in, estimated_streams_only(order[cand], d_in, reference_layout(image, n, 0, order[cand]), n), n, stream);
-            if (e != cudaSuccess) {
-                note_cuda_error(e);
-                return Status::kCudaError;
+            if (!fused) {
+                cudaError_t e = launch_transform(order[cand], d_in, estimated_streams_only(order[cand], d_in, reference_layout(image, n, 0, order[cand]), n), n, stream);
+                if (e != cudaSuccess) {
+                    note_cuda_error(e);
+                    return Status::kCudaError;
+                }
             }
             for (size_t j = 0; j < plan.segs.size(); j++)
                 if (plan.segs[j].cand == cand) {

@@ -1165,6 +1165,162 @@ cudaError_t launch_copy_batch(const CopyBatchItem* d_items, int nitems, uint64_t
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Endpoint streams of several candidates from one read (see bcn_kernels.h)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct EndpointCandidateSet {
+    EndpointCandidate c[kMaxEndpointCandidates];
+    int n;
+    unsigned variant_mask;   // which YCoCg variants occur
+};
+
+// eight elements of `W` bytes each, held in the low bits of v[0..8), to dst (element-aligned); one or two 128-bit stores
+// when dst is 16-byte aligned, element stores otherwise (odd block counts put the second stream of a split pair anywhere)
+template <int W>
+__device__ __forceinline__ void store8(uint8_t* dst, const uint32_t (&v)[8]) {
+    if constexpr (W == 4) {
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            reinterpret_cast<uint4*>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<uint4*>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) reinterpret_cast<uint32_t*>(dst)[j] = v[j];
+        }
+    } else if constexpr (W == 2) {
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(__byte_perm(v[0], v[1], 0x5410), __byte_perm(v[2], v[3], 0x5410),
+                                                        __byte_perm(v[4], v[5], 0x5410), __byte_perm(v[6], v[7], 0x5410));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) reinterpret_cast<uint16_t*>(dst)[j] = (uint16_t)v[j];
+        }
+    } else {
+        if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+            *reinterpret_cast<uint2*>(dst) = make_uint2((v[0] & 0xFF) | (v[1] & 0xFF) << 8 | (v[2] & 0xFF) << 16 | v[3] << 24,
+                                                        (v[4] & 0xFF) | (v[5] & 0xFF) << 8 | (v[6] & 0xFF) << 16 | v[7] << 24);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) dst[j] = (uint8_t)v[j];
+        }
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) endpoint_candidates_kernel(const uint8_t* __restrict__ blocks, const uint64_t nblocks,
+                                                                   const EndpointCandidateSet set) {
+    const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;   // group of eight blocks
+    const uint64_t b0 = g * 8;
+    if (b0 >= nblocks) return;
+    const int valid = nblocks - b0 >= 8 ? 8 : (int)(nblocks - b0);
+    uint32_t cw[8], aw[8];   // colour words (c0 | c1 << 16), BC3 alpha endpoints (a0 | a1 << 8)
+    if constexpr (FMT == 1) {
+        const uint4* p = reinterpret_cast<const uint4*>(blocks) + g * 4;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (2 * j < valid) {
+                if (2 * j + 1 < valid) v = ldg_stream16(p + j);
+                else v.x = __ldg(reinterpret_cast<const uint32_t*>(p + j));   // the last, odd block: 8 bytes exist
+            }
+            cw[2 * j] = v.x, cw[2 * j + 1] = v.z;
+            aw[2 * j] = aw[2 * j + 1] = 0;
+        }
+    } else {
+        const uint4* p = reinterpret_cast<const uint4*>(blocks) + b0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint4 v = j < valid ? ldg_stream16(p + j) : make_uint4(0, 0, 0, 0);
+            cw[j] = v.z, aw[j] = v.x & 0xFFFFu;
+        }
+    }
+#pragma unroll
+    for (int var = 0; var < 4; var++) {
+        if (!(set.variant_mask & (1u << var))) continue;
+        uint32_t d[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            d[j] = var == kNone ? cw[j] : var == kVariant1 ? decorrelate2<kVariant1>(cw[j]) : var == kVariant2 ? decorrelate2<kVariant2>(cw[j])
+                                                                                                          : decorrelate2<kVariant3>(cw[j]);
+#pragma unroll
+        for (int k = 0; k < kMaxEndpointCandidates; k++) {   // (constant indices: the set stays in the parameter space)
+            if (k >= set.n) break;
+            const EndpointCandidate c = set.c[k];
+            if (c.variant != var || c.colour == nullptr) continue;
+            if (valid == 8) {
+                if (!c.split_colour) {
+                    store8<4>(c.colour + 4 * b0, d);
+                } else {
+                    uint32_t hi[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) hi[j] = d[j] >> 16;
+                    store8<2>(c.colour + 2 * b0, d);
+                    store8<2>(c.colour + 2 * nblocks + 2 * b0, hi);
+                }
+            } else {
+                for (int j = 0; j < valid; j++) {
+                    if (!c.split_colour) {
+                        reinterpret_cast<uint32_t*>(c.colour)[b0 + j] = d[j];
+                    } else {
+                        reinterpret_cast<uint16_t*>(c.colour)[b0 + j] = (uint16_t)d[j];
+                        reinterpret_cast<uint16_t*>(c.colour + 2 * nblocks)[b0 + j] = (uint16_t)(d[j] >> 16);
+                    }
+                }
+            }
+        }
+    }
+    if constexpr (FMT == 3) {
+#pragma unroll
+        for (int k = 0; k < kMaxEndpointCandidates; k++) {
+            if (k >= set.n) break;
+            const EndpointCandidate c = set.c[k];
+            if (c.alpha == nullptr) continue;
+            if (valid == 8) {
+                if (!c.split_alpha) {
+                    store8<2>(c.alpha + 2 * b0, aw);
+                } else {
+                    uint32_t hi[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) hi[j] = aw[j] >> 8;
+                    store8<1>(c.alpha + b0, aw);
+                    store8<1>(c.alpha + nblocks + b0, hi);
+                }
+            } else {
+                for (int j = 0; j < valid; j++) {
+                    if (!c.split_alpha) {
+                        reinterpret_cast<uint16_t*>(c.alpha)[b0 + j] = (uint16_t)aw[j];
+                    } else {
+                        c.alpha[b0 + j] = (uint8_t)aw[j];
+                        c.alpha[nblocks + b0 + j] = (uint8_t)(aw[j] >> 8);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_endpoint_candidates(int format, const uint8_t* blocks, uint64_t nblocks, const EndpointCandidate* cands, int count,
+                                       cudaStream_t stream) {
+    if (nblocks == 0 || count <= 0) return cudaSuccess;
+    if (count > kMaxEndpointCandidates || (reinterpret_cast<uintptr_t>(blocks) & 15)) return cudaErrorInvalidValue;
+    EndpointCandidateSet set{};
+    set.n = count;
+    for (int k = 0; k < count; k++) {
+        set.c[k] = cands[k];
+        if (cands[k].colour) set.variant_mask |= 1u << cands[k].variant;
+    }
+    const uint64_t groups = (nblocks + 7) / 8;
+    const unsigned grid = (unsigned)((groups + 255) / 256);
+    if (format == 1) endpoint_candidates_kernel<1><<<grid, 256, 0, stream>>>(blocks, nblocks, set);
+    else if (format == 2) endpoint_candidates_kernel<2><<<grid, 256, 0, stream>>>(blocks, nblocks, set);
+    else endpoint_candidates_kernel<3><<<grid, 256, 0, stream>>>(blocks, nblocks, set);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 uint64_t kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 }  // namespace dlt

@@ -25,6 +25,24 @@ bool transform_batch_item_ok(const Settings& st, const TransformBatchItem& item,
 cudaError_t launch_transform_batch(const Settings& st, const TransformBatchItem* d_items, int nitems, uint64_t max_blocks,
                                    bool ragged, cudaStream_t stream);
 
+// The ENDPOINT streams of up to eight transform candidates of one payload from ONE read of its blocks (the best-settings
+// search only looks at those: transform_auto.rs estimates out[0, len/2) for BC1, out[len/2, +len/4) for BC2, the alpha-
+// endpoint and colour ranges for BC3).  The bytes are exactly what transform_bcN_with_settings writes into those ranges:
+//   colour : start of the colour range of the candidate's image — c0c1 words (4 B per block), or with split_colour the c0
+//            stream followed by the c1 stream at colour + 2 N
+//   alpha  : BC3 only, start of the alpha-endpoint range (nullptr: not wanted) — a0a1 pairs, or with split_alpha the a0
+//            stream followed by the a1 stream at alpha + N
+// `blocks` must be 16-byte aligned; the streams may start anywhere their element size allows.
+struct EndpointCandidate {
+    uint8_t* colour;
+    uint8_t* alpha;
+    int variant;
+    bool split_colour, split_alpha;
+};
+constexpr int kMaxEndpointCandidates = 8;
+cudaError_t launch_endpoint_candidates(int format, const uint8_t* blocks, uint64_t nblocks, const EndpointCandidate* cands, int count,
+                                       cudaStream_t stream);
+
 // ... and the inverse: item.in = the payload's streams, item.out = its blocks (16-byte aligned).
 struct UntransformBatchItem {
     StreamPtrs in;
